@@ -1,0 +1,116 @@
+"""Run the UNMODIFIED reference DCNv3 source over the torch-backed TF shim (authoring container only).
+
+TEST INFRASTRUCTURE ONLY -- used by tests/golden/make_golden.py to freeze golden vectors and by
+tests marked `needs_reference`.  It executes, by file path, the reference's own
+
+    /root/reference/layers/dcn_v3/utils.py   (get_reference_points :14, generate_dilation_grids :65,
+                                              dcnv3_bilinear_sampler :110)
+    /root/reference/layers/dcn_v3/op.py      (dcnv3_op :16)
+    /root/reference/layers/dcn_v3/dcn_v3.py  (DeformableConvolutionV3 :16)
+
+with `import tensorflow` resolving to oracle/tf_shim/tensorflow (torch CPU tensors) and with the two
+`iseg.utils` helpers those files import replaced by local stand-ins (the real `iseg/utils/__init__`
+pulls in keras, distutils and the whole library).  No reference source is copied: the files are
+loaded from where they lie.  /root/reference does not exist on the GPU box; callers must check
+`available()`.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("ISEG_REFERENCE_ROOT", "/root/reference")
+_SHIM_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tf_shim")
+
+_loaded = None
+
+
+def available():
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "layers", "dcn_v3", "op.py"))
+
+
+def _load_file(modname, path):
+    spec = importlib.util.spec_from_file_location(modname, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[modname] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load():
+    """Returns a namespace with the reference's dcnv3_op, sampler helpers and layer class."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not available():
+        raise RuntimeError(f"reference not present at {REFERENCE_ROOT}")
+    if "tensorflow" in sys.modules and not getattr(
+        sys.modules["tensorflow"], "__version__", ""
+    ).endswith("torchshim"):
+        raise RuntimeError("a real tensorflow is already imported; use it directly instead")
+    if _SHIM_DIR not in sys.path:
+        sys.path.insert(0, _SHIM_DIR)
+    import tensorflow as tf  # the shim
+
+    # Stand-ins for iseg.utils.get_tensor_shape (utils/common.py:67: static shape, dynamic fallback;
+    # shapes are always static here) and iseg.utils.keras3_utils.Keras3_Model_Wrapper
+    # (utils/keras3_utils.py:23: keras.Model that rewrites '/' in the name).
+    def get_tensor_shape(x, return_list=False):
+        shp = [int(s) for s in x.shape]
+        return shp if return_list else tuple(shp)
+
+    class Keras3_Model_Wrapper(tf.keras.Model):
+        def __init__(self, *args, name=None, **kwargs):
+            super().__init__(*args, name=None if name is None else name.replace("/", "."), **kwargs)
+
+    def pkg(name, path=None):
+        m = types.ModuleType(name)
+        m.__path__ = [path] if path else []
+        sys.modules[name] = m
+        return m
+
+    for name in list(sys.modules):
+        if name == "iseg" or name.startswith("iseg."):
+            del sys.modules[name]
+    pkg("iseg")
+    u = pkg("iseg.utils")
+    u.get_tensor_shape = get_tensor_shape
+    k3 = types.ModuleType("iseg.utils.keras3_utils")
+    k3.Keras3_Model_Wrapper = Keras3_Model_Wrapper
+    sys.modules["iseg.utils.keras3_utils"] = k3
+    pkg("iseg.layers")
+    d = os.path.join(REFERENCE_ROOT, "layers", "dcn_v3")
+    pkg("iseg.layers.dcn_v3", d)
+    utils = _load_file("iseg.layers.dcn_v3.utils", os.path.join(d, "utils.py"))
+    op = _load_file("iseg.layers.dcn_v3.op", os.path.join(d, "op.py"))
+    layer = _load_file("iseg.layers.dcn_v3.dcn_v3", os.path.join(d, "dcn_v3.py"))
+    _loaded = types.SimpleNamespace(
+        tf=tf,
+        dcnv3_op=op.dcnv3_op,
+        get_reference_points=utils.get_reference_points,
+        generate_dilation_grids=utils.generate_dilation_grids,
+        dcnv3_bilinear_sampler=utils.dcnv3_bilinear_sampler,
+        DeformableConvolutionV3=layer.DeformableConvolutionV3,
+    )
+    return _loaded
+
+
+def run_op(x, offset, mask, kernel_size=(3, 3), strides=(1, 1), padding="SAME",
+           dilation_rate=(1, 1), groups=4, group_channels=16, offset_scale=1.0, grad_out=None):
+    """Runs the reference dcnv3_op on numpy inputs.  Returns out, or (out, gx, goff, gmask) when
+    grad_out is given (gradients by torch autograd through the reference's own forward graph,
+    standing in for TF autodiff: floor / int casts / clip cut the graph in both)."""
+    import numpy as np
+    import torch
+
+    ref = load()
+    tx, to, tm = (ref.tf.convert_to_tensor(torch.from_numpy(np.ascontiguousarray(a)))
+                  for a in (x, offset, mask))
+    if grad_out is not None:
+        tx.requires_grad_(True), to.requires_grad_(True), tm.requires_grad_(True)
+    out = ref.dcnv3_op(tx, to, tm, list(kernel_size), list(strides), padding, list(dilation_rate),
+                       groups, group_channels, offset_scale)
+    if grad_out is None:
+        return out.detach().numpy()
+    out.backward(torch.from_numpy(np.ascontiguousarray(grad_out)))
+    return (out.detach().numpy(), tx.grad.numpy(), to.grad.numpy(), tm.grad.numpy())

@@ -1,0 +1,112 @@
+"""The oracle against the golden vectors (outputs of the reference's own source, see
+tests/golden/make_golden.py), and the three restatements against each other.  CPU only."""
+import numpy as np
+import pytest
+
+from helpers import golden_op_cases, load_op_case, make_inputs, rel_err, GOLDEN
+from oracle import c_oracle, dcnv3_oracle as O, ref_runner
+
+TOL = {np.dtype("float32"): 2e-6, np.dtype("float64"): 1e-14}
+
+
+@pytest.mark.parametrize("name", golden_op_cases())
+def test_numpy_oracle_matches_golden(name):
+    z, kw = load_op_case(name)
+    x, off, m, go = z["x"], z["offset"], z["mask"], z["grad_out"]
+    tol = TOL[x.dtype]
+    # forward: same float operation order as the reference => bit-exact
+    assert np.array_equal(O.forward_literal(x, off, m, **kw), z["out"])
+    assert np.array_equal(O.forward(x, off, m, **kw), z["out"])
+    gx, goff, gm = O.backward(x, off, m, go, **kw)
+    assert rel_err(gx, z["grad_x"]) < tol
+    assert rel_err(goff, z["grad_offset"]) < tol
+    assert rel_err(gm, z["grad_mask"]) < tol
+
+
+@pytest.mark.parametrize("name", [n for n in golden_op_cases() if not n.endswith("f64")])
+def test_c_oracle_matches_golden(name):
+    z, kw = load_op_case(name)
+    x, off, m, go = z["x"], z["offset"], z["mask"], z["grad_out"]
+    assert np.array_equal(c_oracle.forward(x, off, m, **kw), z["out"])
+    gx, goff, gm = c_oracle.backward(x, off, m, go, **kw)
+    assert rel_err(gx, z["grad_x"]) < 2e-6
+    assert rel_err(goff, z["grad_offset"]) < 2e-6
+    assert rel_err(gm, z["grad_mask"]) < 2e-6
+
+
+def test_known_answers():
+    z = np.load(f"{GOLDEN}/kat_ramp.npz")
+    kw = dict(groups=2, group_channels=1)
+    out = O.forward(z["x"], z["offset"], z["mask"], **kw)
+    # transposed sampling + (W_in-2) pixel mapping: out[h,w] = 10*(yq-1)+(xq-1), xq=(h+1.5)*6/8
+    assert abs(out[0, 1, 4, 0] - 32.125) < 1e-5
+    assert abs(out[0, 0, 0, 0] - 1.375) < 1e-5
+    assert abs(out[0, 5, 5, 0] - 42.625) < 1e-5
+    assert np.array_equal(out, z["out"])
+    assert np.array_equal(O.forward(z["x"], z["offset_shift"], z["mask"], **kw), z["out_shift"])
+    # a shift of W_in/(W_in-2) in offset channel 0 = one column to the right on the ramp (+1)
+    inner = z["out_shift"][0, :4, :, 0] - z["out"][0, :4, :, 0]
+    assert np.allclose(inner, 1.0, atol=1e-4)
+    dead = O.forward(z["x"], z["offset_dead"], z["mask"], **kw)
+    assert np.all(dead == 0) and np.all(z["out_dead"] == 0)
+    gx, goff, gm = O.backward(z["x"], z["offset_dead"], z["mask"], np.ones_like(out), **kw)
+    assert not gx.any() and not goff.any() and not gm.any()
+    zc = np.load(f"{GOLDEN}/kat_const.npz")
+    oc = O.forward(zc["x"], zc["offset"], zc["mask"], groups=1, group_channels=16)
+    assert np.array_equal(oc, zc["out"])
+    assert np.allclose(oc[0, 2:6, 2:6], 2.5, atol=1e-5)  # interior: all 36 corners inside the image
+
+
+def test_error_conventions():
+    x, off, m, _ = make_inputs(1, 4, 4, 1, 4)
+    with pytest.raises(TypeError):
+        O.forward(x, off, m, padding=1, groups=1, group_channels=4)
+    with pytest.raises(ValueError):
+        O.forward(x, off, m, padding="full", groups=1, group_channels=4)
+    with pytest.raises(ValueError):
+        O.forward(x, off[:, :3], m, groups=1, group_channels=4)
+
+
+def test_c_oracle_thread_count_independent():
+    x, off, m, go = make_inputs(3, 20, 24, 4, 16, sigma=3.0, seed=5)
+    a = c_oracle.backward(x, off, m, go, nthreads=1)
+    b = c_oracle.backward(x, off, m, go, nthreads=8)
+    assert all(np.array_equal(p, q) for p, q in zip(a, b))
+    assert np.array_equal(c_oracle.forward(x, off, m, nthreads=1), c_oracle.forward(x, off, m, nthreads=5))
+
+
+def test_c_vs_numpy_medium():
+    x, off, m, go = make_inputs(2, 33, 29, 8, 16, sigma=2.0, seed=9)
+    kw = dict(groups=8, group_channels=16, offset_scale=1.3)
+    assert np.array_equal(c_oracle.forward(x, off, m, **kw), O.forward(x, off, m, **kw))
+    for a, b in zip(c_oracle.backward(x, off, m, go, **kw), O.backward(x, off, m, go, **kw)):
+        assert rel_err(a, b) < 2e-6
+
+
+def test_softmax_matches_layer_semantics():
+    rng = np.random.default_rng(0)
+    z = rng.standard_normal((2, 3, 3, 4 * 9)).astype(np.float32)
+    s = O.mask_softmax(z, 4).reshape(2, 3, 3, 4, 9)
+    assert np.allclose(s.sum(-1), 1, atol=1e-6)
+
+
+@pytest.mark.needs_reference
+def test_golden_is_reproducible_from_reference():
+    """Re-runs the reference source for two fixtures and checks the files on disk are what it gives."""
+    for name in ("rand_5x7_g2c3_s1.7", "valid_11x13_g2c4"):
+        z, kw = load_op_case(name)
+        out, gx, goff, gm = ref_runner.run_op(z["x"], z["offset"], z["mask"], grad_out=z["grad_out"], **kw)
+        assert np.array_equal(out, z["out"]) and np.array_equal(gx, z["grad_x"])
+        assert np.array_equal(goff, z["grad_offset"]) and np.array_equal(gm, z["grad_mask"])
+
+
+@pytest.mark.needs_reference
+def test_reference_rejects_bad_padding():
+    ref = ref_runner.load()
+    x, off, m, _ = make_inputs(1, 4, 4, 1, 4)
+    import torch
+    tx, to, tm = (torch.from_numpy(a) for a in (x, off, m))
+    with pytest.raises(TypeError):
+        ref.dcnv3_op(tx, to, tm, [3, 3], [1, 1], 1, [1, 1], 1, 4, 1.0)
+    with pytest.raises(ValueError):
+        ref.dcnv3_op(tx, to, tm, [3, 3], [1, 1], "full", [1, 1], 1, 4, 1.0)
