@@ -1,0 +1,123 @@
+/*
+ * dcnv3_b200 -- C ABI of the B200-native DCNv3 core operator (forward + backward).
+ *
+ * Drop-in boundary for edwardyehuang/iSeg's
+ *     layers/dcn_v3/op.py:16   dcnv3_op(x, offset, mask, kernel_size, strides, padding,
+ *                                       dilation_rate, groups, group_channels, offset_scale)
+ * (its only caller: layers/dcn_v3/dcn_v3.py:125) and for the gradient TF autodiff derives from that
+ * function (no source).  Tensor layouts are the reference's (op.py:89-107):
+ *     x          [N, H,  W,  G*gc]                      NHWC, dense, row-major
+ *     offset     [N, Ho, Wo, G*P*2]   element (g*P+p)*2+{0,1}; channel 0 is the "x"/W_in coordinate
+ *     mask       [N, Ho, Wo, G*P]     already soft-maxed over P by the layer (dcn_v3.py:120-123),
+ *                                     or raw logits when DCNV3_FLAG_MASK_LOGITS is set
+ *     out        [N, Ho, Wo, G*gc]
+ * P = kh*kw, tap p = i*kh + j with i the W-direction displacement (utils.py:77-101).
+ * "SAME"/"VALID" (op.py:29-39) are resolved to pad_h/pad_w by the host wrapper.
+ *
+ * Conventions: every entry point returns 0 or a negative dcnv3_status; nothing throws across the
+ * ABI; dcnv3_last_error() gives a thread-local message for the last failure on the calling thread.
+ * No user-visible memory is allocated: outputs and the backward workspace are caller-owned device
+ * buffers.  All work is enqueued on the caller's CUDA stream (cudaStream_t passed as void*); the
+ * calls are asynchronous except the *_host variants.  The library is re-entrant.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * DCNV3_ERR_CUDA.
+ */
+#ifndef DCNV3_B200_H_
+#define DCNV3_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "dcnv3_dlpack.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCNV3_ABI_VERSION 1
+
+typedef enum {
+    DCNV3_OK = 0,
+    DCNV3_ERR_DTYPE = -1,      /* unsupported / mismatching element type */
+    DCNV3_ERR_SHAPE = -2,      /* shapes inconsistent with the parameters (op.py:83 reshape) */
+    DCNV3_ERR_LAYOUT = -3,     /* not dense row-major, or misaligned */
+    DCNV3_ERR_DEVICE = -4,     /* not CUDA memory / tensors on different devices */
+    DCNV3_ERR_CUDA = -5,       /* CUDA runtime error (no device, launch failure, ...) */
+    DCNV3_ERR_WORKSPACE = -6,  /* backward workspace missing or too small */
+    DCNV3_ERR_ARGUMENT = -7    /* NULL pointer, non-positive size, unsupported parameter */
+} dcnv3_status;
+
+typedef enum { DCNV3_F32 = 0, DCNV3_BF16 = 1 } dcnv3_dtype;
+
+/* mask argument holds pre-softmax logits; softmax over P is fused (dcn_v3.py:120-123) and
+   grad_mask is the gradient w.r.t. the logits */
+#define DCNV3_FLAG_MASK_LOGITS 1u
+
+typedef struct dcnv3_params {
+    int32_t n, h, w;                 /* x is [n, h, w, groups*group_channels] */
+    int32_t ho, wo;                  /* spatial size of offset / mask / out (op.py:51) */
+    int32_t groups, group_channels;
+    int32_t kh, kw;                  /* kernel_size  */
+    int32_t sh, sw;                  /* strides      */
+    int32_t ph, pw;                  /* zero padding added on each side (op.py:34-37,46) */
+    int32_t dh, dw;                  /* dilation_rate */
+    float offset_scale;
+    int32_t dtype;                   /* dcnv3_dtype of all seven tensors */
+    uint32_t flags;
+} dcnv3_params;
+
+int dcnv3_abi_version(void);
+const char* dcnv3_last_error(void);
+/* e.g. "dcnv3_b200 abi 1, sm_100a, nvcc 12.9" */
+const char* dcnv3_build_info(void);
+
+/* Validates a parameter block the way the reference's reshapes would. */
+int dcnv3_check_params(const dcnv3_params* p);
+
+/* ---- device-pointer entry points (replace op.py:16 and its autodiff gradient) ---- */
+int dcnv3_forward(const void* x, const void* offset, const void* mask, void* out,
+                  const dcnv3_params* p, void* cuda_stream);
+
+size_t dcnv3_backward_workspace_bytes(const dcnv3_params* p);
+
+/* grad_x / grad_offset / grad_mask are fully overwritten.  Bitwise reproducible run to run. */
+int dcnv3_backward(const void* x, const void* offset, const void* mask, const void* grad_out,
+                   void* grad_x, void* grad_offset, void* grad_mask, void* workspace,
+                   size_t workspace_bytes, const dcnv3_params* p, void* cuda_stream);
+
+/* ---- DLPack entry points: same calls, tensors described by DLManagedTensor (zero copy);
+        shapes, dtype, device and contiguity are taken from / checked against the tensors ---- */
+int dcnv3_forward_dlpack(const DLManagedTensor* x, const DLManagedTensor* offset,
+                         const DLManagedTensor* mask, DLManagedTensor* out, int kh, int kw, int sh,
+                         int sw, int pad_h, int pad_w, int dh, int dw, int groups,
+                         int group_channels, float offset_scale, unsigned flags, void* cuda_stream);
+
+int dcnv3_backward_dlpack(const DLManagedTensor* x, const DLManagedTensor* offset,
+                          const DLManagedTensor* mask, const DLManagedTensor* grad_out,
+                          DLManagedTensor* grad_x, DLManagedTensor* grad_offset,
+                          DLManagedTensor* grad_mask, DLManagedTensor* workspace, int kh, int kw,
+                          int sh, int sw, int pad_h, int pad_w, int dh, int dw, int groups,
+                          int group_channels, float offset_scale, unsigned flags,
+                          void* cuda_stream);
+
+/* ---- host-buffer entry points: what a CPU-tensor caller (e.g. the reference's TF CPU path) binds.
+        Copies host -> device, runs, copies results back and synchronises.  Device scratch is cached
+        per device inside the library.  Pinned host memory makes the copies asynchronous. ---- */
+int dcnv3_forward_host(const void* x, const void* offset, const void* mask, void* out,
+                       const dcnv3_params* p, int device);
+
+int dcnv3_forward_backward_host(const void* x, const void* offset, const void* mask,
+                                const void* grad_out, void* out, void* grad_x, void* grad_offset,
+                                void* grad_mask, const dcnv3_params* p, int device);
+
+/* Releases the per-device scratch used by the *_host entry points. */
+int dcnv3_release_host_scratch(void);
+
+/* Number of kernels this library has launched on behalf of the calling process (monotonic). */
+uint64_t dcnv3_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCNV3_B200_H_ */

@@ -1,0 +1,134 @@
+"""ctypes binding of the C ABI in include/dcnv3_b200.h (the thin shim of BASELINE north_star).
+
+Tensors cross the boundary as DLPack `DLManagedTensor*` taken zero-copy from torch tensors; the
+library validates dtype / shape / device / contiguity itself.  There is no CPU fallback: if the
+shared library is missing, importing this module raises.
+"""
+import ctypes
+import os
+
+import torch
+from torch.utils.dlpack import to_dlpack
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libdcnv3_b200.so")
+
+F32, BF16 = 0, 1
+FLAG_MASK_LOGITS = 1
+
+ERR_DTYPE, ERR_SHAPE, ERR_LAYOUT, ERR_DEVICE, ERR_CUDA, ERR_WORKSPACE, ERR_ARGUMENT = range(-1, -8, -1)
+
+
+class Params(ctypes.Structure):
+    """struct dcnv3_params"""
+    _fields_ = [(k, ctypes.c_int32) for k in
+                ("n", "h", "w", "ho", "wo", "groups", "group_channels", "kh", "kw", "sh", "sw", "ph",
+                 "pw", "dh", "dw")] + [("offset_scale", ctypes.c_float), ("dtype", ctypes.c_int32),
+                                       ("flags", ctypes.c_uint32)]
+
+
+class DCNv3Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"dcnv3_b200 error {code}: {message}")
+        self.code = code
+
+
+def _load():
+    if not os.path.isfile(_LIB_PATH):
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `python -m iseg_b200.build` "
+            "(there is no CPU / PyTorch fallback for the DCNv3 op)")
+    lib = ctypes.CDLL(_LIB_PATH)
+    vp, ci, cf, cu = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_uint
+    pp = ctypes.POINTER(Params)
+    lib.dcnv3_abi_version.restype = ci
+    lib.dcnv3_last_error.restype = ctypes.c_char_p
+    lib.dcnv3_build_info.restype = ctypes.c_char_p
+    lib.dcnv3_check_params.argtypes = [pp]
+    lib.dcnv3_forward.argtypes = [vp] * 4 + [pp, vp]
+    lib.dcnv3_backward_workspace_bytes.argtypes = [pp]
+    lib.dcnv3_backward_workspace_bytes.restype = ctypes.c_size_t
+    lib.dcnv3_backward.argtypes = [vp] * 8 + [ctypes.c_size_t, pp, vp]
+    scal = [ci] * 10 + [cf, cu, vp]
+    lib.dcnv3_forward_dlpack.argtypes = [vp] * 4 + scal
+    lib.dcnv3_backward_dlpack.argtypes = [vp] * 8 + scal
+    lib.dcnv3_forward_host.argtypes = [vp] * 4 + [pp, ci]
+    lib.dcnv3_forward_backward_host.argtypes = [vp] * 8 + [pp, ci]
+    lib.dcnv3_kernel_launch_count.restype = ctypes.c_uint64
+    if lib.dcnv3_abi_version() != 1:
+        raise ImportError("libdcnv3_b200.so ABI version mismatch")
+    return lib
+
+
+lib = _load()
+
+_capsule_ptr = ctypes.pythonapi.PyCapsule_GetPointer
+_capsule_ptr.restype = ctypes.c_void_p
+_capsule_ptr.argtypes = [ctypes.py_object, ctypes.c_char_p]
+
+
+def _dl(t):
+    """(capsule, DLManagedTensor*) -- the capsule keeps the export alive for the call."""
+    cap = to_dlpack(t)
+    return cap, _capsule_ptr(cap, b"dltensor")
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib.dcnv3_last_error().decode()
+        if rc == ERR_SHAPE:
+            raise ValueError(f"dcnv3_b200: {msg}")
+        if rc == ERR_DTYPE:
+            raise TypeError(f"dcnv3_b200: {msg}")
+        raise DCNv3Error(rc, msg)
+
+
+def launch_count():
+    return int(lib.dcnv3_kernel_launch_count())
+
+
+def make_params(x_shape, out_hw, kernel_size, strides, pad, dilation_rate, groups, group_channels,
+                offset_scale, dtype, flags=0):
+    n, h, w, _ = x_shape
+    return Params(n, h, w, out_hw[0], out_hw[1], groups, group_channels, kernel_size[0],
+                  kernel_size[1], strides[0], strides[1], pad[0], pad[1], dilation_rate[0],
+                  dilation_rate[1], float(offset_scale), dtype, flags)
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def forward(x, offset, mask, kernel_size, strides, pad, dilation_rate, groups, group_channels,
+            offset_scale, flags=0):
+    """dcnv3_forward_dlpack on torch CUDA tensors; returns a fresh output tensor."""
+    if not (x.is_cuda and offset.is_cuda and mask.is_cuda):
+        raise DCNv3Error(ERR_DEVICE, "dcnv3_op needs CUDA tensors (no CPU fallback)")
+    out = torch.empty((x.shape[0], offset.shape[1], offset.shape[2], groups * group_channels),
+                      dtype=x.dtype, device=x.device)
+    caps = [_dl(t) for t in (x, offset, mask, out)]
+    with torch.cuda.device(x.device):
+        rc = lib.dcnv3_forward_dlpack(
+            *[c[1] for c in caps], kernel_size[0], kernel_size[1], strides[0], strides[1], pad[0],
+            pad[1], dilation_rate[0], dilation_rate[1], groups, group_channels, float(offset_scale),
+            flags, _stream(x))
+    check(rc)
+    return out
+
+
+def backward(x, offset, mask, grad_out, kernel_size, strides, pad, dilation_rate, groups,
+             group_channels, offset_scale, flags=0):
+    """dcnv3_backward_dlpack; returns (grad_x, grad_offset, grad_mask)."""
+    gx, goff, gm = torch.empty_like(x), torch.empty_like(offset), torch.empty_like(mask)
+    dt = F32 if x.dtype == torch.float32 else BF16
+    p = make_params(x.shape, offset.shape[1:3], kernel_size, strides, pad, dilation_rate, groups,
+                    group_channels, offset_scale, dt, flags)
+    ws_bytes = int(lib.dcnv3_backward_workspace_bytes(ctypes.byref(p)))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=x.device)
+    caps = [_dl(t) for t in (x, offset, mask, grad_out, gx, goff, gm, ws)]
+    with torch.cuda.device(x.device):
+        rc = lib.dcnv3_backward_dlpack(
+            *[c[1] for c in caps], kernel_size[0], kernel_size[1], strides[0], strides[1], pad[0],
+            pad[1], dilation_rate[0], dilation_rate[1], groups, group_channels, float(offset_scale),
+            flags, _stream(x))
+    check(rc)
+    return gx, goff, gm

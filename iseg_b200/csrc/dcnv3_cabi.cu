@@ -1,0 +1,414 @@
+// C ABI of dcnv3_b200 (include/dcnv3_b200.h): validation, parameter derivation, dispatch, DLPack and
+// host-buffer front ends.  No kernels here.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "dcnv3_kernels.h"
+
+namespace dcnv3 {
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static thread_local char t_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int cuda_fail(cudaError_t e, const char* what) {
+    return fail(DCNV3_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+static size_t elem_size(int dtype) { return dtype == DCNV3_F32 ? 4 : 2; }
+
+// The envelope the reference enforces through tf.reshape (op.py:83 with utils.py:26-27): the
+// reference-point grid must have the offset's spatial size.
+static int check(const dcnv3_params* p) {
+    if (p == nullptr) return fail(DCNV3_ERR_ARGUMENT, "params is NULL");
+    if (p->dtype != DCNV3_F32 && p->dtype != DCNV3_BF16)
+        return fail(DCNV3_ERR_DTYPE, "dtype %d not supported (0=f32, 1=bf16)", p->dtype);
+    if (p->n < 0 || p->h <= 0 || p->w <= 0 || p->groups <= 0 || p->group_channels <= 0)
+        return fail(DCNV3_ERR_SHAPE, "non-positive tensor dimension");
+    if (p->kh <= 0 || p->kw <= 0 || p->kh * p->kw > DCNV3_MAX_TAPS)
+        return fail(DCNV3_ERR_ARGUMENT, "kernel_size %dx%d unsupported (kh*kw <= %d)", p->kh, p->kw,
+                    DCNV3_MAX_TAPS);
+    if (p->sh <= 0 || p->sw <= 0 || p->dh <= 0 || p->dw <= 0 || p->ph < 0 || p->pw < 0)
+        return fail(DCNV3_ERR_ARGUMENT, "strides/dilation must be positive, padding non-negative");
+    const long hin = (long)p->h + 2 * p->ph, win = (long)p->w + 2 * p->pw;
+    const long eh = hin - ((long)p->dh * (p->kh - 1) + 1), ew = win - ((long)p->dw * (p->kw - 1) + 1);
+    if (eh < 0 || ew < 0) return fail(DCNV3_ERR_SHAPE, "kernel extent exceeds the padded input");
+    const long ho = eh / p->sh + 1, wo = ew / p->sw + 1;
+    if (ho != p->ho || wo != p->wo)
+        return fail(DCNV3_ERR_SHAPE,
+                    "offset/mask spatial size %dx%d does not match the reference-point grid %ldx%ld "
+                    "(op.py:83 reshape)", p->ho, p->wo, ho, wo);
+    const double elems = (double)p->n * hin * win * p->groups * p->group_channels;
+    const double offs = (double)p->n * p->ho * p->wo * p->groups * p->kh * p->kw * 2;
+    if (elems > 2.0e18 || offs > 2.0e18) return fail(DCNV3_ERR_SHAPE, "tensor too large");
+    return DCNV3_OK;
+}
+
+static KParams derive(const dcnv3_params* p) {
+    KParams q;
+    memset(&q, 0, sizeof(q));
+    q.n = p->n; q.h = p->h; q.w = p->w; q.ho = p->ho; q.wo = p->wo;
+    q.G = p->groups; q.gc = p->group_channels; q.P = p->kh * p->kw; q.kh = p->kh;
+    q.sh = p->sh; q.sw = p->sw; q.ph = p->ph; q.pw = p->pw;
+    q.hin = p->h + 2 * p->ph; q.win = p->w + 2 * p->pw;
+    q.hin_f = (float)q.hin; q.win_f = (float)q.win;
+    q.hm2_f = (float)(q.hin - 2); q.wm2_f = (float)(q.win - 2);
+    q.y0c = (float)((p->dh * (p->kh - 1)) / 2 + 0.5f);
+    q.x0c = (float)((p->dw * (p->kw - 1)) / 2 + 0.5f);
+    q.scale = p->offset_scale;
+    // volatile: keep each operation a separately rounded fp32 operation on the host as well
+    volatile float fx = q.wm2_f * q.scale; fx = fx / q.win_f;
+    volatile float fy = q.hm2_f * q.scale; fy = fy / q.hin_f;
+    q.fx = fx; q.fy = fy;
+    q.flags = p->flags;
+    for (int t = 0; t < q.P; ++t) {
+        const int i = t / p->kh, j = t % p->kh;  // utils.py:77-101
+        volatile float g0 = (float)(-((p->dw * (p->kw - 1)) / 2) + i * p->dw) / q.win_f;
+        volatile float g1 = (float)(-((p->dh * (p->kh - 1)) / 2) + j * p->dh) / q.hin_f;
+        volatile float a = g0 * q.scale, b = g1 * q.scale;
+        q.gs0[t] = a; q.gs1[t] = b;
+    }
+    return q;
+}
+
+static int check_ptr_align(const void* ptr, const char* name, size_t align = 16) {
+    if (ptr == nullptr) return fail(DCNV3_ERR_ARGUMENT, "%s is NULL", name);
+    if (((uintptr_t)ptr) % align != 0) return fail(DCNV3_ERR_LAYOUT, "%s is not %zu-byte aligned", name, align);
+    return 0;
+}
+
+static int forward_impl(const void* x, const void* offset, const void* mask, void* out,
+                        const dcnv3_params* p, cudaStream_t st) {
+    int rc = check(p);
+    if (rc) return rc;
+    if ((rc = check_ptr_align(x, "x")) || (rc = check_ptr_align(offset, "offset")) ||
+        (rc = check_ptr_align(mask, "mask")) || (rc = check_ptr_align(out, "out")))
+        return rc;
+    if (p->n == 0) return DCNV3_OK;
+    const KParams q = derive(p);
+    cudaError_t e = launch_fwd_generic(x, offset, mask, out, q, p->dtype, st);
+    if (e != cudaSuccess) return cuda_fail(e, "dcnv3_forward launch");
+    return DCNV3_OK;
+}
+
+static size_t backward_ws_bytes(const dcnv3_params* p) {
+    const KParams q = derive(p);
+    return bwd_generic_workspace_bytes(q);
+}
+
+static int backward_impl(const void* x, const void* offset, const void* mask, const void* grad_out,
+                         void* grad_x, void* grad_offset, void* grad_mask, void* ws, size_t ws_bytes,
+                         const dcnv3_params* p, cudaStream_t st) {
+    int rc = check(p);
+    if (rc) return rc;
+    if ((rc = check_ptr_align(x, "x")) || (rc = check_ptr_align(offset, "offset")) ||
+        (rc = check_ptr_align(mask, "mask")) || (rc = check_ptr_align(grad_out, "grad_out")) ||
+        (rc = check_ptr_align(grad_x, "grad_x")) || (rc = check_ptr_align(grad_offset, "grad_offset")) ||
+        (rc = check_ptr_align(grad_mask, "grad_mask")))
+        return rc;
+    if (p->n == 0) return DCNV3_OK;
+    const size_t need = backward_ws_bytes(p);
+    if (ws == nullptr || ws_bytes < need)
+        return fail(DCNV3_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", need, ws_bytes);
+    if ((rc = check_ptr_align(ws, "workspace", 256))) return rc;
+    const KParams q = derive(p);
+    cudaError_t e = launch_bwd_generic(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q,
+                                       p->dtype, st);
+    if (e != cudaSuccess) return cuda_fail(e, "dcnv3_backward launch");
+    return DCNV3_OK;
+}
+
+// ---- DLPack helpers ------------------------------------------------------------------------------
+static int dl_dtype(const DLTensor& t, int* dtype, const char* name) {
+    if (t.dtype.lanes != 1) return fail(DCNV3_ERR_DTYPE, "%s: vector lanes unsupported", name);
+    if (t.dtype.code == kDLFloat && t.dtype.bits == 32) { *dtype = DCNV3_F32; return 0; }
+    if (t.dtype.code == kDLBfloat && t.dtype.bits == 16) { *dtype = DCNV3_BF16; return 0; }
+    return fail(DCNV3_ERR_DTYPE, "%s: dtype code %d bits %d unsupported (float32 / bfloat16)", name,
+                (int)t.dtype.code, (int)t.dtype.bits);
+}
+
+static int dl_check(const DLManagedTensor* m, const char* name, int ndim, int device_id, int dtype,
+                    void** data) {
+    if (m == nullptr) return fail(DCNV3_ERR_ARGUMENT, "%s is NULL", name);
+    const DLTensor& t = m->dl_tensor;
+    if (t.device.device_type != kDLCUDA && t.device.device_type != kDLCUDAManaged)
+        return fail(DCNV3_ERR_DEVICE, "%s is not a CUDA tensor (device_type %d)", name, t.device.device_type);
+    if (device_id >= 0 && t.device.device_id != device_id)
+        return fail(DCNV3_ERR_DEVICE, "%s is on device %d, expected %d", name, t.device.device_id, device_id);
+    if (t.ndim != ndim) return fail(DCNV3_ERR_SHAPE, "%s has %d dims, expected %d", name, t.ndim, ndim);
+    int dt;
+    int rc = dl_dtype(t, &dt, name);
+    if (rc) return rc;
+    if (dtype >= 0 && dt != dtype) return fail(DCNV3_ERR_DTYPE, "%s dtype differs from x", name);
+    if (t.strides != nullptr) {  // must be compact row-major (size-1 dims may carry any stride)
+        int64_t expect = 1;
+        for (int i = t.ndim - 1; i >= 0; --i) {
+            if (t.shape[i] != 1 && t.strides[i] != expect)
+                return fail(DCNV3_ERR_LAYOUT, "%s is not dense row-major (NHWC contiguous)", name);
+            expect *= t.shape[i];
+        }
+    }
+    *data = (char*)t.data + t.byte_offset;
+    return 0;
+}
+
+static int dl_expect_shape(const DLManagedTensor* m, const char* name, int64_t a, int64_t b, int64_t c,
+                           int64_t d) {
+    const int64_t* s = m->dl_tensor.shape;
+    if (s[0] != a || s[1] != b || s[2] != c || s[3] != d)
+        return fail(DCNV3_ERR_SHAPE, "%s has shape [%lld,%lld,%lld,%lld], expected [%lld,%lld,%lld,%lld]",
+                    name, (long long)s[0], (long long)s[1], (long long)s[2], (long long)s[3],
+                    (long long)a, (long long)b, (long long)c, (long long)d);
+    return 0;
+}
+
+static int dl_params(const DLManagedTensor* x, const DLManagedTensor* offset, int kh, int kw, int sh,
+                     int sw, int ph, int pw, int dh, int dw, int groups, int gc, float scale,
+                     unsigned flags, dcnv3_params* p) {
+    int dtype;
+    int rc = dl_dtype(x->dl_tensor, &dtype, "x");
+    if (rc) return rc;
+    const int64_t* xs = x->dl_tensor.shape;
+    const int64_t* os = offset->dl_tensor.shape;
+    for (int i = 0; i < 4; ++i)
+        if (xs[i] > 0x7fffffff || os[i] > 0x7fffffff) return fail(DCNV3_ERR_SHAPE, "dimension too large");
+    p->n = (int)xs[0]; p->h = (int)xs[1]; p->w = (int)xs[2];
+    p->ho = (int)os[1]; p->wo = (int)os[2];
+    p->groups = groups; p->group_channels = gc;
+    p->kh = kh; p->kw = kw; p->sh = sh; p->sw = sw; p->ph = ph; p->pw = pw; p->dh = dh; p->dw = dw;
+    p->offset_scale = scale; p->dtype = dtype; p->flags = flags;
+    return 0;
+}
+
+// ---- host-buffer scratch -------------------------------------------------------------------------
+struct HostScratch {
+    void* buf = nullptr;
+    size_t bytes = 0;
+    cudaStream_t stream = nullptr;
+};
+static std::mutex g_scratch_mu;
+static HostScratch g_scratch[64];
+
+static int scratch_reserve(int device, size_t bytes, HostScratch** out) {
+    if (device < 0 || device >= 64) return fail(DCNV3_ERR_DEVICE, "device %d out of range", device);
+    HostScratch& s = g_scratch[device];
+    cudaError_t e;
+    if (s.stream == nullptr) {
+        if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess)
+            return cuda_fail(e, "cudaStreamCreate");
+    }
+    if (s.bytes < bytes) {
+        if (s.buf) cudaFree(s.buf);
+        s.buf = nullptr; s.bytes = 0;
+        if ((e = cudaMalloc(&s.buf, bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
+        s.bytes = bytes;
+    }
+    *out = &s;
+    return 0;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace dcnv3
+
+using namespace dcnv3;
+
+extern "C" {
+
+int dcnv3_abi_version(void) { return DCNV3_ABI_VERSION; }
+
+const char* dcnv3_last_error(void) { return t_err; }
+
+const char* dcnv3_build_info(void) {
+    static char info[128];
+    snprintf(info, sizeof(info), "dcnv3_b200 abi %d, sm_100a, nvcc %d.%d", DCNV3_ABI_VERSION,
+             __CUDACC_VER_MAJOR__, __CUDACC_VER_MINOR__);
+    return info;
+}
+
+int dcnv3_check_params(const dcnv3_params* p) { return check(p); }
+
+int dcnv3_forward(const void* x, const void* offset, const void* mask, void* out,
+                  const dcnv3_params* p, void* cuda_stream) {
+    return forward_impl(x, offset, mask, out, p, (cudaStream_t)cuda_stream);
+}
+
+size_t dcnv3_backward_workspace_bytes(const dcnv3_params* p) {
+    if (check(p) != DCNV3_OK) return 0;
+    return backward_ws_bytes(p);
+}
+
+int dcnv3_backward(const void* x, const void* offset, const void* mask, const void* grad_out,
+                   void* grad_x, void* grad_offset, void* grad_mask, void* workspace,
+                   size_t workspace_bytes, const dcnv3_params* p, void* cuda_stream) {
+    return backward_impl(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, workspace,
+                         workspace_bytes, p, (cudaStream_t)cuda_stream);
+}
+
+int dcnv3_forward_dlpack(const DLManagedTensor* x, const DLManagedTensor* offset,
+                         const DLManagedTensor* mask, DLManagedTensor* out, int kh, int kw, int sh,
+                         int sw, int pad_h, int pad_w, int dh, int dw, int groups,
+                         int group_channels, float offset_scale, unsigned flags, void* cuda_stream) {
+    void *px, *po, *pm, *pout;
+    int rc;
+    if ((rc = dl_check(x, "x", 4, -1, -1, &px))) return rc;
+    const int dev = x->dl_tensor.device.device_id;
+    int dtype;
+    dl_dtype(x->dl_tensor, &dtype, "x");
+    if ((rc = dl_check(offset, "offset", 4, dev, dtype, &po)) || (rc = dl_check(mask, "mask", 4, dev, dtype, &pm)) ||
+        (rc = dl_check(out, "out", 4, dev, dtype, &pout)))
+        return rc;
+    dcnv3_params p;
+    if ((rc = dl_params(x, offset, kh, kw, sh, sw, pad_h, pad_w, dh, dw, groups, group_channels,
+                        offset_scale, flags, &p)))
+        return rc;
+    const int64_t C = (int64_t)groups * group_channels, GP = (int64_t)groups * kh * kw;
+    if ((rc = dl_expect_shape(x, "x", p.n, p.h, p.w, C)) ||
+        (rc = dl_expect_shape(offset, "offset", p.n, p.ho, p.wo, GP * 2)) ||
+        (rc = dl_expect_shape(mask, "mask", p.n, p.ho, p.wo, GP)) ||
+        (rc = dl_expect_shape(out, "out", p.n, p.ho, p.wo, C)))
+        return rc;
+    return forward_impl(px, po, pm, pout, &p, (cudaStream_t)cuda_stream);
+}
+
+int dcnv3_backward_dlpack(const DLManagedTensor* x, const DLManagedTensor* offset,
+                          const DLManagedTensor* mask, const DLManagedTensor* grad_out,
+                          DLManagedTensor* grad_x, DLManagedTensor* grad_offset,
+                          DLManagedTensor* grad_mask, DLManagedTensor* workspace, int kh, int kw,
+                          int sh, int sw, int pad_h, int pad_w, int dh, int dw, int groups,
+                          int group_channels, float offset_scale, unsigned flags,
+                          void* cuda_stream) {
+    void *px, *po, *pm, *pgo, *pgx, *pgoff, *pgm;
+    int rc;
+    if ((rc = dl_check(x, "x", 4, -1, -1, &px))) return rc;
+    const int dev = x->dl_tensor.device.device_id;
+    int dtype;
+    dl_dtype(x->dl_tensor, &dtype, "x");
+    if ((rc = dl_check(offset, "offset", 4, dev, dtype, &po)) || (rc = dl_check(mask, "mask", 4, dev, dtype, &pm)) ||
+        (rc = dl_check(grad_out, "grad_out", 4, dev, dtype, &pgo)) ||
+        (rc = dl_check(grad_x, "grad_x", 4, dev, dtype, &pgx)) ||
+        (rc = dl_check(grad_offset, "grad_offset", 4, dev, dtype, &pgoff)) ||
+        (rc = dl_check(grad_mask, "grad_mask", 4, dev, dtype, &pgm)))
+        return rc;
+    dcnv3_params p;
+    if ((rc = dl_params(x, offset, kh, kw, sh, sw, pad_h, pad_w, dh, dw, groups, group_channels,
+                        offset_scale, flags, &p)))
+        return rc;
+    const int64_t C = (int64_t)groups * group_channels, GP = (int64_t)groups * kh * kw;
+    if ((rc = dl_expect_shape(x, "x", p.n, p.h, p.w, C)) ||
+        (rc = dl_expect_shape(offset, "offset", p.n, p.ho, p.wo, GP * 2)) ||
+        (rc = dl_expect_shape(mask, "mask", p.n, p.ho, p.wo, GP)) ||
+        (rc = dl_expect_shape(grad_out, "grad_out", p.n, p.ho, p.wo, C)) ||
+        (rc = dl_expect_shape(grad_x, "grad_x", p.n, p.h, p.w, C)) ||
+        (rc = dl_expect_shape(grad_offset, "grad_offset", p.n, p.ho, p.wo, GP * 2)) ||
+        (rc = dl_expect_shape(grad_mask, "grad_mask", p.n, p.ho, p.wo, GP)))
+        return rc;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    if (workspace != nullptr) {
+        const DLTensor& t = workspace->dl_tensor;
+        if (t.device.device_type != kDLCUDA || t.device.device_id != dev)
+            return fail(DCNV3_ERR_DEVICE, "workspace must be a CUDA tensor on x's device");
+        size_t count = 1;
+        for (int i = 0; i < t.ndim; ++i) count *= (size_t)t.shape[i];
+        ws = (char*)t.data + t.byte_offset;
+        ws_bytes = count * ((t.dtype.bits + 7) / 8) * t.dtype.lanes;
+    }
+    return backward_impl(px, po, pm, pgo, pgx, pgoff, pgm, ws, ws_bytes, &p, (cudaStream_t)cuda_stream);
+}
+
+static int host_run(const void* x, const void* offset, const void* mask, const void* grad_out,
+                    void* out, void* grad_x, void* grad_offset, void* grad_mask,
+                    const dcnv3_params* p, int device, bool with_backward) {
+    int rc = check(p);
+    if (rc) return rc;
+    if (!x || !offset || !mask || !out || (with_backward && (!grad_out || !grad_x || !grad_offset || !grad_mask)))
+        return fail(DCNV3_ERR_ARGUMENT, "NULL host buffer");
+    if (p->n == 0) return DCNV3_OK;
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    const size_t es = elem_size(p->dtype);
+    const size_t C = (size_t)p->groups * p->group_channels, GP = (size_t)p->groups * p->kh * p->kw;
+    const size_t b_x = align_up((size_t)p->n * p->h * p->w * C * es, 256);
+    const size_t b_o = align_up((size_t)p->n * p->ho * p->wo * C * es, 256);
+    const size_t b_off = align_up((size_t)p->n * p->ho * p->wo * GP * 2 * es, 256);
+    const size_t b_m = align_up((size_t)p->n * p->ho * p->wo * GP * es, 256);
+    const size_t b_ws = with_backward ? align_up(backward_ws_bytes(p), 256) : 0;
+    size_t total = b_x + b_off + b_m + b_o;
+    if (with_backward) total += b_o + b_x + b_off + b_m + b_ws;
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    HostScratch* s;
+    if ((rc = scratch_reserve(device, total, &s))) return rc;
+    char* base = (char*)s->buf;
+    char* d_x = base; base += b_x;
+    char* d_off = base; base += b_off;
+    char* d_m = base; base += b_m;
+    char* d_out = base; base += b_o;
+    cudaStream_t st = s->stream;
+#define H2D(dst, src, bytes) if ((e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D copy")
+#define D2H(dst, src, bytes) if ((e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H copy")
+    const size_t n_x = (size_t)p->n * p->h * p->w * C * es, n_o = (size_t)p->n * p->ho * p->wo * C * es;
+    const size_t n_off = (size_t)p->n * p->ho * p->wo * GP * 2 * es, n_m = n_off / 2;
+    H2D(d_x, x, n_x);
+    H2D(d_off, offset, n_off);
+    H2D(d_m, mask, n_m);
+    if ((rc = forward_impl(d_x, d_off, d_m, d_out, p, st))) return rc;
+    D2H(out, d_out, n_o);
+    if (with_backward) {
+        char* d_go = base; base += b_o;
+        char* d_gx = base; base += b_x;
+        char* d_goff = base; base += b_off;
+        char* d_gm = base; base += b_m;
+        char* d_ws = base;
+        H2D(d_go, grad_out, n_o);
+        if ((rc = backward_impl(d_x, d_off, d_m, d_go, d_gx, d_goff, d_gm, d_ws, b_ws, p, st))) return rc;
+        D2H(grad_x, d_gx, n_x);
+        D2H(grad_offset, d_goff, n_off);
+        D2H(grad_mask, d_gm, n_m);
+    }
+#undef H2D
+#undef D2H
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "stream synchronize");
+    return DCNV3_OK;
+}
+
+int dcnv3_forward_host(const void* x, const void* offset, const void* mask, void* out,
+                       const dcnv3_params* p, int device) {
+    return host_run(x, offset, mask, nullptr, out, nullptr, nullptr, nullptr, p, device, false);
+}
+
+int dcnv3_forward_backward_host(const void* x, const void* offset, const void* mask,
+                                const void* grad_out, void* out, void* grad_x, void* grad_offset,
+                                void* grad_mask, const dcnv3_params* p, int device) {
+    return host_run(x, offset, mask, grad_out, out, grad_x, grad_offset, grad_mask, p, device, true);
+}
+
+int dcnv3_release_host_scratch(void) {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    for (int d = 0; d < 64; ++d) {
+        HostScratch& s = g_scratch[d];
+        if (s.buf || s.stream) {
+            cudaSetDevice(d);
+            if (s.buf) cudaFree(s.buf);
+            if (s.stream) cudaStreamDestroy(s.stream);
+            s = HostScratch();
+        }
+    }
+    return DCNV3_OK;
+}
+
+uint64_t dcnv3_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

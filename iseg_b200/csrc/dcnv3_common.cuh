@@ -1,0 +1,149 @@
+// Shared device-side definitions for the DCNv3 kernels (sm_100a).
+//
+// The coordinate arithmetic mirrors, operation by operation and in fp32 round-to-nearest without
+// FMA contraction, what the reference computes in
+//   layers/dcn_v3/utils.py:14-58   get_reference_points   (ref_y lands in channel 0, :52)
+//   layers/dcn_v3/utils.py:65-103  generate_dilation_grids (tap p = i*kh + j)
+//   layers/dcn_v3/op.py:77-87      loc = ref + grid*s + offset*s/[W_in,H_in];  g = 2*loc - 1
+//   layers/dcn_v3/utils.py:142-166 q = 0.5*((g+1)*(max-1)); floor; clip; deltas from clipped corners
+// so that floor()/clip decisions are bit-identical to the oracle's.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dcnv3_b200.h"
+
+#define DCNV3_MAX_TAPS 49  // kh*kw <= 7*7
+
+namespace dcnv3 {
+
+// Kernel-side parameter block (passed by value, lives in constant bank 0).
+struct KParams {
+    int n, h, w, ho, wo, G, gc, P, kh;
+    int sh, sw, ph, pw;
+    int hin, win;          // padded extent
+    float hin_f, win_f;    // (float)H_in, (float)W_in
+    float hm2_f, wm2_f;    // (float)(H_in-2), (float)(W_in-2)   (utils.py:142-143: max-1)
+    float y0c, x0c;        // (d*(k-1))//2 + 0.5                (utils.py:29-33)
+    float scale;           // offset_scale
+    float fx, fy;          // d xq/d offset0 = (W_in-2)*s/W_in ; d yq/d offset1 = (H_in-2)*s/H_in
+    unsigned flags;
+    float gs0[DCNV3_MAX_TAPS];  // (dx_p / W_in) * s   -- grid*offset_scale, channel 0 (op.py:82)
+    float gs1[DCNV3_MAX_TAPS];  // (dy_p / H_in) * s
+};
+
+struct Tap {
+    int x0, y0;        // clipped lower corner (x1 = x0+1, y1 = y0+1 whenever the tap is alive)
+    float dx0, dx1, dy0, dy1;
+    bool alive;        // false <=> a clipped corner pair coincides => the tap contributes exactly 0
+};
+
+// One normalised coordinate -> pixel coordinate, exactly as op.py:82-87 + utils.py:142.
+__device__ __forceinline__ float pixel_coord(float ref, float gs, float off, float scale, float dim_f,
+                                             float dim_m2_f) {
+    float loc = __fadd_rn(ref, gs);
+    loc = __fadd_rn(loc, __fdiv_rn(__fmul_rn(off, scale), dim_f));
+    const float g = __fsub_rn(__fmul_rn(2.0f, loc), 1.0f);
+    return __fmul_rn(0.5f, __fmul_rn(__fadd_rn(g, 1.0f), dim_m2_f));
+}
+
+// Reference point of output pixel (h, w): (h*sh + y0c)/H_in goes to channel 0 (paired with W_in
+// further down -- the reference's transposed sampling), (w*sw + x0c)/W_in to channel 1.
+__device__ __forceinline__ void ref_point(const KParams& q, int h, int w, float& ref0, float& ref1) {
+    ref0 = __fdiv_rn(__fadd_rn((float)(h * q.sh), q.y0c), q.hin_f);
+    ref1 = __fdiv_rn(__fadd_rn((float)(w * q.sw), q.x0c), q.win_f);
+}
+
+__device__ __forceinline__ Tap make_tap(const KParams& q, float ref0, float ref1, int p, float offx,
+                                        float offy) {
+    Tap t;
+    const float xq = pixel_coord(ref0, q.gs0[p], offx, q.scale, q.win_f, q.wm2_f);
+    const float yq = pixel_coord(ref1, q.gs1[p], offy, q.scale, q.hin_f, q.hm2_f);
+    // clamp before the int conversion (huge offsets); NaN falls to -2 => dead
+    const float fxq = fminf(fmaxf(floorf(xq), -2.0f), q.win_f);
+    const float fyq = fminf(fmaxf(floorf(yq), -2.0f), q.hin_f);
+    const int ix = (int)fxq, iy = (int)fyq;
+    // utils.py:152-155: both corners clipped to [0, max]; they coincide iff ix < 0 or ix >= max
+    t.alive = (ix >= 0) && (ix < q.win - 1) && (iy >= 0) && (iy < q.hin - 1);
+    t.x0 = min(max(ix, 0), q.win - 1);
+    t.y0 = min(max(iy, 0), q.hin - 1);
+    const int x1 = min(max(ix + 1, 0), q.win - 1);
+    const int y1 = min(max(iy + 1, 0), q.hin - 1);
+    t.dx0 = __fsub_rn(xq, (float)t.x0);  // utils.py:163-166
+    t.dx1 = __fsub_rn((float)x1, xq);
+    t.dy0 = __fsub_rn(yq, (float)t.y0);
+    t.dy1 = __fsub_rn((float)y1, yq);
+    return t;
+}
+
+// ---- element access -----------------------------------------------------------------------------
+template <typename T>
+struct Elem;
+template <>
+struct Elem<float> {
+    static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
+    static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+    static __device__ __forceinline__ float4 ld4(const float* p) {
+        return __ldg(reinterpret_cast<const float4*>(p));
+    }
+    static __device__ __forceinline__ void st4(float* p, float4 v) {
+        *reinterpret_cast<float4*>(p) = v;
+    }
+};
+template <>
+struct Elem<__nv_bfloat16> {
+    static __device__ __forceinline__ float ld(const __nv_bfloat16* p) {
+        return __bfloat162float(__ldg(p));
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) {
+        *p = __float2bfloat16_rn(v);
+    }
+    static __device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+        const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+        float4 v;
+        v.x = __uint_as_float(r.x << 16);
+        v.y = __uint_as_float(r.x & 0xffff0000u);
+        v.z = __uint_as_float(r.y << 16);
+        v.w = __uint_as_float(r.y & 0xffff0000u);
+        return v;
+    }
+    static __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+        const __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 r;
+        r.x = *reinterpret_cast<const unsigned*>(&a);
+        r.y = *reinterpret_cast<const unsigned*>(&b);
+        *reinterpret_cast<uint2*>(p) = r;
+    }
+};
+
+// ---- fixed-point accumulation (order-independent => bitwise reproducible scatter) ----------------
+// Workspace header written by the amax pre-pass.
+struct WsHeader {
+    unsigned amax_go_bits;  // max |grad_out| as float bits
+    unsigned amax_m_bits;   // max |mask|     as float bits
+    unsigned pad[62];
+};
+
+// Exponent e such that every contribution |v| <= amax_go*amax_m maps to |v * 2^e| <= 2^46, leaving
+// 2^16 accumulations of headroom in an int64.
+__device__ __forceinline__ int fixed_exponent(const WsHeader* hd, bool mask_is_prob) {
+    const float a = __uint_as_float(hd->amax_go_bits);
+    const float m = mask_is_prob ? 1.0f : __uint_as_float(hd->amax_m_bits);
+    const float bound = a * m;
+    if (!(bound > 0.0f) || !(bound < 3.0e38f)) return 0;
+    int ex;
+    frexpf(bound, &ex);  // bound = f * 2^ex, f in [0.5, 1)  =>  bound < 2^ex
+    int e = 46 - ex;
+    return max(min(e, 120), -120);
+}
+
+__device__ __forceinline__ long long to_fixed(float v, int e) {
+    return __float2ll_rn(ldexpf(v, e));  // exact scaling, exact conversion (24-bit mantissa)
+}
+
+
+
+}  // namespace dcnv3

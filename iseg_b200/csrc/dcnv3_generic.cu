@@ -1,0 +1,270 @@
+// Generic DCNv3 kernels: any kernel size / stride / dilation / padding / group width the reference
+// accepts.  Correctness-first path; the k=3/s=1/d=1 InternImage shapes are
+// served by the tiled kernels in dcnv3_tiled.cu when they apply.
+//
+// forward : one thread per (pixel, group, channel chunk); 4 corner loads per tap straight from the
+//           un-padded NHWC tensor (the zero ring of op.py:46 is never materialised).
+// backward: one thread per (pixel, group); grad_offset / grad_mask need no cross-thread reduction;
+//           grad_x contributions are scattered as 64-bit fixed-point integer atomics (integer
+//           addition is associative => bitwise reproducible, no float atomics), then converted.
+#include "dcnv3_kernels.h"
+
+namespace dcnv3 {
+
+template <typename T>
+__device__ __forceinline__ const T* slab_ptr(const T* x, const KParams& q, int n, int yp, int xp,
+                                             int g) {
+    const int y = yp - q.ph, xx = xp - q.pw;
+    if (y < 0 || y >= q.h || xx < 0 || xx >= q.w) return nullptr;
+    return x + ((((size_t)n * q.h + y) * q.w + xx) * q.G + g) * q.gc;
+}
+
+// softmax over the P logits of one (pixel, group): returns max and 1/sum (dcn_v3.py:120-123)
+template <typename T>
+__device__ __forceinline__ void softmax_stats(const T* logits, int P, float& mx, float& inv_sum) {
+    mx = -INFINITY;
+    for (int p = 0; p < P; ++p) mx = fmaxf(mx, Elem<T>::ld(logits + p));
+    float s = 0.f;
+    for (int p = 0; p < P; ++p) s += expf(Elem<T>::ld(logits + p) - mx);
+    inv_sum = 1.0f / s;
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+fwd_generic_kernel(const T* __restrict__ x, const T* __restrict__ offset, const T* __restrict__ mask,
+                   T* __restrict__ out, const KParams q) {
+    const int cq_n = q.gc / VEC;
+    const size_t total = (size_t)q.n * q.ho * q.wo * q.G * cq_n;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cq = (int)(idx % cq_n);
+    const size_t pg = idx / cq_n;
+    const int g = (int)(pg % q.G);
+    const size_t pix = pg / q.G;
+    const int w = (int)(pix % q.wo);
+    const int h = (int)((pix / q.wo) % q.ho);
+    const int n = (int)(pix / ((size_t)q.wo * q.ho));
+    float ref0, ref1;
+    ref_point(q, h, w, ref0, ref1);
+    const T* off = offset + pg * q.P * 2;
+    const T* msk = mask + pg * q.P;
+    float mx = 0.f, inv_sum = 1.f;
+    const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
+    if (logits) softmax_stats(msk, q.P, mx, inv_sum);
+    float acc[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+    const int c0 = cq * VEC;
+    for (int p = 0; p < q.P; ++p) {
+        const Tap t = make_tap(q, ref0, ref1, p, Elem<T>::ld(off + 2 * p), Elem<T>::ld(off + 2 * p + 1));
+        if (!t.alive) continue;
+        float m = Elem<T>::ld(msk + p);
+        if (logits) m = expf(m - mx) * inv_sum;
+        const float wgt[4] = {t.dx1 * t.dy1, t.dx1 * t.dy0, t.dx0 * t.dy1, t.dx0 * t.dy0};
+        float s[VEC];
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) s[c] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // a b c d = (y0,x0) (y1,x0) (y0,x1) (y1,x1), utils.py:177-178
+            const T* src = slab_ptr(x, q, n, t.y0 + (k & 1), t.x0 + (k >> 1), g);
+            if (src == nullptr) continue;
+            if (VEC == 4) {
+                const float4 v = Elem<T>::ld4(src + c0);
+                s[0] += v.x * wgt[k];
+                s[1 % VEC] += v.y * wgt[k];
+                s[2 % VEC] += v.z * wgt[k];
+                s[3 % VEC] += v.w * wgt[k];
+            } else {
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) s[c] += Elem<T>::ld(src + c0 + c) * wgt[k];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) acc[c] += s[c] * m;
+    }
+    T* o = out + pg * q.gc + c0;
+    if (VEC == 4) {
+        Elem<T>::st4(o, make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]));
+    } else {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) Elem<T>::st(o + c, acc[c]);
+    }
+}
+
+// max |grad_out| and max |mask| -> workspace header (atomicMax on the float bit pattern of |v| is
+// order independent)
+template <typename T>
+__global__ void __launch_bounds__(256)
+amax_kernel(const T* __restrict__ grad_out, size_t n_go, const T* __restrict__ mask, size_t n_m,
+            WsHeader* hd) {
+    float a = 0.f, b = 0.f;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_go; i += stride)
+        a = fmaxf(a, fabsf(Elem<T>::ld(grad_out + i)));
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_m; i += stride)
+        b = fmaxf(b, fabsf(Elem<T>::ld(mask + i)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&hd->amax_go_bits, __float_as_uint(a));
+        atomicMax(&hd->amax_m_bits, __float_as_uint(b));
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+bwd_generic_kernel(const T* __restrict__ x, const T* __restrict__ offset, const T* __restrict__ mask,
+                   const T* __restrict__ grad_out, T* __restrict__ grad_offset,
+                   T* __restrict__ grad_mask, const WsHeader* __restrict__ hd,
+                   unsigned long long* __restrict__ acc64, const KParams q) {
+    const size_t total = (size_t)q.n * q.ho * q.wo * q.G;
+    const size_t pg = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pg >= total) return;
+    const int g = (int)(pg % q.G);
+    const size_t pix = pg / q.G;
+    const int w = (int)(pix % q.wo);
+    const int h = (int)((pix / q.wo) % q.ho);
+    const int n = (int)(pix / ((size_t)q.wo * q.ho));
+    const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
+    const int e = fixed_exponent(hd, logits);
+    float ref0, ref1;
+    ref_point(q, h, w, ref0, ref1);
+    const T* off = offset + pg * q.P * 2;
+    const T* msk = mask + pg * q.P;
+    const T* go = grad_out + pg * q.gc;
+    T* goff = grad_offset + pg * q.P * 2;
+    T* gmsk = grad_mask + pg * q.P;
+    float mx = 0.f, inv_sum = 1.f;
+    if (logits) softmax_stats(msk, q.P, mx, inv_sum);
+    float gm_dot_m = 0.f;       // sum_p m_p * dL/dm_p, for the softmax Jacobian
+    float gm_local[DCNV3_MAX_TAPS];
+    for (int p = 0; p < q.P; ++p) {
+        const Tap t = make_tap(q, ref0, ref1, p, Elem<T>::ld(off + 2 * p), Elem<T>::ld(off + 2 * p + 1));
+        float m = Elem<T>::ld(msk + p);
+        if (logits) m = expf(m - mx) * inv_sum;
+        float gm = 0.f, gxq = 0.f, gyq = 0.f;
+        if (t.alive) {
+            const float wgt[4] = {t.dx1 * t.dy1, t.dx1 * t.dy0, t.dx0 * t.dy1, t.dx0 * t.dy0};
+            float dot[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int yp = t.y0 + (k & 1), xp = t.x0 + (k >> 1);
+                const T* src = slab_ptr(x, q, n, yp, xp, g);
+                float d = 0.f;
+                if (src != nullptr) {
+                    const float mw = m * wgt[k];
+                    unsigned long long* dst =
+                        acc64 + ((((size_t)n * q.h + (yp - q.ph)) * q.w + (xp - q.pw)) * q.G + g) * q.gc;
+                    for (int c = 0; c < q.gc; ++c) {
+                        const float gv = Elem<T>::ld(go + c);
+                        d += gv * Elem<T>::ld(src + c);
+                        atomicAdd(dst + c, (unsigned long long)to_fixed(gv * mw, e));
+                    }
+                }
+                dot[k] = d;
+            }
+            gm = wgt[0] * dot[0] + wgt[1] * dot[1] + wgt[2] * dot[2] + wgt[3] * dot[3];
+            gxq = m * (t.dy1 * (dot[2] - dot[0]) + t.dy0 * (dot[3] - dot[1]));
+            gyq = m * (t.dx1 * (dot[1] - dot[0]) + t.dx0 * (dot[3] - dot[2]));
+        }
+        Elem<T>::st(goff + 2 * p, gxq * q.fx);
+        Elem<T>::st(goff + 2 * p + 1, gyq * q.fy);
+        if (logits) {
+            gm_local[p] = gm;
+            gm_dot_m += gm * m;
+        } else {
+            Elem<T>::st(gmsk + p, gm);
+        }
+    }
+    if (logits) {
+        for (int p = 0; p < q.P; ++p) {
+            const float m = expf(Elem<T>::ld(msk + p) - mx) * inv_sum;
+            Elem<T>::st(gmsk + p, m * (gm_local[p] - gm_dot_m));
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+fixed_to_float_kernel(const long long* __restrict__ acc64, const WsHeader* __restrict__ hd,
+                      T* __restrict__ grad_x, size_t count, unsigned flags) {
+    const int e = fixed_exponent(hd, flags & DCNV3_FLAG_MASK_LOGITS);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        Elem<T>::st(grad_x + i, (float)ldexp((double)acc64[i], -e));
+}
+
+// ---- launchers -----------------------------------------------------------------------------------
+static inline unsigned blocks_for(size_t total, int threads) {
+    return (unsigned)((total + threads - 1) / threads);
+}
+
+template <typename T>
+cudaError_t launch_fwd_generic_t(const void* x, const void* offset, const void* mask, void* out,
+                                 const KParams& q, cudaStream_t st) {
+    const size_t pg = (size_t)q.n * q.ho * q.wo * q.G;
+    if (pg == 0) return cudaSuccess;
+    const bool vec = (q.gc % 4 == 0);
+    if (vec) {
+        const size_t total = pg * (q.gc / 4);
+        fwd_generic_kernel<T, 4><<<blocks_for(total, 256), 256, 0, st>>>(
+            (const T*)x, (const T*)offset, (const T*)mask, (T*)out, q);
+    } else {
+        const size_t total = pg * q.gc;
+        fwd_generic_kernel<T, 1><<<blocks_for(total, 256), 256, 0, st>>>(
+            (const T*)x, (const T*)offset, (const T*)mask, (T*)out, q);
+    }
+    count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fwd_generic(const void* x, const void* offset, const void* mask, void* out,
+                               const KParams& q, int dtype, cudaStream_t st) {
+    return dtype == DCNV3_F32 ? launch_fwd_generic_t<float>(x, offset, mask, out, q, st)
+                              : launch_fwd_generic_t<__nv_bfloat16>(x, offset, mask, out, q, st);
+}
+
+size_t bwd_generic_workspace_bytes(const KParams& q) {
+    return sizeof(WsHeader) + sizeof(long long) * (size_t)q.n * q.h * q.w * q.G * q.gc;
+}
+
+template <typename T>
+cudaError_t launch_bwd_generic_t(const void* x, const void* offset, const void* mask,
+                                 const void* grad_out, void* grad_x, void* grad_offset,
+                                 void* grad_mask, void* ws, const KParams& q, cudaStream_t st) {
+    const size_t n_x = (size_t)q.n * q.h * q.w * q.G * q.gc;
+    const size_t pg = (size_t)q.n * q.ho * q.wo * q.G;
+    cudaError_t err = cudaMemsetAsync(ws, 0, bwd_generic_workspace_bytes(q), st);
+    if (err != cudaSuccess) return err;
+    WsHeader* hd = (WsHeader*)ws;
+    unsigned long long* acc = (unsigned long long*)((char*)ws + sizeof(WsHeader));
+    if (pg > 0) {
+        const size_t n_go = pg * q.gc, n_m = pg * q.P;
+        const unsigned nb = (unsigned)min((size_t)148 * 8, (n_go + 255) / 256);
+        amax_kernel<T><<<nb, 256, 0, st>>>((const T*)grad_out, n_go, (const T*)mask,
+                                           (q.flags & DCNV3_FLAG_MASK_LOGITS) ? 0 : n_m, hd);
+        bwd_generic_kernel<T><<<blocks_for(pg, 128), 128, 0, st>>>(
+            (const T*)x, (const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_offset,
+            (T*)grad_mask, hd, acc, q);
+        count_launch(2);
+    }
+    if (n_x > 0) {
+        const unsigned nb = (unsigned)min((size_t)148 * 16, (n_x + 255) / 256);
+        fixed_to_float_kernel<T><<<nb, 256, 0, st>>>((const long long*)acc, hd, (T*)grad_x, n_x, q.flags);
+        count_launch(1);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bwd_generic(const void* x, const void* offset, const void* mask,
+                               const void* grad_out, void* grad_x, void* grad_offset, void* grad_mask,
+                               void* ws, const KParams& q, int dtype, cudaStream_t st) {
+    return dtype == DCNV3_F32
+               ? launch_bwd_generic_t<float>(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, st)
+               : launch_bwd_generic_t<__nv_bfloat16>(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, st);
+}
+
+}  // namespace dcnv3

@@ -1,0 +1,18 @@
+// Internal launcher interface between the C ABI (dcnv3_cabi.cu) and the kernel translation units.
+#pragma once
+
+#include "dcnv3_common.cuh"
+
+namespace dcnv3 {
+
+void count_launch(unsigned n);
+
+// generic path (dcnv3_generic.cu)
+cudaError_t launch_fwd_generic(const void* x, const void* offset, const void* mask, void* out,
+                               const KParams& q, int dtype, cudaStream_t st);
+size_t bwd_generic_workspace_bytes(const KParams& q);
+cudaError_t launch_bwd_generic(const void* x, const void* offset, const void* mask,
+                               const void* grad_out, void* grad_x, void* grad_offset, void* grad_mask,
+                               void* ws, const KParams& q, int dtype, cudaStream_t st);
+
+}  // namespace dcnv3

@@ -1,0 +1,50 @@
+"""`dcnv3_op` -- host-side mirror of the reference's operator entry point
+(reference layers/dcn_v3/op.py:16-27): same name, argument order, argument meaning and error
+behaviour, NHWC tensors in and out.  The arithmetic runs in the sm_100a kernels behind the C ABI;
+the gradient the reference gets from TF autodiff is registered here as a torch.autograd.Function.
+"""
+import torch
+
+from ... import _cabi
+
+
+def _resolve_padding(kernel_size, padding):
+    # reference op.py:29-39
+    if not isinstance(padding, str):
+        raise TypeError("padding must be a string in 'SAME' or 'VALID'")
+    padding = padding.upper()
+    if padding == "SAME":
+        return (kernel_size[0] // 2, kernel_size[1] // 2)
+    if padding == "VALID":
+        return (0, 0)
+    raise ValueError("padding must be 'SAME' or 'VALID'")
+
+
+class _DCNv3Function(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, offset, mask, cfg):
+        x, offset, mask = x.contiguous(), offset.contiguous(), mask.contiguous()
+        ctx.cfg = cfg
+        ctx.save_for_backward(x, offset, mask)
+        return _cabi.forward(x, offset, mask, *cfg)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, offset, mask = ctx.saved_tensors
+        gx, goff, gm = _cabi.backward(x, offset, mask, grad_out.contiguous(), *ctx.cfg)
+        return gx, goff, gm, None
+
+
+def dcnv3_op(x, offset, mask, kernel_size, strides, padding, dilation_rate, groups, group_channels,
+             offset_scale, mask_is_logits=False):
+    """x [N,H,W,G*gc], offset [N,Ho,Wo,G*P*2], mask [N,Ho,Wo,G*P] -> [N,Ho,Wo,G*gc] (dtype of x).
+
+    `mask_is_logits=True` (extension, not in the reference signature) fuses the softmax over the P
+    taps that the layer applies just before the call (dcn_v3.py:120-123)."""
+    pad = _resolve_padding(kernel_size, padding)
+    if offset.dtype != x.dtype or mask.dtype != x.dtype:
+        raise TypeError("x, offset and mask must have the same dtype")
+    cfg = (tuple(int(k) for k in kernel_size), tuple(int(s) for s in strides), pad,
+           tuple(int(d) for d in dilation_rate), int(groups), int(group_channels),
+           float(offset_scale), _cabi.FLAG_MASK_LOGITS if mask_is_logits else 0)
+    return _DCNv3Function.apply(x, offset, mask, cfg)

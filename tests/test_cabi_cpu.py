@@ -1,0 +1,96 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/dcnv3_b200.h declares, validates parameters like the reference's reshapes would, and the host
+wrapper keeps the reference's error behaviour.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def cabi():
+    from iseg_b200 import build
+    build.build()
+    from iseg_b200 import _cabi
+    return _cabi
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "dcnv3_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dcnv3_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(cabi):
+    names = declared_functions()
+    assert len(names) >= 12
+    for name in names:
+        assert hasattr(cabi.lib, name), f"{name} declared in include/dcnv3_b200.h but not exported"
+
+
+def test_version_and_build_info(cabi):
+    assert cabi.lib.dcnv3_abi_version() == 1
+    assert b"sm_100a" in cabi.lib.dcnv3_build_info()
+
+
+def test_param_validation_mirrors_reference_reshape(cabi):
+    mk = lambda **kw: cabi.make_params(  # noqa: E731
+        kw.get("x", (2, 8, 9, 64)), kw.get("out", (8, 9)), kw.get("k", (3, 3)), kw.get("s", (1, 1)),
+        kw.get("pad", (1, 1)), kw.get("d", (1, 1)), kw.get("g", 4), kw.get("gc", 16), 1.0,
+        kw.get("dtype", 0))
+    chk = lambda p: cabi.lib.dcnv3_check_params(ctypes.byref(p))  # noqa: E731
+    assert chk(mk()) == 0
+    assert chk(mk(out=(7, 9))) == cabi.ERR_SHAPE          # offset grid != reference-point grid
+    assert b"op.py:83" in cabi.lib.dcnv3_last_error()
+    assert chk(mk(pad=(0, 0), out=(6, 7))) == 0            # VALID
+    assert chk(mk(s=(2, 2), out=(4, 5))) == 0              # (10-3)//2+1, (11-3)//2+1
+    assert chk(mk(d=(2, 2), out=(6, 7))) == 0              # dilation 2 with SAME pad 1
+    assert chk(mk(k=(9, 9), pad=(4, 4))) == cabi.ERR_ARGUMENT
+    assert chk(mk(dtype=7)) == cabi.ERR_DTYPE
+    assert chk(mk(x=(2, 1, 1, 64), pad=(0, 0), out=(1, 1))) == cabi.ERR_SHAPE  # kernel > input
+    assert cabi.lib.dcnv3_backward_workspace_bytes(ctypes.byref(mk())) > 0
+    assert cabi.lib.dcnv3_backward_workspace_bytes(ctypes.byref(mk(out=(1, 1)))) == 0
+
+
+def test_compute_entry_points_fail_loudly_without_cuda(cabi):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    p = cabi.make_params((1, 4, 4, 16), (4, 4), (3, 3), (1, 1), (1, 1), (1, 1), 1, 16, 1.0, 0)
+    buf = (ctypes.c_float * 4096)()
+    rc = cabi.lib.dcnv3_forward_host(buf, buf, buf, buf, ctypes.byref(p), 0)
+    assert rc == cabi.ERR_CUDA and cabi.lib.dcnv3_last_error()
+
+
+def test_op_error_conventions(cabi):
+    from iseg_b200 import dcnv3_op
+    x = torch.zeros(1, 4, 4, 16)
+    off = torch.zeros(1, 4, 4, 18)
+    m = torch.zeros(1, 4, 4, 9)
+    with pytest.raises(TypeError):  # reference op.py:29-30
+        dcnv3_op(x, off, m, [3, 3], [1, 1], 1, [1, 1], 1, 16, 1.0)
+    with pytest.raises(ValueError):  # reference op.py:38-39
+        dcnv3_op(x, off, m, [3, 3], [1, 1], "full", [1, 1], 1, 16, 1.0)
+    with pytest.raises(cabi.DCNv3Error):  # CPU tensors: no fallback
+        dcnv3_op(x, off, m, [3, 3], [1, 1], "same", [1, 1], 1, 16, 1.0)
+
+
+def test_layer_signature_matches_reference():
+    import inspect
+    from iseg_b200 import DeformableConvolutionV3
+    sig = inspect.signature(DeformableConvolutionV3.__init__)
+    ref_args = ["filters", "kernel_size", "depthwise_kernel_size", "strides", "padding",
+                "dilation_rate", "groups", "offset_scale", "activation", "center_feature_scale", "name"]
+    assert list(sig.parameters)[1:1 + len(ref_args)] == ref_args  # dcn_v3.py:18-31
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert (d["filters"], d["kernel_size"], d["strides"], d["padding"], d["groups"]) == (64, 3, 1, "SAME", 4)
+    with pytest.raises(AssertionError):
+        DeformableConvolutionV3(filters=10, groups=4)  # dcn_v3.py:34
+    layer = DeformableConvolutionV3(filters=32, groups=2, center_feature_scale=True, input_channels=32)
+    names = {n.split(".")[0] for n, _ in layer.named_parameters()}
+    assert names == {"dw_conv", "dw_conv_norm", "offset", "mask", "input_proj", "output_proj",
+                     "center_feature_scale_proj"}  # dcn_v3.py:62-102
+    assert not layer.offset.weight.any() and not layer.mask.weight.any()  # zero init, :74-86

@@ -1,0 +1,251 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden vectors.
+
+Bar: fp32  max|d|/max|ref| <= 1e-5 ; bf16 <= 1e-2 against the fp32 oracle evaluated
+on the bf16-rounded inputs ; gradients bit-identical run to run."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, golden_op_cases, load_op_case, make_inputs, rel_err
+from oracle import c_oracle, dcnv3_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-5
+TOL_BF16 = 1e-2
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import iseg_b200
+    from iseg_b200 import _cabi
+    return iseg_b200, _cabi
+
+
+def cuda(*arrs, dtype=torch.float32):
+    return [torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dtype) for a in arrs]
+
+
+def run_op(ops, x, off, m, go=None, dtype=torch.float32, mask_is_logits=False, **kw):
+    iseg, _ = ops
+    tx, to, tm = cuda(x, off, m, dtype=dtype)
+    if go is not None:
+        tx.requires_grad_(True), to.requires_grad_(True), tm.requires_grad_(True)
+    out = iseg.dcnv3_op(tx, to, tm, list(kw.get("kernel_size", (3, 3))), list(kw.get("strides", (1, 1))),
+                        kw.get("padding", "SAME"), list(kw.get("dilation_rate", (1, 1))), kw["groups"],
+                        kw["group_channels"], kw.get("offset_scale", 1.0), mask_is_logits=mask_is_logits)
+    if go is None:
+        return out.float().cpu().numpy()
+    out.backward(cuda(go, dtype=dtype)[0])
+    return tuple(t.float().cpu().numpy() for t in (out.detach(), tx.grad, to.grad, tm.grad))
+
+
+@pytest.mark.parametrize("name", [n for n in golden_op_cases() if not n.endswith("f64")])
+def test_golden_fp32(ops, name):
+    z, kw = load_op_case(name)
+    out, gx, goff, gm = run_op(ops, z["x"], z["offset"], z["mask"], z["grad_out"], **kw)
+    assert rel_err(out, z["out"]) <= TOL_F32
+    assert rel_err(gx, z["grad_x"]) <= TOL_F32
+    assert rel_err(goff, z["grad_offset"]) <= TOL_F32
+    assert rel_err(gm, z["grad_mask"]) <= TOL_F32
+
+
+def test_known_answers(ops):
+    z = np.load(f"{GOLDEN}/kat_ramp.npz")
+    kw = dict(groups=2, group_channels=1)
+    out = run_op(ops, z["x"], z["offset"], z["mask"], **kw)
+    assert abs(out[0, 1, 4, 0] - 32.125) < 1e-4 and abs(out[0, 5, 5, 0] - 42.625) < 1e-4
+    assert rel_err(out, z["out"]) <= TOL_F32
+    assert rel_err(run_op(ops, z["x"], z["offset_shift"], z["mask"], **kw), z["out_shift"]) <= TOL_F32
+    res = run_op(ops, z["x"], z["offset_dead"], z["mask"], np.ones_like(z["out"]), **kw)
+    assert all(not r.any() for r in res)  # dead taps: output and all three gradients exactly 0
+    zc = np.load(f"{GOLDEN}/kat_const.npz")
+    assert rel_err(run_op(ops, zc["x"], zc["offset"], zc["mask"], groups=1, group_channels=16), zc["out"]) <= TOL_F32
+
+
+CASES = [  # n, h, w, G, gc, sigma, offset_scale
+    (2, 128, 128, 4, 16, 1.0, 1.0),    # BASELINE config 1
+    (2, 64, 64, 8, 16, 1.0, 1.0),
+    (3, 32, 32, 16, 16, 2.0, 1.0),
+    (2, 16, 16, 32, 16, 1.0, 1.0),
+    (1, 49, 97, 4, 16, 4.0, 1.0),      # odd, non-square (sliding-window tile shapes), wide offsets
+    (1, 40, 40, 10, 16, 1.0, 2.0),     # InternImage-L style: G=10, offset_scale 2
+    (1, 20, 20, 40, 32, 1.0, 2.0),     # gc = 32
+    (1, 24, 24, 7, 16, 1.0, 1.0),      # odd group count (InternImage-B)
+    (1, 9, 11, 3, 5, 1.5, 1.0),        # gc not a multiple of 4 -> scalar path
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_random_fp32_vs_c_oracle(ops, case):
+    n, h, w, g, gc, sigma, scale = case
+    x, off, m, go = make_inputs(n, h, w, g, gc, sigma=sigma, seed=h * 131 + g)
+    off.reshape(-1)[::97] *= 50.0  # ~1 % outliers: exercise clipping / dead taps
+    kw = dict(groups=g, group_channels=gc, offset_scale=scale)
+    out, gx, goff, gm = run_op(ops, x, off, m, go, **kw)
+    ref_out = c_oracle.forward(x, off, m, **kw)
+    rx, roff, rm = c_oracle.backward(x, off, m, go, **kw)
+    assert rel_err(out, ref_out) <= TOL_F32
+    assert rel_err(gx, rx) <= TOL_F32
+    assert rel_err(goff, roff) <= TOL_F32
+    assert rel_err(gm, rm) <= TOL_F32
+
+
+@pytest.mark.parametrize("case", CASES[:4] + CASES[5:7])
+def test_random_bf16(ops, case):
+    n, h, w, g, gc, sigma, scale = case
+    x, off, m, go = make_inputs(n, h, w, g, gc, sigma=sigma, seed=7 + h)
+    rnd = lambda a: torch.from_numpy(a).bfloat16().float().numpy()  # noqa: E731
+    x, off, m, go = rnd(x), rnd(off), rnd(m), rnd(go)
+    kw = dict(groups=g, group_channels=gc, offset_scale=scale)
+    out, gx, goff, gm = run_op(ops, x, off, m, go, dtype=torch.bfloat16, **kw)
+    ref_out = c_oracle.forward(x, off, m, **kw)
+    rx, roff, rm = c_oracle.backward(x, off, m, go, **kw)
+    assert rel_err(out, ref_out) <= TOL_BF16
+    assert rel_err(gx, rx) <= TOL_BF16
+    assert rel_err(goff, roff) <= TOL_BF16
+    assert rel_err(gm, rm) <= TOL_BF16
+
+
+def test_backward_bitwise_reproducible(ops):
+    x, off, m, go = make_inputs(4, 64, 64, 8, 16, sigma=2.0, seed=3)
+    kw = dict(groups=8, group_channels=16)
+    a = run_op(ops, x, off, m, go, **kw)
+    for _ in range(3):
+        b = run_op(ops, x, off, m, go, **kw)
+        assert all(np.array_equal(p, q) for p, q in zip(a, b))
+    # heavy collisions: every tap of every pixel lands in the same cell
+    off2 = np.zeros_like(off)
+    off2[..., 0::2] = (30.0 - np.arange(64, dtype=np.float32)).reshape(1, 64, 1, 1) * 66 / 64
+    off2[..., 1::2] = (30.0 - np.arange(64, dtype=np.float32)).reshape(1, 1, 64, 1) * 66 / 64
+    a = run_op(ops, x, off2, m, go, **kw)
+    b = run_op(ops, x, off2, m, go, **kw)
+    assert all(np.array_equal(p, q) for p, q in zip(a, b))
+    rx, roff, rm = c_oracle.backward(x, off2, m, go, **kw)
+    assert rel_err(a[1], rx) <= TOL_F32 and rel_err(a[2], roff) <= TOL_F32
+
+
+def test_fused_softmax_matches_layer_semantics(ops):
+    n, h, w, g, gc = 2, 24, 20, 4, 16
+    x, off, _, go = make_inputs(n, h, w, g, gc, seed=11)
+    logits = np.random.default_rng(5).standard_normal((n, h, w, g * 9)).astype(np.float32) * 2
+    kw = dict(groups=g, group_channels=gc)
+    out, gx, goff, gl = run_op(ops, x, off, logits, go, mask_is_logits=True, **kw)
+    mask = O.mask_softmax(logits, g)
+    assert rel_err(out, c_oracle.forward(x, off, mask, **kw)) <= TOL_F32
+    rx, roff, rm = c_oracle.backward(x, off, mask, go, **kw)
+    mm, gg = mask.reshape(n, h, w, g, 9), rm.reshape(n, h, w, g, 9)
+    rl = (mm * (gg - (mm * gg).sum(-1, keepdims=True))).reshape(n, h, w, g * 9)  # softmax Jacobian
+    assert rel_err(gx, rx) <= TOL_F32 and rel_err(goff, roff) <= TOL_F32 and rel_err(gl, rl) <= TOL_F32
+
+
+def test_empty_and_tiny(ops):
+    iseg, _ = ops
+    e = lambda *s: torch.zeros(*s, device="cuda")  # noqa: E731
+    out = iseg.dcnv3_op(e(0, 8, 8, 64), e(0, 8, 8, 72), e(0, 8, 8, 36), [3, 3], [1, 1], "SAME", [1, 1], 4, 16, 1.0)
+    assert out.shape == (0, 8, 8, 64)
+    x, off, m, go = make_inputs(1, 1, 1, 1, 16, seed=2)
+    kw = dict(groups=1, group_channels=16)
+    out = run_op(ops, x, off, m, **kw)
+    assert rel_err(out, c_oracle.forward(x, off, m, **kw)) <= TOL_F32 or not c_oracle.forward(x, off, m, **kw).any()
+
+
+def test_shape_and_dtype_errors(ops):
+    iseg, cabi = ops
+    x = torch.zeros(1, 8, 8, 64, device="cuda")
+    off = torch.zeros(1, 8, 8, 72, device="cuda")
+    m = torch.zeros(1, 8, 8, 36, device="cuda")
+    with pytest.raises(ValueError):
+        iseg.dcnv3_op(x, off[:, :7], m[:, :7], [3, 3], [1, 1], "SAME", [1, 1], 4, 16, 1.0)
+    with pytest.raises(ValueError):
+        iseg.dcnv3_op(x, off, m, [3, 3], [1, 1], "SAME", [1, 1], 8, 16, 1.0)
+    with pytest.raises(TypeError):
+        iseg.dcnv3_op(x, off.half(), m, [3, 3], [1, 1], "SAME", [1, 1], 4, 16, 1.0)
+    with pytest.raises(TypeError):
+        iseg.dcnv3_op(x.half(), off.half(), m.half(), [3, 3], [1, 1], "SAME", [1, 1], 4, 16, 1.0)
+
+
+def test_raw_pointer_and_host_entry_points(ops):
+    _, cabi = ops
+    n, h, w, g, gc = 2, 20, 28, 4, 16
+    x, off, m, go = make_inputs(n, h, w, g, gc, seed=21)
+    kw = dict(groups=g, group_channels=gc)
+    ref_out = c_oracle.forward(x, off, m, **kw)
+    rx, roff, rm = c_oracle.backward(x, off, m, go, **kw)
+    p = cabi.make_params(x.shape, (h, w), (3, 3), (1, 1), (1, 1), (1, 1), g, gc, 1.0, cabi.F32)
+    # host buffers in, host buffers out (what a CPU-tensor caller binds)
+    out, gx, goff, gm = np.empty_like(ref_out), np.empty_like(x), np.empty_like(off), np.empty_like(m)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    cabi.check(cabi.lib.dcnv3_forward_backward_host(vp(x), vp(off), vp(m), vp(go), vp(out), vp(gx), vp(goff),
+                                                    vp(gm), ctypes.byref(p), 0))
+    assert rel_err(out, ref_out) <= TOL_F32 and rel_err(gx, rx) <= TOL_F32
+    assert rel_err(goff, roff) <= TOL_F32 and rel_err(gm, rm) <= TOL_F32
+    out2 = np.empty_like(ref_out)
+    cabi.check(cabi.lib.dcnv3_forward_host(vp(x), vp(off), vp(m), vp(out2), ctypes.byref(p), 0))
+    assert np.array_equal(out, out2)
+    # raw device pointers
+    tx, to, tm = cuda(x, off, m)
+    tout = torch.empty(n, h, w, g * gc, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    cabi.check(cabi.lib.dcnv3_forward(tx.data_ptr(), to.data_ptr(), tm.data_ptr(), tout.data_ptr(), ctypes.byref(p), st))
+    assert np.array_equal(tout.cpu().numpy(), out)
+    # too-small workspace is refused
+    rc = cabi.lib.dcnv3_backward(tx.data_ptr(), to.data_ptr(), tm.data_ptr(), tout.data_ptr(), tx.data_ptr(),
+                                 to.data_ptr(), tm.data_ptr(), tx.data_ptr(), 16, ctypes.byref(p), st)
+    assert rc == cabi.ERR_WORKSPACE
+
+
+def test_layer_matches_reference_layer(ops):
+    iseg, _ = ops
+    for name in ("c64_g4_cfs", "c32_g2_dw5"):
+        z = np.load(f"{GOLDEN}/layer_{name}.npz")
+        w = {k[2:]: z[k] for k in z.files if k.startswith("w.")}
+        for fuse in (True, False):
+            layer = iseg.DeformableConvolutionV3(
+                filters=int(z["filters"]), kernel_size=int(z["kernel_size"]),
+                depthwise_kernel_size=int(z["depthwise_kernel_size"]) or None, groups=int(z["groups"]),
+                offset_scale=float(z["offset_scale"]), center_feature_scale=bool(z["center_feature_scale"]),
+                input_channels=z["x"].shape[-1], fuse_softmax=fuse)
+            layer.load_reference_weights(w)
+            layer = layer.cuda()
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            with torch.no_grad():
+                y = layer(torch.from_numpy(z["x"]).cuda()).cpu().numpy()
+            assert rel_err(y, z["y"]) <= 5e-5, (name, fuse)  # dense / conv / LN around the op are cuBLAS / cuDNN
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_full_size_properties(ops, dtype):
+    """BASELINE config 2, stage 1 at full size (batch 16, 128x128, C=64, G=4): properties that need no
+    oracle.  out is linear in x and in mask, so with L = <out, go>:
+        <x, grad_x> = L          (adjoint identity ties forward and backward scatter)
+        <mask, grad_mask> = L
+    and the forward is linear in x."""
+    iseg, _ = ops
+    n, h, w, g, gc = 16, 128, 128, 4, 16
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    r = lambda *s: torch.randn(*s, device="cuda", generator=gen)  # noqa: E731
+    x, x2, off, go = r(n, h, w, g * gc), r(n, h, w, g * gc), r(n, h, w, g * 18), r(n, h, w, g * gc)
+    mask = torch.softmax(r(n, h, w, g, 9), -1).reshape(n, h, w, g * 9)
+    x, x2, off, go, mask = (t.to(dtype) for t in (x, x2, off, go, mask))
+    args = ([3, 3], [1, 1], "SAME", [1, 1], g, gc, 1.0)
+    xr, orq, mr = x.clone().requires_grad_(), off.clone().requires_grad_(), mask.clone().requires_grad_()
+    out = iseg.dcnv3_op(xr, orq, mr, *args)
+    out.backward(go)
+    L = (out.double() * go.double()).sum().item()
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    scale = (out.double().abs() * go.double().abs()).sum().item()
+    assert abs((x.double() * xr.grad.double()).sum().item() - L) <= tol * scale
+    assert abs((mask.double() * mr.grad.double()).sum().item() - L) <= tol * scale
+    out2 = iseg.dcnv3_op(x2, off, mask, *args)
+    out12 = iseg.dcnv3_op((x.float() * 0.5 + x2.float() * 2).to(dtype), off, mask, *args)
+    lin = out.detach().float() * 0.5 + out2.float() * 2
+    assert (out12.float() - lin).abs().max().item() <= (1e-5 if dtype == torch.float32 else 6e-2) * lin.abs().max().item()
+    # determinism at full size
+    xr2, or2, mr2 = x.clone().requires_grad_(), off.clone().requires_grad_(), mask.clone().requires_grad_()
+    iseg.dcnv3_op(xr2, or2, mr2, *args).backward(go)
+    assert torch.equal(xr.grad, xr2.grad) and torch.equal(orq.grad, or2.grad) and torch.equal(mr.grad, mr2.grad)
