@@ -61,7 +61,7 @@ static KParams derive(const dcnv3_params* p) {
     memset(&q, 0, sizeof(q));
     q.n = p->n; q.h = p->h; q.w = p->w; q.ho = p->ho; q.wo = p->wo;
     q.G = p->groups; q.gc = p->group_channels; q.P = p->kh * p->kw; q.kh = p->kh;
-    q.sh = p->sh; q.sw = p->sw; q.ph = p->ph; q.pw = p->pw;
+    q.sh = p->sh; q.sw = p->sw; q.ph = p->ph; q.pw = p->pw; q.dh = p->dh; q.dw = p->dw;
     q.hin = p->h + 2 * p->ph; q.win = p->w + 2 * p->pw;
     q.hin_f = (float)q.hin; q.win_f = (float)q.win;
     q.hm2_f = (float)(q.hin - 2); q.wm2_f = (float)(q.win - 2);
@@ -93,12 +93,14 @@ static int forward_impl(const void* x, const void* offset, const void* mask, voi
                         const dcnv3_params* p, cudaStream_t st) {
     int rc = check(p);
     if (rc) return rc;
+    if (p->n == 0) return DCNV3_OK;  // empty batch: nothing to do (data pointers may be NULL)
     if ((rc = check_ptr_align(x, "x")) || (rc = check_ptr_align(offset, "offset")) ||
         (rc = check_ptr_align(mask, "mask")) || (rc = check_ptr_align(out, "out")))
         return rc;
-    if (p->n == 0) return DCNV3_OK;
     const KParams q = derive(p);
-    cudaError_t e = launch_fwd_generic(x, offset, mask, out, q, p->dtype, st);
+    const bool tiled = tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC);
+    cudaError_t e = tiled ? launch_fwd_tiled(x, offset, mask, out, q, p->dtype, st)
+                          : launch_fwd_generic(x, offset, mask, out, q, p->dtype, st);
     if (e != cudaSuccess) return cuda_fail(e, "dcnv3_forward launch");
     return DCNV3_OK;
 }
@@ -113,12 +115,12 @@ static int backward_impl(const void* x, const void* offset, const void* mask, co
                          const dcnv3_params* p, cudaStream_t st) {
     int rc = check(p);
     if (rc) return rc;
+    if (p->n == 0) return DCNV3_OK;
     if ((rc = check_ptr_align(x, "x")) || (rc = check_ptr_align(offset, "offset")) ||
         (rc = check_ptr_align(mask, "mask")) || (rc = check_ptr_align(grad_out, "grad_out")) ||
         (rc = check_ptr_align(grad_x, "grad_x")) || (rc = check_ptr_align(grad_offset, "grad_offset")) ||
         (rc = check_ptr_align(grad_mask, "grad_mask")))
         return rc;
-    if (p->n == 0) return DCNV3_OK;
     const size_t need = backward_ws_bytes(p);
     if (ws == nullptr || ws_bytes < need)
         return fail(DCNV3_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", need, ws_bytes);

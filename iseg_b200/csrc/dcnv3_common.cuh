@@ -22,7 +22,7 @@ namespace dcnv3 {
 // Kernel-side parameter block (passed by value, lives in constant bank 0).
 struct KParams {
     int n, h, w, ho, wo, G, gc, P, kh;
-    int sh, sw, ph, pw;
+    int sh, sw, ph, pw, dh, dw;
     int hin, win;          // padded extent
     float hin_f, win_f;    // (float)H_in, (float)W_in
     float hm2_f, wm2_f;    // (float)(H_in-2), (float)(W_in-2)   (utils.py:142-143: max-1)

@@ -1,0 +1,239 @@
+// Tiled DCNv3 forward (sm_100a).  One CTA = one output tile x one group chunk of one image.
+//   1. an elected thread issues ONE TMA box load (cp.async.bulk.tensor.4d) of the chunk's input slab
+//      covering the tile's predictable footprint (+halo) into shared memory; out-of-image cells are
+//      zero-filled by the TMA unit, i.e. the zero ring of op.py:46 is never materialised;
+//   2. every lane owns one (pixel, group): 18 offsets + 9 mask values in registers, 9 taps x 4
+//      corners gathered as conflict-free LDS.128 (see dcnv3_tiled.cuh), fp32 accumulation in the
+//      reference's tap order (utils.py:195-206);
+//   3. taps whose 2x2 patch leaves the staged box (large learned offsets) fall back to L2/global
+//      loads -- correctness never depends on the halo, only speed does.
+// Algorithmic HBM bytes per (pixel, group): x 16 + out 16 + offset 18 + mask 9 elements.
+#include "dcnv3_kernels.h"
+#include "dcnv3_tiled.cuh"
+
+namespace dcnv3 {
+
+template <typename T>
+__device__ __forceinline__ const T* global_slab(const T* x, const KParams& q, int n, int yp, int xp, int g) {
+    const int y = yp - q.ph, xx = xp - q.pw;
+    if (y < 0 || y >= q.h || xx < 0 || xx >= q.w) return nullptr;
+    return x + ((((size_t)n * q.h + y) * q.w + xx) * q.G + g) * kGC;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict__ x,
+                 const T* __restrict__ offset, const T* __restrict__ mask, T* __restrict__ out,
+                 const KParams q, const TileGeom tg) {
+    using C = Chunk<T>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+
+    // ---- which tile ----
+    int b = blockIdx.x;
+    const int tx = b % tg.tiles_w; b /= tg.tiles_w;
+    const int ty = b % tg.tiles_h; b /= tg.tiles_h;
+    const int chunk = b % tg.chunks;
+    const int n = b / tg.chunks;
+    const int h0 = ty * tg.th, w0 = tx * tg.tw;
+    const int th = min(tg.th, q.ho - h0), tw = min(tg.tw, q.wo - w0);
+    // box origin in padded coordinates (output rows h walk along x, columns w along y)
+    const int cx0 = (int)floorf(nominal_x(q, h0)) - tg.halo_x;
+    const int cy0 = (int)floorf(nominal_y(q, w0)) - tg.halo_y;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, (uint32_t)(tg.bw * tg.bh * kCellBytes));
+        tma_load_4d(smem, &xmap, &bar, chunk * C::GQ * kGC, cx0 - q.pw, cy0 - q.ph, n);
+    }
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g_l = lane % C::GQ, px_l = lane / C::GQ;
+    const int g = chunk * C::GQ + g_l;
+    const int rot = Slab<T>::rot_of(px_l);
+    const unsigned char* sbase = smem + g_l * (kGC * (int)sizeof(T));
+    const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
+    const int npix = th * tw;
+    bool waited = false;
+
+    for (int p0 = warp * C::PXW; p0 < npix; p0 += (blockDim.x >> 5) * C::PXW) {
+        const int pix = p0 + px_l;
+        const bool valid = pix < npix;
+        const int ph = valid ? pix / tw : 0, pw = valid ? pix % tw : 0;
+        const int h = h0 + ph, w = w0 + pw;
+        const size_t pg = (((size_t)n * q.ho + h) * q.wo + w) * q.G + g;
+        float o[18], m[9];
+        if (valid) {
+            load_offsets_mask<T>(offset + pg * 18, mask + pg * 9, o, m);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 18; ++i) o[i] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) m[i] = 0.f;
+        }
+        if (logits) softmax9(m);
+        float ref0, ref1;
+        ref_point(q, h, w, ref0, ref1);
+        float acc[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+        if (!waited) {  // the box is needed from here on
+            mbar_wait(&bar, 0);
+            waited = true;
+        }
+#pragma unroll
+        for (int p = 0; p < kTaps; ++p) {
+            const Tap t = make_tap(q, ref0, ref1, p, o[2 * p], o[2 * p + 1]);
+            const int bx = t.x0 - cx0, by = t.y0 - cy0;
+            const bool inbox = bx >= 0 && bx + 1 < tg.bw && by >= 0 && by + 1 < tg.bh;
+            const bool live = t.alive && valid;
+            const float mm = live ? m[p] : 0.f;
+            const float wa = t.dx1 * t.dy1 * mm, wb = t.dx1 * t.dy0 * mm;   // (y0,x0) (y1,x0)
+            const float wc = t.dx0 * t.dy1 * mm, wd = t.dx0 * t.dy0 * mm;   // (y0,x1) (y1,x1)
+            if (__builtin_expect(live && !inbox, 0)) {
+                // rare: patch outside the staged box -> straight from global memory
+                const float wk[4] = {wa, wb, wc, wd};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const T* src = global_slab(x, q, n, t.y0 + (k & 1), t.x0 + (k >> 1), g);
+                    if (src == nullptr) continue;
+#pragma unroll
+                    for (int pc = 0; pc < C::NPIECE; ++pc) {
+                        float v[C::CH_PER_PIECE];
+                        load_piece<T>(src + Slab<T>::chan_of(pc, rot), v);
+#pragma unroll
+                        for (int j = 0; j < C::CH_PER_PIECE; ++j) acc[pc * C::CH_PER_PIECE + j] += v[j] * wk[k];
+                    }
+                }
+            } else {
+                const int cell = (live && inbox) ? by * tg.bw + bx : 0;
+                const float s = (live && inbox) ? 1.f : 0.f;
+                const unsigned char* a = sbase + (size_t)cell * kCellBytes;
+                float v[16];
+                Slab<T>::load(a, rot, v);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[c] += v[c] * (wa * s);
+                Slab<T>::load(a + (size_t)tg.bw * kCellBytes, rot, v);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[c] += v[c] * (wb * s);
+                Slab<T>::load(a + kCellBytes, rot, v);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[c] += v[c] * (wc * s);
+                Slab<T>::load(a + (size_t)(tg.bw + 1) * kCellBytes, rot, v);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[c] += v[c] * (wd * s);
+            }
+        }
+        if (valid) {
+            T* dst = out + pg * kGC;
+#pragma unroll
+            for (int pc = 0; pc < C::NPIECE; ++pc)
+                store_piece<T>(dst + Slab<T>::chan_of(pc, rot), acc + pc * C::CH_PER_PIECE);
+        }
+    }
+    if (!waited) mbar_wait(&bar, 0);  // never leave with a TMA in flight
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+bool make_x_tensor_map(CUtensorMap* map, const void* x, const KParams& q, int dtype, int bw, int bh) {
+    EncodeTiledFn fn = encode_fn();
+    if (fn == nullptr) return false;
+    const cuuint64_t es = dtype == DCNV3_F32 ? 4 : 2;
+    const int gq = dtype == DCNV3_F32 ? 2 : 4;
+    const cuuint64_t C = (cuuint64_t)q.G * q.gc;
+    const cuuint64_t dims[4] = {C, (cuuint64_t)q.w, (cuuint64_t)q.h, (cuuint64_t)q.n};
+    const cuuint64_t strides[3] = {C * es, (cuuint64_t)q.w * C * es, (cuuint64_t)q.h * q.w * C * es};
+    const cuuint32_t box[4] = {(cuuint32_t)(gq * kGC), (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = fn(map, dtype == DCNV3_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                          4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// Tiled kernels serve the InternImage configuration only.
+bool tiled_applicable(const KParams& q, int dtype) {
+    const int gq = dtype == DCNV3_F32 ? 2 : 4;
+    return q.P == 9 && q.kh == 3 && q.sh == 1 && q.sw == 1 && q.dh == 1 && q.dw == 1 && q.gc == kGC &&
+           q.G % gq == 0 && q.ho == q.h && q.wo == q.w && q.ph == 1 && q.pw == 1 && q.scale > 0.f &&
+           q.scale <= 16.f;
+}
+
+// Box geometry: the nominal footprint of a th x tw output tile spans (th-1)*ax columns and (tw-1)*ay
+// rows (ax = (W_in-2)/H_in, ay = (H_in-2)/W_in); taps add (1 + |offset|)*scale*(dim-2)/dim on each side
+// and the bilinear patch one more cell.  `reach` is the |offset| (reference units) served from shared
+// memory; beyond it the global fallback takes over.
+TileGeom make_geom(const KParams& q, int dtype, int th, int tw, float reach, int max_cells) {
+    TileGeom tg;
+    tg.th = min(th, q.ho);
+    tg.tw = min(tw, q.wo);
+    tg.tiles_h = (q.ho + tg.th - 1) / tg.th;
+    tg.tiles_w = (q.wo + tg.tw - 1) / tg.tw;
+    tg.chunks = q.G / (dtype == DCNV3_F32 ? 2 : 4);
+    const float ax = q.wm2_f / q.hin_f, ay = q.hm2_f / q.win_f;
+    const float rx = q.wm2_f / q.win_f, ry = q.hm2_f / q.hin_f;
+    for (;; reach *= 0.75f) {
+        tg.halo_x = (int)ceilf((1.0f + reach) * fabsf(q.scale) * rx) + 1;
+        tg.halo_y = (int)ceilf((1.0f + reach) * fabsf(q.scale) * ry) + 1;
+        tg.bw = (int)ceilf((tg.th - 1) * ax) + 2 * tg.halo_x + 2;
+        tg.bh = (int)ceilf((tg.tw - 1) * ay) + 2 * tg.halo_y + 2;
+        // never stage more than the padded image itself (+1 so that the +1 corner stays inside)
+        tg.bw = min(tg.bw, min(q.win + 1, 256));
+        tg.bh = min(tg.bh, min(q.hin + 1, 256));
+        if (tg.bw * tg.bh <= max_cells || reach < 0.05f) break;
+    }
+    return tg;
+}
+
+template <typename T>
+static cudaError_t launch_fwd_tiled_t(const void* x, const void* offset, const void* mask, void* out,
+                                      const KParams& q, int dtype, cudaStream_t st) {
+    const int max_cells = 100 * 1024 / kCellBytes;  // two CTAs per SM
+    const TileGeom tg = make_geom(q, dtype, 16, 16, 3.0f, max_cells);
+    if (tg.bw * tg.bh > max_cells) return cudaErrorInvalidConfiguration;
+    CUtensorMap map;
+    if (!make_x_tensor_map(&map, x, q, dtype, tg.bw, tg.bh)) return cudaErrorNotSupported;
+    const size_t smem = (size_t)tg.bw * tg.bh * kCellBytes;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {  // per device: the attribute lives in the context
+        cudaError_t e = cudaFuncSetAttribute(fwd_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             100 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63] = true;
+    }
+    const unsigned grid = (unsigned)((size_t)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
+    fwd_tiled_kernel<T><<<grid, 256, smem, st>>>(map, (const T*)x, (const T*)offset, (const T*)mask, (T*)out, q, tg);
+    count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fwd_tiled(const void* x, const void* offset, const void* mask, void* out,
+                             const KParams& q, int dtype, cudaStream_t st) {
+    return dtype == DCNV3_F32 ? launch_fwd_tiled_t<float>(x, offset, mask, out, q, dtype, st)
+                              : launch_fwd_tiled_t<__nv_bfloat16>(x, offset, mask, out, q, dtype, st);
+}
+
+}  // namespace dcnv3
