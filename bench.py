@@ -193,7 +193,8 @@ class Layer:
                                   cabi.F32 if dtype == "f32" else cabi.BF16)
         self.pref = ctypes.byref(self.p)
         self.ws_bytes = int(cabi.lib.dcnv3_backward_workspace_bytes(self.pref))
-        self.ws = torch.empty(max(self.ws_bytes, 256), dtype=torch.uint8, device=device)
+        self.ws = torch.zeros(max(self.ws_bytes, 256), dtype=torch.uint8, device=device)
+        self.p.flags |= cabi.FLAG_WORKSPACE_ZEROED  # zeroed once; dcnv3_backward leaves it zeroed
         self.shape = (h, w, c, g)
         self.fwd_args = [ctypes.c_void_p(t.data_ptr()) for t in (self.x, self.off, self.mask, self.out)]
         self.bwd_args = [ctypes.c_void_p(t.data_ptr()) for t in

@@ -53,6 +53,9 @@ typedef enum { DCNV3_F32 = 0, DCNV3_BF16 = 1 } dcnv3_dtype;
 /* mask argument holds pre-softmax logits; softmax over P is fused (dcn_v3.py:120-123) and
    grad_mask is the gradient w.r.t. the logits */
 #define DCNV3_FLAG_MASK_LOGITS 1u
+/* backward only: the caller guarantees the workspace is all-zero on entry (e.g. it was zeroed once
+   and only ever used by dcnv3_backward, which leaves it zeroed); saves a memset of the workspace */
+#define DCNV3_FLAG_WORKSPACE_ZEROED 4u
 /* testing aid: bypass the shared-memory tiled kernels and run the generic kernels */
 #define DCNV3_FLAG_FORCE_GENERIC 2u
 

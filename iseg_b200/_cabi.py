@@ -14,6 +14,8 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "lib
 
 F32, BF16 = 0, 1
 FLAG_MASK_LOGITS = 1
+FLAG_FORCE_GENERIC = 2
+FLAG_WORKSPACE_ZEROED = 4
 
 ERR_DTYPE, ERR_SHAPE, ERR_LAYOUT, ERR_DEVICE, ERR_CUDA, ERR_WORKSPACE, ERR_ARGUMENT = range(-1, -8, -1)
 
@@ -98,6 +100,22 @@ def _stream(t):
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+_ws_cache = {}
+
+
+def _workspace(device, nbytes):
+    """Backward workspace, zeroed once and kept per (device, stream, size): dcnv3_backward leaves it
+    zeroed, so later calls on the same stream skip the memset (DCNV3_FLAG_WORKSPACE_ZEROED)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, int(nbytes))
+    ws = _ws_cache.get(key)
+    if ws is None:
+        if len(_ws_cache) >= 64:
+            _ws_cache.clear()
+        ws = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
 def forward(x, offset, mask, kernel_size, strides, pad, dilation_rate, groups, group_channels,
             offset_scale, flags=0):
     """dcnv3_forward_dlpack on torch CUDA tensors; returns a fresh output tensor."""
@@ -123,12 +141,12 @@ def backward(x, offset, mask, grad_out, kernel_size, strides, pad, dilation_rate
     p = make_params(x.shape, offset.shape[1:3], kernel_size, strides, pad, dilation_rate, groups,
                     group_channels, offset_scale, dt, flags)
     ws_bytes = int(lib.dcnv3_backward_workspace_bytes(ctypes.byref(p)))
-    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=x.device)
+    ws = _workspace(x.device, ws_bytes)
     caps = [_dl(t) for t in (x, offset, mask, grad_out, gx, goff, gm, ws)]
     with torch.cuda.device(x.device):
         rc = lib.dcnv3_backward_dlpack(
             *[c[1] for c in caps], kernel_size[0], kernel_size[1], strides[0], strides[1], pad[0],
             pad[1], dilation_rate[0], dilation_rate[1], groups, group_channels, float(offset_scale),
-            flags, _stream(x))
+            flags | FLAG_WORKSPACE_ZEROED, _stream(x))
     check(rc)
     return gx, goff, gm

@@ -64,6 +64,7 @@ static KParams derive(const dcnv3_params* p) {
     q.sh = p->sh; q.sw = p->sw; q.ph = p->ph; q.pw = p->pw; q.dh = p->dh; q.dw = p->dw;
     q.hin = p->h + 2 * p->ph; q.win = p->w + 2 * p->pw;
     q.hin_f = (float)q.hin; q.win_f = (float)q.win;
+    q.rhin_f = 1.0f / q.hin_f; q.rwin_f = 1.0f / q.win_f;
     q.hm2_f = (float)(q.hin - 2); q.wm2_f = (float)(q.win - 2);
     q.y0c = (float)((p->dh * (p->kh - 1)) / 2 + 0.5f);
     q.x0c = (float)((p->dw * (p->kw - 1)) / 2 + 0.5f);
@@ -107,7 +108,8 @@ static int forward_impl(const void* x, const void* offset, const void* mask, voi
 
 static size_t backward_ws_bytes(const dcnv3_params* p) {
     const KParams q = derive(p);
-    return bwd_generic_workspace_bytes(q);
+    const size_t a = bwd_generic_workspace_bytes(q), b = bwd_tiled_workspace_bytes(q);
+    return a > b ? a : b;
 }
 
 static int backward_impl(const void* x, const void* offset, const void* mask, const void* grad_out,
@@ -126,8 +128,11 @@ static int backward_impl(const void* x, const void* offset, const void* mask, co
         return fail(DCNV3_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", need, ws_bytes);
     if ((rc = check_ptr_align(ws, "workspace", 256))) return rc;
     const KParams q = derive(p);
-    cudaError_t e = launch_bwd_generic(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q,
-                                       p->dtype, st);
+    const bool tiled = tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC);
+    cudaError_t e =
+        tiled ? launch_bwd_tiled(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, p->dtype,
+                                 (p->flags & DCNV3_FLAG_WORKSPACE_ZEROED) != 0, st)
+              : launch_bwd_generic(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, p->dtype, st);
     if (e != cudaSuccess) return cuda_fail(e, "dcnv3_backward launch");
     return DCNV3_OK;
 }

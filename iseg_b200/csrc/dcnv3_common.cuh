@@ -25,6 +25,7 @@ struct KParams {
     int sh, sw, ph, pw, dh, dw;
     int hin, win;          // padded extent
     float hin_f, win_f;    // (float)H_in, (float)W_in
+    float rhin_f, rwin_f;  // RN(1/H_in), RN(1/W_in): seeds of the correctly rounded divisions
     float hm2_f, wm2_f;    // (float)(H_in-2), (float)(W_in-2)   (utils.py:142-143: max-1)
     float y0c, x0c;        // (d*(k-1))//2 + 0.5                (utils.py:29-33)
     float scale;           // offset_scale
@@ -40,11 +41,19 @@ struct Tap {
     bool alive;        // false <=> a clipped corner pair coincides => the tap contributes exactly 0
 };
 
+// a / b, correctly rounded, from r = RN(1/b): q0 = RN(a*r); q = RN(q0 + (a - q0*b)*r)  (the tail of
+// the IEEE division sequence without its special-case checks; b is a small positive integer here).
+__device__ __forceinline__ float div_rn(float a, float b, float r) {
+    const float q0 = __fmul_rn(a, r);
+    const float e = __fmaf_rn(-q0, b, a);
+    return __fmaf_rn(e, r, q0);
+}
+
 // One normalised coordinate -> pixel coordinate, exactly as op.py:82-87 + utils.py:142.
 __device__ __forceinline__ float pixel_coord(float ref, float gs, float off, float scale, float dim_f,
-                                             float dim_m2_f) {
+                                             float rdim_f, float dim_m2_f) {
     float loc = __fadd_rn(ref, gs);
-    loc = __fadd_rn(loc, __fdiv_rn(__fmul_rn(off, scale), dim_f));
+    loc = __fadd_rn(loc, div_rn(__fmul_rn(off, scale), dim_f, rdim_f));
     const float g = __fsub_rn(__fmul_rn(2.0f, loc), 1.0f);
     return __fmul_rn(0.5f, __fmul_rn(__fadd_rn(g, 1.0f), dim_m2_f));
 }
@@ -56,25 +65,44 @@ __device__ __forceinline__ void ref_point(const KParams& q, int h, int w, float&
     ref1 = __fdiv_rn(__fadd_rn((float)(w * q.sw), q.x0c), q.win_f);
 }
 
+// One axis of a tap: clipped lower corner index, the two deltas from the clipped corners
+// (utils.py:146-166) and whether the corner pair is distinct.  Everything stays in the float domain
+// except the final index conversion, so huge or non-finite coordinates need no special casing: they
+// fail the range test and the tap is dead (contributes exactly 0).
+struct Axis {
+    int i0;
+    float d0, d1;
+    bool alive;
+};
+__device__ __forceinline__ Axis make_axis(float coord, float max_f /* dim-1 */) {
+    Axis a;
+    const float f = floorf(coord);
+    a.alive = (f >= 0.0f) && (f < max_f);          // clipped corners coincide otherwise
+    const float c0 = fminf(fmaxf(f, 0.0f), max_f);
+    const float c1 = fminf(fmaxf(f + 1.0f, 0.0f), max_f);
+    a.i0 = a.alive ? (int)c0 : 0;
+    a.d0 = a.alive ? __fsub_rn(coord, c0) : 0.0f;
+    a.d1 = a.alive ? __fsub_rn(c1, coord) : 0.0f;
+    return a;
+}
+__device__ __forceinline__ Axis axis_x(const KParams& q, float ref0, int p, float offx) {
+    return make_axis(pixel_coord(ref0, q.gs0[p], offx, q.scale, q.win_f, q.rwin_f, q.wm2_f), q.wm2_f + 1.0f);
+}
+__device__ __forceinline__ Axis axis_y(const KParams& q, float ref1, int p, float offy) {
+    return make_axis(pixel_coord(ref1, q.gs1[p], offy, q.scale, q.hin_f, q.rhin_f, q.hm2_f), q.hm2_f + 1.0f);
+}
+
 __device__ __forceinline__ Tap make_tap(const KParams& q, float ref0, float ref1, int p, float offx,
                                         float offy) {
+    const Axis ax = axis_x(q, ref0, p, offx), ay = axis_y(q, ref1, p, offy);
     Tap t;
-    const float xq = pixel_coord(ref0, q.gs0[p], offx, q.scale, q.win_f, q.wm2_f);
-    const float yq = pixel_coord(ref1, q.gs1[p], offy, q.scale, q.hin_f, q.hm2_f);
-    // clamp before the int conversion (huge offsets); NaN falls to -2 => dead
-    const float fxq = fminf(fmaxf(floorf(xq), -2.0f), q.win_f);
-    const float fyq = fminf(fmaxf(floorf(yq), -2.0f), q.hin_f);
-    const int ix = (int)fxq, iy = (int)fyq;
-    // utils.py:152-155: both corners clipped to [0, max]; they coincide iff ix < 0 or ix >= max
-    t.alive = (ix >= 0) && (ix < q.win - 1) && (iy >= 0) && (iy < q.hin - 1);
-    t.x0 = min(max(ix, 0), q.win - 1);
-    t.y0 = min(max(iy, 0), q.hin - 1);
-    const int x1 = min(max(ix + 1, 0), q.win - 1);
-    const int y1 = min(max(iy + 1, 0), q.hin - 1);
-    t.dx0 = __fsub_rn(xq, (float)t.x0);  // utils.py:163-166
-    t.dx1 = __fsub_rn((float)x1, xq);
-    t.dy0 = __fsub_rn(yq, (float)t.y0);
-    t.dy1 = __fsub_rn((float)y1, yq);
+    t.alive = ax.alive && ay.alive;
+    t.x0 = ax.i0;
+    t.y0 = ay.i0;
+    t.dx0 = t.alive ? ax.d0 : 0.0f;
+    t.dx1 = t.alive ? ax.d1 : 0.0f;
+    t.dy0 = t.alive ? ay.d0 : 0.0f;
+    t.dy1 = t.alive ? ay.d1 : 0.0f;
     return t;
 }
 
@@ -84,6 +112,7 @@ struct Elem;
 template <>
 struct Elem<float> {
     static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
+    static __device__ __forceinline__ float ld_plain(const float* p) { return *p; }
     static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
     static __device__ __forceinline__ float4 ld4(const float* p) {
         return __ldg(reinterpret_cast<const float4*>(p));
@@ -97,6 +126,7 @@ struct Elem<__nv_bfloat16> {
     static __device__ __forceinline__ float ld(const __nv_bfloat16* p) {
         return __bfloat162float(__ldg(p));
     }
+    static __device__ __forceinline__ float ld_plain(const __nv_bfloat16* p) { return __bfloat162float(*p); }
     static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) {
         *p = __float2bfloat16_rn(v);
     }
@@ -138,6 +168,16 @@ __device__ __forceinline__ int fixed_exponent(const WsHeader* hd, bool mask_is_p
     frexpf(bound, &ex);  // bound = f * 2^ex, f in [0.5, 1)  =>  bound < 2^ex
     int e = 46 - ex;
     return max(min(e, 120), -120);
+}
+
+// frexp exponent of max|grad_out| (amax < 2^ex), clamped so that every derived power of two is a
+// normal float; 30 (=> unit scale) when the maximum is 0 or not finite.
+__device__ __forceinline__ int fixed_exponent_raw(const WsHeader* hd) {
+    const float a = __uint_as_float(hd->amax_go_bits);
+    if (!(a > 0.0f) || !(a < 3.0e38f)) return 30;
+    int ex;
+    frexpf(a, &ex);
+    return max(min(ex, 120), -90);
 }
 
 __device__ __forceinline__ long long to_fixed(float v, int e) {

@@ -20,4 +20,9 @@ bool tiled_applicable(const KParams& q, int dtype);
 cudaError_t launch_fwd_tiled(const void* x, const void* offset, const void* mask, void* out,
                              const KParams& q, int dtype, cudaStream_t st);
 
+size_t bwd_tiled_workspace_bytes(const KParams& q);
+cudaError_t launch_bwd_tiled(const void* x, const void* offset, const void* mask, const void* grad_out,
+                             void* grad_x, void* grad_offset, void* grad_mask, void* ws, const KParams& q,
+                             int dtype, bool ws_clean, cudaStream_t st);
+
 }  // namespace dcnv3

@@ -26,6 +26,7 @@ struct Chunk {
     static constexpr int PXW = 32 / GQ;                            // pixels per warp iteration
     static constexpr int NPIECE = kGC * (int)sizeof(T) / 16;       // 16-byte pieces per slab: 4 / 2
     static constexpr int CH_PER_PIECE = 16 / (int)sizeof(T);       // 4 / 8
+    static constexpr int PAIRS = CH_PER_PIECE / 2;                 // packed fp32 pairs per piece: 2 / 4
 };
 
 // Geometry of one launch (host-computed, identical for every CTA).
@@ -36,6 +37,10 @@ struct TileGeom {
     int halo_x, halo_y;    // cells kept on each side of the nominal footprint
     int chunks;            // G / GQ
 };
+
+// host helpers implemented in dcnv3_tiled_fwd.cu
+TileGeom make_geom(const KParams& q, int dtype, int th, int tw, float reach, int max_cells);
+bool make_x_tensor_map(CUtensorMap* map, const void* x, const KParams& q, int dtype, int bw, int bh);
 
 // Nominal sampling position of output row h / column w (zero offset, centre tap), reference
 // arithmetic collapsed: xq = ((h + 1.5) / H_in) * (W_in - 2)  -- note H_in under h: the reference
@@ -88,7 +93,26 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
-// ---- one corner slab -> 16 fp32 values in the lane's rotated channel order ------------------------
+// ---- packed fp32 pairs: Blackwell issues two fp32 FMAs per instruction (PTX fma.rn.f32x2, SASS FFMA2) ----
+typedef unsigned long long f2;  // {lo, hi} = two consecutive channels
+
+__device__ __forceinline__ f2 pack2(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo_of(f2 a) { return __uint_as_float((unsigned)a); }
+__device__ __forceinline__ float hi_of(f2 a) { return __uint_as_float((unsigned)(a >> 32)); }
+// acc += v * {w, w}
+__device__ __forceinline__ void ffma2s(f2& acc, f2 v, float w) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(v), "l"(pack2(w, w)));
+}
+// acc += v * g
+__device__ __forceinline__ void ffma2v(f2& acc, f2 v, f2 g) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(v), "l"(g));
+}
+
+// ---- one corner slab -> 8 packed pairs (16 channels) in the lane's rotated channel order ---------
 // fp32: piece k of the loop is physical quad (k + px) & 3; bf16: physical half (k + px) & 1.
 template <typename T>
 struct Slab;
@@ -96,11 +120,12 @@ struct Slab;
 template <>
 struct Slab<float> {
     // base = the lane's group slab inside a cell of the staged box; rot = px & 3
-    static __device__ __forceinline__ void load(const unsigned char* base, int rot, float (&v)[16]) {
+    static __device__ __forceinline__ void load(const unsigned char* base, int rot, f2 (&v)[8]) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float4 r = *reinterpret_cast<const float4*>(base + (((k + rot) & 3) << 4));
-            v[4 * k] = r.x; v[4 * k + 1] = r.y; v[4 * k + 2] = r.z; v[4 * k + 3] = r.w;
+            const ulonglong2 r = *reinterpret_cast<const ulonglong2*>(base + (((k + rot) & 3) << 4));
+            v[2 * k] = r.x;
+            v[2 * k + 1] = r.y;
         }
     }
     static __device__ __forceinline__ int rot_of(int px) { return px & 3; }
@@ -108,98 +133,85 @@ struct Slab<float> {
     static __device__ __forceinline__ int chan_of(int k, int rot) { return ((k + rot) & 3) * 4; }
 };
 
+__device__ __forceinline__ f2 bf16x2_to_f2(unsigned r) {
+    return pack2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u));
+}
+
 template <>
 struct Slab<__nv_bfloat16> {
-    static __device__ __forceinline__ void load(const unsigned char* base, int rot, float (&v)[16]) {
+    static __device__ __forceinline__ void load(const unsigned char* base, int rot, f2 (&v)[8]) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const uint4 rr = *reinterpret_cast<const uint4*>(base + (((k + rot) & 1) << 4));
-            const uint32_t r0 = rr.x, r1 = rr.y, r2 = rr.z, r3 = rr.w;
-            v[8 * k + 0] = __uint_as_float(r0 << 16);
-            v[8 * k + 1] = __uint_as_float(r0 & 0xffff0000u);
-            v[8 * k + 2] = __uint_as_float(r1 << 16);
-            v[8 * k + 3] = __uint_as_float(r1 & 0xffff0000u);
-            v[8 * k + 4] = __uint_as_float(r2 << 16);
-            v[8 * k + 5] = __uint_as_float(r2 & 0xffff0000u);
-            v[8 * k + 6] = __uint_as_float(r3 << 16);
-            v[8 * k + 7] = __uint_as_float(r3 & 0xffff0000u);
+            const uint4 r = *reinterpret_cast<const uint4*>(base + (((k + rot) & 1) << 4));
+            v[4 * k + 0] = bf16x2_to_f2(r.x);
+            v[4 * k + 1] = bf16x2_to_f2(r.y);
+            v[4 * k + 2] = bf16x2_to_f2(r.z);
+            v[4 * k + 3] = bf16x2_to_f2(r.w);
         }
     }
     static __device__ __forceinline__ int rot_of(int px) { return px & 1; }
     static __device__ __forceinline__ int chan_of(int k, int rot) { return ((k + rot) & 1) * 8; }
 };
 
-// global 16-byte piece <-> fp32 registers
+// global 16-byte piece <-> packed pairs (PAIRS = 2 for fp32, 4 for bf16)
 template <typename T>
-__device__ __forceinline__ void load_piece(const T* p, float* v);
+__device__ __forceinline__ void load_piece(const T* p, f2* v);
 template <>
-__device__ __forceinline__ void load_piece<float>(const float* p, float* v) {
-    const float4 r = __ldg(reinterpret_cast<const float4*>(p));
-    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+__device__ __forceinline__ void load_piece<float>(const float* p, f2* v) {
+    const ulonglong2 r = __ldg(reinterpret_cast<const ulonglong2*>(p));
+    v[0] = r.x; v[1] = r.y;
 }
 template <>
-__device__ __forceinline__ void load_piece<__nv_bfloat16>(const __nv_bfloat16* p, float* v) {
+__device__ __forceinline__ void load_piece<__nv_bfloat16>(const __nv_bfloat16* p, f2* v) {
     const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
-    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
-    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
-    v[4] = __uint_as_float(r.z << 16); v[5] = __uint_as_float(r.z & 0xffff0000u);
-    v[6] = __uint_as_float(r.w << 16); v[7] = __uint_as_float(r.w & 0xffff0000u);
-}
-template <typename T>
-__device__ __forceinline__ void store_piece(T* p, const float* v);
-template <>
-__device__ __forceinline__ void store_piece<float>(float* p, const float* v) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    v[0] = bf16x2_to_f2(r.x); v[1] = bf16x2_to_f2(r.y); v[2] = bf16x2_to_f2(r.z); v[3] = bf16x2_to_f2(r.w);
 }
 __device__ __forceinline__ unsigned pack_bf16x2(float a, float b) {
     const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const unsigned*>(&t);
 }
+template <typename T>
+__device__ __forceinline__ void store_piece(T* p, const f2* v);
 template <>
-__device__ __forceinline__ void store_piece<__nv_bfloat16>(__nv_bfloat16* p, const float* v) {
+__device__ __forceinline__ void store_piece<float>(float* p, const f2* v) {
+    *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(v[0], v[1]);
+}
+template <>
+__device__ __forceinline__ void store_piece<__nv_bfloat16>(__nv_bfloat16* p, const f2* v) {
     uint4 r;
-    r.x = pack_bf16x2(v[0], v[1]); r.y = pack_bf16x2(v[2], v[3]);
-    r.z = pack_bf16x2(v[4], v[5]); r.w = pack_bf16x2(v[6], v[7]);
+    r.x = pack_bf16x2(lo_of(v[0]), hi_of(v[0])); r.y = pack_bf16x2(lo_of(v[1]), hi_of(v[1]));
+    r.z = pack_bf16x2(lo_of(v[2]), hi_of(v[2])); r.w = pack_bf16x2(lo_of(v[3]), hi_of(v[3]));
     *reinterpret_cast<uint4*>(p) = r;
 }
 
-// The lane's 18 offsets and 9 mask values (one (pixel, group)) -> registers.
+// Per-tap inputs of one (pixel, group): the offset pair and the mask value (or logit) of tap p.
 template <typename T>
-__device__ __forceinline__ void load_offsets_mask(const T* off, const T* msk, float (&o)[18], float (&m)[9]);
+__device__ __forceinline__ void load_tap_inputs(const T* off, const T* msk, int p, float& ox, float& oy, float& ml);
 template <>
-__device__ __forceinline__ void load_offsets_mask<float>(const float* off, const float* msk, float (&o)[18],
-                                                         float (&m)[9]) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        const float2 r = __ldg(reinterpret_cast<const float2*>(off) + i);
-        o[2 * i] = r.x; o[2 * i + 1] = r.y;
-    }
-#pragma unroll
-    for (int i = 0; i < 9; ++i) m[i] = __ldg(msk + i);
+__device__ __forceinline__ void load_tap_inputs<float>(const float* off, const float* msk, int p, float& ox,
+                                                       float& oy, float& ml) {
+    const float2 r = __ldg(reinterpret_cast<const float2*>(off) + p);
+    ox = r.x; oy = r.y;
+    ml = __ldg(msk + p);
 }
 template <>
-__device__ __forceinline__ void load_offsets_mask<__nv_bfloat16>(const __nv_bfloat16* off, const __nv_bfloat16* msk,
-                                                                 float (&o)[18], float (&m)[9]) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {  // 18 bf16 = 36 B per (pixel, group): 4-byte aligned pairs
-        const unsigned r = __ldg(reinterpret_cast<const unsigned*>(off) + i);
-        o[2 * i] = __uint_as_float(r << 16); o[2 * i + 1] = __uint_as_float(r & 0xffff0000u);
-    }
-#pragma unroll
-    for (int i = 0; i < 9; ++i) m[i] = __bfloat162float(__ldg(msk + i));
+__device__ __forceinline__ void load_tap_inputs<__nv_bfloat16>(const __nv_bfloat16* off, const __nv_bfloat16* msk,
+                                                               int p, float& ox, float& oy, float& ml) {
+    const unsigned r = __ldg(reinterpret_cast<const unsigned*>(off) + p);  // 2 bf16, 4-byte aligned
+    ox = __uint_as_float(r << 16); oy = __uint_as_float(r & 0xffff0000u);
+    ml = __bfloat162float(__ldg(msk + p));
 }
 
-// softmax over the 9 taps, in registers (dcn_v3.py:120-123)
-__device__ __forceinline__ void softmax9(float (&m)[9]) {
-    float mx = m[0];
+// softmax over the 9 tap logits of one (pixel, group) (dcn_v3.py:120-123): max and 1/sum
+template <typename T>
+__device__ __forceinline__ void softmax_stats9(const T* msk, float& mx, float& inv_sum) {
+    mx = -INFINITY;
 #pragma unroll
-    for (int i = 1; i < 9; ++i) mx = fmaxf(mx, m[i]);
+    for (int p = 0; p < kTaps; ++p) mx = fmaxf(mx, Elem<T>::ld(msk + p));
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { m[i] = expf(m[i] - mx); s += m[i]; }
-    const float inv = 1.0f / s;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) m[i] *= inv;
+    for (int p = 0; p < kTaps; ++p) s += expf(Elem<T>::ld(msk + p) - mx);
+    inv_sum = 1.0f / s;
 }
 
 }  // namespace dcnv3

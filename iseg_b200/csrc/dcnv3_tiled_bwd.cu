@@ -1,0 +1,617 @@
+// Tiled DCNv3 backward (sm_100a): two kernels, both deterministic.
+//
+//  bwd_gather_kernel  -- grad_offset and grad_mask.  Same structure as the tiled forward: one CTA per
+//      output tile x group chunk, the chunk's input box staged by one TMA load, every lane owns one
+//      (pixel, group), gathers the 4 corner slabs of every tap (conflict-free rotated LDS.128) and forms
+//      the four dot products <grad_out, I_k> with packed FFMA2; from them the two gradients
+//      (SURVEY.md App. A.2).  No cross-lane reduction, no atomics.
+//
+//  bwd_scatter_kernel -- grad_x, OWNER COMPUTES.  One CTA = one 16x16 tile J of INPUT pixels x one group
+//      chunk.  Shared memory holds an int32 accumulator for exactly the cells of J.  The CTA walks every
+//      output pixel whose taps can plausibly reach J (home pixels + a margin) and adds
+//          q = floor(G[c] * Wk / 2^32) + b        G = grad_out, Wk = mask * bilinear weight (fixed point),
+//                                                 b = parity bit that makes the truncation unbiased
+//      with shared-memory integer atomics (ATOMS.ADD; measured 31.6 updates/clk/SM when conflict free,
+//      tools/microbench2.cu; rows and cells of the accumulator have odd pitches so that neighbouring
+//      pixels fall into different banks).  Integer addition is associative: the result is bitwise
+//      independent of warp scheduling.  Every cell of J is owned by exactly one CTA: grad_x is written
+//      once, there is no cross-CTA reduction and no float atomic anywhere.
+//
+//  Overflow / far taps -- every landing also adds ceil(|Wk|*1024) to a per-(cell, group) counter; while
+//      that sum stays <= 8*1024 the int32 accumulator provably cannot wrap.  Cells that exceed it
+//      ("hot", only with adversarial inputs) are zeroed at flush and recomputed exactly by
+//      redo_hot_kernel with 64-bit integer global atomics; taps of home pixels that land in a tile
+//      whose owner does not visit the pixel (|offset| beyond the margin) take the same 64-bit side
+//      path directly.  The side buffer uses the SAME integers q and is merged by merge_far_kernel; which
+//      path a contribution takes is a deterministic function of the inputs.
+//
+// The common scale comes from max|grad_out| (amax_go_kernel): G = round(go * 2^eg), 2^29 <= max|G| < 2^30.
+#include "dcnv3_kernels.h"
+#include "dcnv3_tiled.cuh"
+
+namespace dcnv3 {
+
+constexpr int TJ = 16;             // input tile edge (cells)
+constexpr int TJP = 17;            // accumulator row pitch in cells (odd: consecutive rows -> different banks)
+constexpr int kBudget = 8 * 1024;  // sum of ceil(|Wk| * 1024) allowed in the int32 accumulator
+constexpr int kWShift = 29;        // Wk fixed point: round(Wk * 2^29), |Wk| < 4
+
+struct BwdGeom {
+    int tiles_x, tiles_y;  // tiles of TJ x TJ un-padded input pixels
+    int chunks;
+    int margin;            // cells by which the scatter kernel looks beyond J for source pixels
+};
+
+struct FarWs {
+    WsHeader* hd;
+    unsigned char* dirty;         // [N][H][W][G]  (pixel, group) has side-buffer contributions
+    int* redo;                    // [N][chunks][tiles_y][tiles_x]  scatter CTA found hot cells
+    unsigned long long* acc64;    // [N][H][W][C] fixed point, zero outside a call
+};
+
+template <typename T>
+struct AccLayout {
+    static constexpr int GQ = Chunk<T>::GQ;
+    static constexpr int CELL = GQ * kGC + 1;  // ints per cell (+1: odd pitch)
+    static constexpr int CELLS = TJ * TJP;
+    static constexpr int ACC_INTS = CELLS * CELL;
+    static constexpr int WSUM_INTS = CELLS * GQ;
+    static __device__ __forceinline__ int cell(int cx, int cy) { return cy * TJP + cx; }
+};
+
+// un-padded nominal input column of output row h (may be -1 at the border), integer arithmetic so
+// that every CTA agrees exactly:  floor((2h+3) * (W_in-2) / (2 H_in)) - 1
+__device__ __forceinline__ int nominal_ux(const KParams& q, int h) {
+    return (int)(((long long)(2 * h + 3) * (q.win - 2)) / (2 * q.hin)) - q.pw;
+}
+__device__ __forceinline__ int nominal_uy(const KParams& q, int w) {
+    return (int)(((long long)(2 * w + 3) * (q.hin - 2)) / (2 * q.win)) - q.ph;
+}
+// smallest index i in [0, n] with nominal(i) >= a   (nominal is non-decreasing)
+template <typename F>
+__device__ __forceinline__ int first_ge(F nominal, int n, int a, long long num_scale, long long den) {
+    // floor((2i+3)*S / (2D)) - 1 >= a   <=>   i >= ((a+1)*2D - 3S) / (2S); closed form, then fix up
+    long long i = (2 * (long long)(a + 1) * den - 3 * num_scale + 2 * num_scale - 1) / (2 * num_scale);
+    if (i < 0) i = 0;
+    if (i > n) i = n;
+    int r = (int)i;
+    while (r > 0 && nominal(r - 1) >= a) --r;
+    while (r < n && nominal(r) < a) ++r;
+    return r;
+}
+
+struct Range { int lo, hi; };
+
+// source range along one axis for tile index j: every i with
+//   nominal(i) in [j*TJ - margin, j*TJ + TJ + margin)   or   home(i) == j
+template <typename F>
+__device__ __forceinline__ Range window_range(F nominal, int n, int j, int ntiles, int margin, long long num,
+                                              long long den) {
+    Range r;
+    r.lo = (j == 0) ? 0 : first_ge(nominal, n, j * TJ - margin, num, den);
+    r.hi = (j == ntiles - 1) ? n : first_ge(nominal, n, j * TJ + TJ + margin, num, den);
+    return r;
+}
+template <typename F>
+__device__ __forceinline__ Range home_range(F nominal, int n, int j, int ntiles, long long num, long long den) {
+    Range r;
+    r.lo = (j == 0) ? 0 : first_ge(nominal, n, j * TJ, num, den);
+    r.hi = (j == ntiles - 1) ? n : first_ge(nominal, n, j * TJ + TJ, num, den);
+    return r;
+}
+// tile indices j whose owner visits a source index with nominal value u: [lo, hi]  (the complement is
+// "far").  Mirrors window_range: u in [j*TJ - margin, j*TJ + TJ + margin), the first tile also takes
+// u < 0 and the last one u >= extent.
+__device__ __forceinline__ Range covering_tiles(int u, int ntiles, int margin) {
+    Range r;
+    int lo = u - TJ - margin + 1;  // need j*TJ >= lo  (ceil division)
+    lo = lo <= 0 ? 0 : (lo + TJ - 1) / TJ;
+    int hi = u + margin;           // need j*TJ <= hi  (floor division)
+    hi = hi < 0 ? 0 : hi / TJ;
+    r.lo = min(lo, ntiles - 1);
+    r.hi = min(hi, ntiles - 1);
+    return r;
+}
+
+__device__ __forceinline__ void tile_ranges(const KParams& q, const BwdGeom& bg, int jx, int jy, Range& home_h,
+                                            Range& home_w, Range& win_h, Range& win_w) {
+    auto nx = [&](int h) { return nominal_ux(q, h); };
+    auto ny = [&](int w) { return nominal_uy(q, w); };
+    // output rows h walk along input x, output columns w along input y
+    home_h = home_range(nx, q.ho, jx, bg.tiles_x, q.win - 2, q.hin);
+    home_w = home_range(ny, q.wo, jy, bg.tiles_y, q.hin - 2, q.win);
+    win_h = window_range(nx, q.ho, jx, bg.tiles_x, bg.margin, q.win - 2, q.hin);
+    win_w = window_range(ny, q.wo, jy, bg.tiles_y, bg.margin, q.hin - 2, q.win);
+}
+
+template <typename T>
+__device__ __forceinline__ const T* global_slab_b(const T* x, const KParams& q, int n, int yp, int xp, int g) {
+    const int y = yp - q.ph, xx = xp - q.pw;
+    if (y < 0 || y >= q.h || xx < 0 || xx >= q.w) return nullptr;
+    return x + ((((size_t)n * q.h + y) * q.w + xx) * q.G + g) * kGC;
+}
+
+// grad_out of one (pixel, group) in fixed point: G[c] = round(go[c] * 2^eg)
+template <typename T>
+__device__ __forceinline__ void load_fixed_point_go(const T* go, float sg, int (&G)[16]) {
+    using C = Chunk<T>;
+    f2 gf[8];
+#pragma unroll
+    for (int pc = 0; pc < C::NPIECE; ++pc) load_piece<T>(go + pc * C::CH_PER_PIECE, gf + pc * C::PAIRS);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        G[2 * c] = __float2int_rn(lo_of(gf[c]) * sg);
+        G[2 * c + 1] = __float2int_rn(hi_of(gf[c]) * sg);
+    }
+}
+
+// =====================================================================================================
+// grad_offset / grad_mask
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict__ x,
+                  const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
+                  T* __restrict__ grad_offset, T* __restrict__ grad_mask, const KParams q, const TileGeom tg) {
+    using C = Chunk<T>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ float park[kTaps][256];  // fused-softmax path: dL/dm_p of the lane's taps until the Jacobian sweep
+
+    int b = blockIdx.x;
+    const int tx = b % tg.tiles_w; b /= tg.tiles_w;
+    const int ty = b % tg.tiles_h; b /= tg.tiles_h;
+    const int chunk = b % tg.chunks;
+    const int n = b / tg.chunks;
+    const int h0 = ty * tg.th, w0 = tx * tg.tw;
+    const int th = min(tg.th, q.ho - h0), tw = min(tg.tw, q.wo - w0);
+    const int cx0 = max(0, min((int)floorf(nominal_x(q, h0)) - tg.halo_x, q.win - tg.bw));
+    const int cy0 = max(0, min((int)floorf(nominal_y(q, w0)) - tg.halo_y, q.hin - tg.bh));
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, (uint32_t)(tg.bw * tg.bh * kCellBytes));
+        tma_load_4d(smem, &xmap, &bar, chunk * C::GQ * kGC, cx0 - q.pw, cy0 - q.ph, n);
+    }
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g_l = lane % C::GQ, px_l = lane / C::GQ;
+    const int g = chunk * C::GQ + g_l;
+    const int rot = Slab<T>::rot_of(px_l);
+    const unsigned char* sbase = smem + g_l * (kGC * (int)sizeof(T));
+    const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
+    const int npix = th * tw;
+    bool waited = false;
+
+    for (int p0 = warp * C::PXW; p0 < npix; p0 += nwarps * C::PXW) {
+        const bool valid = p0 + px_l < npix;
+        const int pix = min(p0 + px_l, npix - 1);
+        const int h = h0 + pix / tw, w = w0 + pix % tw;
+        const size_t pg = (((size_t)n * q.ho + h) * q.wo + w) * q.G + g;
+        const T* offp = offset + pg * 18;
+        const T* mskp = mask + pg * 9;
+        T* goff = grad_offset + pg * 18;
+        T* gmsk = grad_mask + pg * 9;
+        f2 go[8];
+#pragma unroll
+        for (int pc = 0; pc < C::NPIECE; ++pc)
+            load_piece<T>(grad_out + pg * kGC + Slab<T>::chan_of(pc, rot), go + pc * C::PAIRS);
+        float mx = 0.f, inv_sum = 1.f;
+        if (logits) softmax_stats9<T>(mskp, mx, inv_sum);
+        float ref0, ref1;
+        ref_point(q, h, w, ref0, ref1);
+        float ox, oy, ml;
+        load_tap_inputs<T>(offp, mskp, 0, ox, oy, ml);
+        if (!waited) {
+            mbar_wait(&bar, 0);
+            waited = true;
+        }
+        float gm_dot_m = 0.f;
+#pragma unroll 1
+        for (int p = 0; p < kTaps; ++p) {
+            const float cx = ox, cy = oy, cm = ml;
+            if (p + 1 < kTaps) load_tap_inputs<T>(offp, mskp, p + 1, ox, oy, ml);
+            const Tap t = make_tap(q, ref0, ref1, p, cx, cy);
+            const int bx = t.x0 - cx0, by = t.y0 - cy0;
+            const bool inbox = bx >= 0 && bx + 1 < tg.bw && by >= 0 && by + 1 < tg.bh;
+            const float mm = logits ? expf(cm - mx) * inv_sum : cm;
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;  // <go, I_k>: a=(y0,x0) b=(y1,x0) c=(y0,x1) d=(y1,x1)
+            if (__builtin_expect(t.alive && !inbox, 0)) {
+#pragma unroll 1
+                for (int k = 0; k < 4; ++k) {
+                    const T* src = global_slab_b(x, q, n, t.y0 + (k & 1), t.x0 + (k >> 1), g);
+                    if (src == nullptr) continue;
+                    f2 dk2 = 0ull;
+#pragma unroll
+                    for (int pc = 0; pc < C::NPIECE; ++pc) {
+                        f2 v[C::PAIRS];
+                        load_piece<T>(src + Slab<T>::chan_of(pc, rot), v);
+#pragma unroll
+                        for (int j = 0; j < C::PAIRS; ++j) ffma2v(dk2, v[j], go[pc * C::PAIRS + j]);
+                    }
+                    const float dk = lo_of(dk2) + hi_of(dk2);
+                    if (k == 0) d0 = dk; else if (k == 1) d1 = dk; else if (k == 2) d2 = dk; else d3 = dk;
+                }
+            } else {
+                const unsigned char* a = sbase + (size_t)(t.alive ? by * tg.bw + bx : 0) * kCellBytes;
+                f2 va[8], vb[8], e0 = 0ull, e1 = 0ull, e2 = 0ull, e3 = 0ull;
+                Slab<T>::load(a, rot, va);
+                Slab<T>::load(a + (size_t)tg.bw * kCellBytes, rot, vb);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) ffma2v(e0, va[c], go[c]);
+                Slab<T>::load(a + kCellBytes, rot, va);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) ffma2v(e1, vb[c], go[c]);
+                Slab<T>::load(a + (size_t)(tg.bw + 1) * kCellBytes, rot, vb);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) ffma2v(e2, va[c], go[c]);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) ffma2v(e3, vb[c], go[c]);
+                d0 = lo_of(e0) + hi_of(e0);
+                d1 = lo_of(e1) + hi_of(e1);
+                d2 = lo_of(e2) + hi_of(e2);
+                d3 = lo_of(e3) + hi_of(e3);
+            }
+            // dead taps have all four deltas zero => zero gradients
+            const float g_m = t.dx1 * t.dy1 * d0 + t.dx1 * t.dy0 * d1 + t.dx0 * t.dy1 * d2 + t.dx0 * t.dy0 * d3;
+            const float gxq = mm * (t.dy1 * (d2 - d0) + t.dy0 * (d3 - d1));
+            const float gyq = mm * (t.dx1 * (d1 - d0) + t.dx0 * (d3 - d2));
+            gm_dot_m += g_m * mm;
+            if (valid) {
+                if (sizeof(T) == 4)
+                    reinterpret_cast<float2*>(goff)[p] = make_float2(gxq * q.fx, gyq * q.fy);
+                else
+                    reinterpret_cast<unsigned*>(goff)[p] = pack_bf16x2(gxq * q.fx, gyq * q.fy);
+                if (!logits) Elem<T>::st(gmsk + p, g_m);
+            }
+            if (logits) park[p][threadIdx.x] = g_m;
+        }
+        if (logits && valid) {
+            // softmax Jacobian needs sum_p m_p*dL/dm_p: second sweep over this lane's own 9 values
+#pragma unroll 1
+            for (int p = 0; p < kTaps; ++p) {
+                const float mm = expf(Elem<T>::ld(mskp + p) - mx) * inv_sum;
+                Elem<T>::st(gmsk + p, mm * (park[p][threadIdx.x] - gm_dot_m));
+            }
+        }
+    }
+    if (!waited) mbar_wait(&bar, 0);
+}
+
+// =====================================================================================================
+// grad_x
+// =====================================================================================================
+// The scatter walk over the source pixels of tile (jx, jy).
+//   MODE 0 (scatter kernel): landings inside J -> int32 shared atomics + weight counters; far landings of
+//                            home pixels -> 64-bit side buffer
+//   MODE 1 (redo, pass 1)  : weight counters only
+//   MODE 2 (redo, pass 2)  : landings on hot cells of J -> 64-bit side buffer
+template <typename T, int MODE>
+__device__ __forceinline__ void scatter_pass(int* acc, int* wsum, const T* __restrict__ offset,
+                                             const T* __restrict__ mask, const T* __restrict__ grad_out,
+                                             const FarWs& ws, const KParams& q, const BwdGeom& bg, int n, int chunk,
+                                             int jx, int jy, Range wh, Range ww, Range hh, Range hw, int eg) {
+    using C = Chunk<T>;
+    using L = AccLayout<T>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g_l = lane % C::GQ, px_l = lane / C::GQ;
+    const int g = chunk * C::GQ + g_l;
+    const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
+    const int ux0 = jx * TJ, uy0 = jy * TJ;
+    const int tjw = min(TJ, q.w - ux0), tjh = min(TJ, q.h - uy0);
+    const float sg = ldexpf(1.0f, eg);  // G = round(go * 2^eg), |G| < 2^30
+    const int nw = ww.hi - ww.lo, npix = (wh.hi - wh.lo) * nw;
+    const size_t img_pixels = (size_t)q.h * q.w;
+    for (int p0 = warp * C::PXW; p0 < npix; p0 += nwarps * C::PXW) {
+        const int pix = p0 + px_l;
+        if (pix >= npix) continue;
+        const int h = wh.lo + pix / nw, w = ww.lo + pix % nw;
+        const bool is_home = MODE == 0 && h >= hh.lo && h < hh.hi && w >= hw.lo && w < hw.hi;
+        const size_t pg = (((size_t)n * q.ho + h) * q.wo + w) * q.G + g;
+        const T* offp = offset + pg * 18;
+        const T* mskp = mask + pg * 9;
+        float mx = 0.f, inv_sum = 1.f;
+        if (logits) softmax_stats9<T>(mskp, mx, inv_sum);
+        float ref0, ref1;
+        ref_point(q, h, w, ref0, ref1);
+        Range covx = {0, 0}, covy = {0, 0};
+        if (is_home) {
+            covx = covering_tiles(nominal_ux(q, h), bg.tiles_x, bg.margin);
+            covy = covering_tiles(nominal_uy(q, w), bg.tiles_y, bg.margin);
+        }
+        int G[16];
+        bool have_g = false;
+        float ox, oy, ml;
+        load_tap_inputs<T>(offp, mskp, 0, ox, oy, ml);
+#pragma unroll 1
+        for (int p = 0; p < kTaps; ++p) {
+            const float cxo = ox, cyo = oy, cm = ml;
+            if (p + 1 < kTaps) load_tap_inputs<T>(offp, mskp, p + 1, ox, oy, ml);
+            // one axis at a time: pixels of the margin are mostly rejected after the first coordinate
+            const Axis axx = axis_x(q, ref0, p, cxo);
+            if (!axx.alive) continue;
+            const int lx = axx.i0 - q.pw - ux0;  // corner (y0,x0) relative to J
+            const bool col0 = lx >= 0 && lx < tjw, col1 = lx + 1 >= 0 && lx + 1 < tjw;
+            if (!is_home && !(col0 || col1)) continue;
+            const Axis axy = axis_y(q, ref1, p, cyo);
+            if (!axy.alive) continue;
+            const int ly = axy.i0 - q.ph - uy0;
+            const bool row0 = ly >= 0 && ly < tjh, row1 = ly + 1 >= 0 && ly + 1 < tjh;
+            if (!is_home && !(row0 || row1)) continue;
+            const float mm = logits ? expf(cm - mx) * inv_sum : cm;
+            const int par = (p ^ h ^ w) & 1;
+            unsigned side_mask = 0;  // corners that need the 64-bit side path
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // a b c d = (y0,x0) (y1,x0) (y0,x1) (y1,x1)
+                const bool in_tile = ((k >> 1) ? col1 : col0) && ((k & 1) ? row1 : row0);
+                const float wf = ((k >> 1) ? axx.d0 : axx.d1) * ((k & 1) ? axy.d0 : axy.d1) * mm;
+                if (wf == 0.f) continue;
+                if (!in_tile) {
+                    if (is_home) side_mask |= 1u << k;  // far test below
+                    continue;
+                }
+                const int cell = L::cell(lx + (k >> 1), ly + (k & 1));
+                const int cellg = cell * C::GQ + g_l;
+                if (MODE == 2) {
+                    if (wsum[cellg] > kBudget) side_mask |= 1u << k;
+                    continue;
+                }
+                // a raw mask beyond the fixed-point range (|Wk| >= 4) makes the cell hot by itself
+                atomicAdd(&wsum[cellg], fabsf(wf) < 3.9f ? (int)ceilf(fabsf(wf) * 1024.f) : kBudget + 1);
+                if (MODE == 1) continue;
+                if (!have_g) {
+                    load_fixed_point_go<T>(grad_out + pg * kGC, sg, G);
+                    have_g = true;
+                }
+                const int wq = __float2int_rn(fminf(fmaxf(wf, -3.9f), 3.9f) * (float)(1 << kWShift));
+                const int bb = par ^ (k & 1) ^ (k >> 1);
+                int* dst = acc + cell * L::CELL + g_l * kGC;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) atomicAdd(dst + c, __mulhi(G[c], wq) + bb);
+            }
+            if (__builtin_expect(side_mask != 0, 0)) {
+#pragma unroll 1
+                for (int k = 0; k < 4; ++k) {
+                    if (!((side_mask >> k) & 1)) continue;
+                    const int ax = lx + (k >> 1) + ux0, ay = ly + (k & 1) + uy0;  // un-padded image coords
+                    if (MODE == 0) {
+                        if (ax < 0 || ax >= q.w || ay < 0 || ay >= q.h) continue;  // zero ring: gradient dropped
+                        const int tx = ax / TJ, ty = ay / TJ;
+                        // the owner of that tile visits this pixel itself unless the tap is far
+                        if (tx >= covx.lo && tx <= covx.hi && ty >= covy.lo && ty <= covy.hi) continue;
+                    }
+                    if (!have_g) {
+                        load_fixed_point_go<T>(grad_out + pg * kGC, sg, G);
+                        have_g = true;
+                    }
+                    const float wf = ((k >> 1) ? axx.d0 : axx.d1) * ((k & 1) ? axy.d0 : axy.d1) * mm;
+                    // same integer q as the shared-memory path; |Wk| >= 4 (raw masks only) is pre-shifted
+                    int sh = 0;
+                    if (!(fabsf(wf) < 3.9f)) sh = min(max((int)((__float_as_uint(wf) >> 23) & 0xffu) - 128, 0), 30);
+                    const int wq = __float2int_rn(ldexpf(wf, kWShift - sh));
+                    const int bb = par ^ (k & 1) ^ (k >> 1);
+                    unsigned long long* dst =
+                        ws.acc64 + (((size_t)n * img_pixels + (size_t)ay * q.w + ax) * q.G + g) * kGC;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                        atomicAdd(dst + c, (unsigned long long)(((long long)__mulhi(G[c], wq) << sh) + bb));
+                    ws.dirty[((size_t)n * img_pixels + (size_t)ay * q.w + ax) * q.G + g] = 1;
+                }
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 3)
+bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
+                   T* __restrict__ grad_x, const FarWs ws, const KParams q, const BwdGeom bg) {
+    using C = Chunk<T>;
+    using L = AccLayout<T>;
+    extern __shared__ __align__(16) int acc[];  // [ACC_INTS] accumulator + [WSUM_INTS] weight counters
+    __shared__ Range s_home_h, s_home_w, s_win_h, s_win_w;
+    int* wsum = acc + L::ACC_INTS;
+
+    int b = blockIdx.x;
+    const int jx = b % bg.tiles_x; b /= bg.tiles_x;
+    const int jy = b % bg.tiles_y; b /= bg.tiles_y;
+    const int chunk = b % bg.chunks;
+    const int n = b / bg.chunks;
+    const int ux0 = jx * TJ, uy0 = jy * TJ;
+    const int tjw = min(TJ, q.w - ux0), tjh = min(TJ, q.h - uy0);
+
+    if (threadIdx.x == 0) tile_ranges(q, bg, jx, jy, s_home_h, s_home_w, s_win_h, s_win_w);
+    const int eg = 30 - fixed_exponent_raw(ws.hd);
+    for (int i = threadIdx.x; i < L::ACC_INTS + L::WSUM_INTS; i += blockDim.x) acc[i] = 0;
+    __syncthreads();
+    scatter_pass<T, 0>(acc, wsum, offset, mask, grad_out, ws, q, bg, n, chunk, jx, jy, s_win_h, s_win_w, s_home_h,
+                       s_home_w, eg);
+    __syncthreads();
+
+    // ---- flush: J is written exactly once ----
+    const float inv_s = ldexpf(1.0f, -(eg + kWShift - 32));  // q = value * 2^(eg + kWShift - 32)
+    constexpr int CH = C::GQ * kGC;  // channels of this chunk per cell
+    constexpr int QPC = CH / 4;      // 4-channel pieces per cell
+    const int ncell = tjw * tjh;
+    bool any_hot = false;
+    for (int i = threadIdx.x; i < ncell * QPC; i += blockDim.x) {
+        const int cl = i / QPC, piece = i % QPC;
+        const int cy = cl / tjw, cx = cl % tjw;
+        const int cell = L::cell(cx, cy);
+        const int gl = (piece * 4) / kGC;
+        // a hot (cell, group) may have wrapped: it is zeroed here and recomputed by redo_hot_kernel
+        const bool hot = wsum[cell * C::GQ + gl] > kBudget;
+        any_hot |= hot;
+        const int* src = acc + cell * L::CELL + piece * 4;
+        const size_t gpix = (size_t)n * q.h * q.w + (size_t)(uy0 + cy) * q.w + (ux0 + cx);
+        const size_t gidx = gpix * ((size_t)q.G * kGC) + (size_t)chunk * CH + piece * 4;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = hot ? 0.f : (float)src[j] * inv_s;
+        if (sizeof(T) == 4) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(grad_x) + gidx) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            uint2 r;
+            r.x = pack_bf16x2(v[0], v[1]);
+            r.y = pack_bf16x2(v[2], v[3]);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(grad_x) + gidx) = r;
+        }
+    }
+    if (any_hot) ws.redo[blockIdx.x] = 1;
+}
+
+// Exact recomputation of the hot cells of one tile (see header): pass 1 rebuilds the weight counters,
+// pass 2 adds the landings on hot cells to the 64-bit side buffer.  Exits at once unless the scatter
+// kernel flagged the CTA -- which only adversarial inputs make it do.
+template <typename T>
+__global__ void __launch_bounds__(256)
+redo_hot_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
+                const FarWs ws, const KParams q, const BwdGeom bg) {
+    using L = AccLayout<T>;
+    if (ws.redo[blockIdx.x] == 0) return;
+    __shared__ int wsum[L::WSUM_INTS];
+    __shared__ Range s_home_h, s_home_w, s_win_h, s_win_w;
+    int b = blockIdx.x;
+    const int jx = b % bg.tiles_x; b /= bg.tiles_x;
+    const int jy = b % bg.tiles_y; b /= bg.tiles_y;
+    const int chunk = b % bg.chunks;
+    const int n = b / bg.chunks;
+    if (threadIdx.x == 0) tile_ranges(q, bg, jx, jy, s_home_h, s_home_w, s_win_h, s_win_w);
+    for (int i = threadIdx.x; i < L::WSUM_INTS; i += blockDim.x) wsum[i] = 0;
+    __syncthreads();
+    const int eg = 30 - fixed_exponent_raw(ws.hd);
+    scatter_pass<T, 1>(nullptr, wsum, offset, mask, grad_out, ws, q, bg, n, chunk, jx, jy, s_win_h, s_win_w, s_home_h,
+                       s_home_w, eg);
+    __syncthreads();
+    scatter_pass<T, 2>(nullptr, wsum, offset, mask, grad_out, ws, q, bg, n, chunk, jx, jy, s_win_h, s_win_w, s_home_h,
+                       s_home_w, eg);
+    __syncthreads();
+    if (threadIdx.x == 0) ws.redo[blockIdx.x] = 0;
+}
+
+// grad_x += side buffer for the (pixel, group)s flagged in the dirty map; leaves the side buffer and
+// the map zeroed for the next call.  One thread per 4 (pixel, group)s; the map is one byte each.
+template <typename T>
+__global__ void __launch_bounds__(256)
+merge_far_kernel(T* __restrict__ grad_x, const FarWs ws, const KParams q, size_t count) {
+    const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= count) return;
+    const unsigned flags = *reinterpret_cast<const unsigned*>(ws.dirty + i4);  // map is padded to 256 bytes
+    if (flags == 0) return;
+    const double inv_s = ldexp(1.0, -(30 - fixed_exponent_raw(ws.hd) + kWShift - 32));
+    for (int j = 0; j < 4; ++j) {
+        if (((flags >> (8 * j)) & 0xffu) == 0 || i4 + j >= count) continue;
+        const size_t idx = (i4 + j) * kGC;
+#pragma unroll 4
+        for (int c = 0; c < kGC; ++c) {
+            const long long v = (long long)ws.acc64[idx + c];
+            if (v != 0) {
+                // |v| can exceed 2^24: go through double so that the exact total is rounded once
+                Elem<T>::st(grad_x + idx + c, Elem<T>::ld_plain(grad_x + idx + c) + (float)((double)v * inv_s));
+                ws.acc64[idx + c] = 0ull;
+            }
+        }
+    }
+    *reinterpret_cast<unsigned*>(ws.dirty + i4) = 0u;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+amax_go_kernel(const T* __restrict__ grad_out, size_t n, WsHeader* hd) {
+    float a = 0.f;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        const float4 v = Elem<T>::ld4(grad_out + i);  // n is a multiple of 16
+        a = fmaxf(a, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(&hd->amax_go_bits, __float_as_uint(a));
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static BwdGeom make_bwd_geom(const KParams& q, int dtype) {
+    BwdGeom bg;
+    bg.tiles_x = (q.w + TJ - 1) / TJ;
+    bg.tiles_y = (q.h + TJ - 1) / TJ;
+    bg.chunks = q.G / (dtype == DCNV3_F32 ? 2 : 4);
+    // source pixels are searched up to ~3 offset units (+1 for the tap grid) beyond the tile
+    const float r = fmaxf(q.wm2_f / q.win_f, q.hm2_f / q.hin_f) * q.scale;
+    bg.margin = min((int)ceilf((1.0f + 3.0f) * r), 12);
+    return bg;
+}
+
+static size_t flag_bytes(size_t count) { return (count * sizeof(int) + 255) / 256 * 256; }
+static size_t dirty_bytes(const KParams& q) { return ((size_t)q.n * q.h * q.w * q.G + 255) / 256 * 256; }
+
+size_t bwd_tiled_workspace_bytes(const KParams& q) {
+    const size_t tiles = (size_t)q.n * ((q.w + TJ - 1) / TJ) * ((q.h + TJ - 1) / TJ);
+    const size_t chunks = (size_t)(q.G + 1) / 2;  // upper bound (fp32 chunks of 2 groups)
+    return sizeof(WsHeader) + dirty_bytes(q) + flag_bytes(tiles * chunks) +
+           sizeof(long long) * (size_t)q.n * q.h * q.w * q.G * q.gc;
+}
+
+template <typename T>
+static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const void* mask, const void* grad_out,
+                                      void* grad_x, void* grad_offset, void* grad_mask, void* wsp,
+                                      const KParams& q, int dtype, bool ws_clean, cudaStream_t st) {
+    using L = AccLayout<T>;
+    const BwdGeom bg = make_bwd_geom(q, dtype);
+    const size_t tiles = (size_t)q.n * bg.tiles_x * bg.tiles_y;
+    const size_t chunks_ub = (size_t)(q.G + 1) / 2;
+    FarWs ws;
+    char* base = (char*)wsp;
+    ws.hd = (WsHeader*)base;
+    ws.dirty = (unsigned char*)(base + sizeof(WsHeader));
+    ws.redo = (int*)(base + sizeof(WsHeader) + dirty_bytes(q));
+    ws.acc64 = (unsigned long long*)(base + sizeof(WsHeader) + dirty_bytes(q) + flag_bytes(tiles * chunks_ub));
+    // flags and side buffer must be zero on entry; redo / merge kernels leave them zero on exit
+    cudaError_t e = cudaMemsetAsync(wsp, 0, ws_clean ? sizeof(WsHeader) : bwd_tiled_workspace_bytes(q), st);
+    if (e != cudaSuccess) return e;
+
+    // ---- grad_offset / grad_mask ----
+    const int max_cells = 100 * 1024 / kCellBytes;
+    const TileGeom tg = make_geom(q, dtype, 16, 16, 3.0f, max_cells);
+    if (tg.bw * tg.bh > max_cells) return cudaErrorInvalidConfiguration;
+    CUtensorMap map;
+    if (!make_x_tensor_map(&map, x, q, dtype, tg.bw, tg.bh)) return cudaErrorNotSupported;
+    const size_t smem_b = (size_t)(L::ACC_INTS + L::WSUM_INTS) * sizeof(int);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        e = cudaFuncSetAttribute(bwd_gather_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(bwd_scatter_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63] = true;
+    }
+    const unsigned grid_a = (unsigned)((size_t)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
+    bwd_gather_kernel<T><<<grid_a, 256, (size_t)tg.bw * tg.bh * kCellBytes, st>>>(
+        map, (const T*)x, (const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_offset, (T*)grad_mask, q, tg);
+
+    // ---- grad_x ----
+    const size_t n_go = (size_t)q.n * q.ho * q.wo * q.G * q.gc;
+    amax_go_kernel<T><<<(unsigned)min((size_t)148 * 8, (n_go / 4 + 255) / 256), 256, 0, st>>>((const T*)grad_out, n_go, ws.hd);
+    const unsigned grid_b = (unsigned)(tiles * bg.chunks);
+    bwd_scatter_kernel<T><<<grid_b, 256, smem_b, st>>>((const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_x, ws, q, bg);
+    redo_hot_kernel<T><<<grid_b, 256, 0, st>>>((const T*)offset, (const T*)mask, (const T*)grad_out, ws, q, bg);
+    const size_t npg = (size_t)q.n * q.h * q.w * q.G;
+    merge_far_kernel<T><<<(unsigned)((npg / 4 + 256) / 256), 256, 0, st>>>((T*)grad_x, ws, q, npg);
+    count_launch(5);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bwd_tiled(const void* x, const void* offset, const void* mask, const void* grad_out,
+                             void* grad_x, void* grad_offset, void* grad_mask, void* ws, const KParams& q,
+                             int dtype, bool ws_clean, cudaStream_t st) {
+    return dtype == DCNV3_F32
+               ? launch_bwd_tiled_t<float>(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, dtype, ws_clean, st)
+               : launch_bwd_tiled_t<__nv_bfloat16>(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, dtype, ws_clean, st);
+}
+
+}  // namespace dcnv3

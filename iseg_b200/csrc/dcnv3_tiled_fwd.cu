@@ -38,8 +38,9 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict__
     const int h0 = ty * tg.th, w0 = tx * tg.tw;
     const int th = min(tg.th, q.ho - h0), tw = min(tg.tw, q.wo - w0);
     // box origin in padded coordinates (output rows h walk along x, columns w along y)
-    const int cx0 = (int)floorf(nominal_x(q, h0)) - tg.halo_x;
-    const int cy0 = (int)floorf(nominal_y(q, w0)) - tg.halo_y;
+    // (kept inside the padded image: cells beyond it can only belong to dead taps)
+    const int cx0 = max(0, min((int)floorf(nominal_x(q, h0)) - tg.halo_x, q.win - tg.bw));
+    const int cy0 = max(0, min((int)floorf(nominal_y(q, w0)) - tg.halo_y, q.hin - tg.bh));
 
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -59,80 +60,76 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict__
     const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
     const int npix = th * tw;
     bool waited = false;
+    (void)th;
 
     for (int p0 = warp * C::PXW; p0 < npix; p0 += (blockDim.x >> 5) * C::PXW) {
-        const int pix = p0 + px_l;
-        const bool valid = pix < npix;
-        const int ph = valid ? pix / tw : 0, pw = valid ? pix % tw : 0;
-        const int h = h0 + ph, w = w0 + pw;
+        const bool valid = p0 + px_l < npix;
+        const int pix = min(p0 + px_l, npix - 1);  // idle lanes shadow the last pixel (loads stay in bounds)
+        const int h = h0 + pix / tw, w = w0 + pix % tw;
         const size_t pg = (((size_t)n * q.ho + h) * q.wo + w) * q.G + g;
-        float o[18], m[9];
-        if (valid) {
-            load_offsets_mask<T>(offset + pg * 18, mask + pg * 9, o, m);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 18; ++i) o[i] = 0.f;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) m[i] = 0.f;
-        }
-        if (logits) softmax9(m);
+        const T* offp = offset + pg * 18;
+        const T* mskp = mask + pg * 9;
+        float mx = 0.f, inv_sum = 1.f;
+        if (logits) softmax_stats9<T>(mskp, mx, inv_sum);
         float ref0, ref1;
         ref_point(q, h, w, ref0, ref1);
-        float acc[16];
+        f2 acc[8];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+        for (int c = 0; c < 8; ++c) acc[c] = 0ull;
+        float ox, oy, ml;
+        load_tap_inputs<T>(offp, mskp, 0, ox, oy, ml);
         if (!waited) {  // the box is needed from here on
             mbar_wait(&bar, 0);
             waited = true;
         }
-#pragma unroll
+#pragma unroll 1
         for (int p = 0; p < kTaps; ++p) {
-            const Tap t = make_tap(q, ref0, ref1, p, o[2 * p], o[2 * p + 1]);
+            const float cx = ox, cy = oy, cm = ml;
+            if (p + 1 < kTaps) load_tap_inputs<T>(offp, mskp, p + 1, ox, oy, ml);  // prefetch the next tap
+            const Tap t = make_tap(q, ref0, ref1, p, cx, cy);
             const int bx = t.x0 - cx0, by = t.y0 - cy0;
             const bool inbox = bx >= 0 && bx + 1 < tg.bw && by >= 0 && by + 1 < tg.bh;
-            const bool live = t.alive && valid;
-            const float mm = live ? m[p] : 0.f;
+            const float mm = t.alive ? (logits ? expf(cm - mx) * inv_sum : cm) : 0.f;
             const float wa = t.dx1 * t.dy1 * mm, wb = t.dx1 * t.dy0 * mm;   // (y0,x0) (y1,x0)
             const float wc = t.dx0 * t.dy1 * mm, wd = t.dx0 * t.dy0 * mm;   // (y0,x1) (y1,x1)
-            if (__builtin_expect(live && !inbox, 0)) {
+            if (__builtin_expect(t.alive && !inbox, 0)) {
                 // rare: patch outside the staged box -> straight from global memory
-                const float wk[4] = {wa, wb, wc, wd};
-#pragma unroll
+#pragma unroll 1
                 for (int k = 0; k < 4; ++k) {
                     const T* src = global_slab(x, q, n, t.y0 + (k & 1), t.x0 + (k >> 1), g);
                     if (src == nullptr) continue;
+                    const float wk = (k & 1) ? ((k >> 1) ? wd : wb) : ((k >> 1) ? wc : wa);
 #pragma unroll
                     for (int pc = 0; pc < C::NPIECE; ++pc) {
-                        float v[C::CH_PER_PIECE];
+                        f2 v[C::PAIRS];
                         load_piece<T>(src + Slab<T>::chan_of(pc, rot), v);
 #pragma unroll
-                        for (int j = 0; j < C::CH_PER_PIECE; ++j) acc[pc * C::CH_PER_PIECE + j] += v[j] * wk[k];
+                        for (int j = 0; j < C::PAIRS; ++j) ffma2s(acc[pc * C::PAIRS + j], v[j], wk);
                     }
                 }
             } else {
-                const int cell = (live && inbox) ? by * tg.bw + bx : 0;
-                const float s = (live && inbox) ? 1.f : 0.f;
-                const unsigned char* a = sbase + (size_t)cell * kCellBytes;
-                float v[16];
-                Slab<T>::load(a, rot, v);
+                // dead taps carry zero weights and read cell 0
+                const unsigned char* a = sbase + (size_t)(t.alive ? by * tg.bw + bx : 0) * kCellBytes;
+                f2 va[8], vb[8];
+                Slab<T>::load(a, rot, va);
+                Slab<T>::load(a + (size_t)tg.bw * kCellBytes, rot, vb);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) acc[c] += v[c] * (wa * s);
-                Slab<T>::load(a + (size_t)tg.bw * kCellBytes, rot, v);
+                for (int c = 0; c < 8; ++c) ffma2s(acc[c], va[c], wa);
+                Slab<T>::load(a + kCellBytes, rot, va);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) acc[c] += v[c] * (wb * s);
-                Slab<T>::load(a + kCellBytes, rot, v);
+                for (int c = 0; c < 8; ++c) ffma2s(acc[c], vb[c], wb);
+                Slab<T>::load(a + (size_t)(tg.bw + 1) * kCellBytes, rot, vb);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) acc[c] += v[c] * (wc * s);
-                Slab<T>::load(a + (size_t)(tg.bw + 1) * kCellBytes, rot, v);
+                for (int c = 0; c < 8; ++c) ffma2s(acc[c], va[c], wc);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) acc[c] += v[c] * (wd * s);
+                for (int c = 0; c < 8; ++c) ffma2s(acc[c], vb[c], wd);
             }
         }
         if (valid) {
             T* dst = out + pg * kGC;
 #pragma unroll
             for (int pc = 0; pc < C::NPIECE; ++pc)
-                store_piece<T>(dst + Slab<T>::chan_of(pc, rot), acc + pc * C::CH_PER_PIECE);
+                store_piece<T>(dst + Slab<T>::chan_of(pc, rot), acc + pc * C::PAIRS);
         }
     }
     if (!waited) mbar_wait(&bar, 0);  // never leave with a TMA in flight
@@ -194,13 +191,13 @@ TileGeom make_geom(const KParams& q, int dtype, int th, int tw, float reach, int
     const float ax = q.wm2_f / q.hin_f, ay = q.hm2_f / q.win_f;
     const float rx = q.wm2_f / q.win_f, ry = q.hm2_f / q.hin_f;
     for (;; reach *= 0.75f) {
-        tg.halo_x = (int)ceilf((1.0f + reach) * fabsf(q.scale) * rx) + 1;
-        tg.halo_y = (int)ceilf((1.0f + reach) * fabsf(q.scale) * ry) + 1;
+        tg.halo_x = (int)ceilf((1.0f + reach) * fabsf(q.scale) * rx);
+        tg.halo_y = (int)ceilf((1.0f + reach) * fabsf(q.scale) * ry);
         tg.bw = (int)ceilf((tg.th - 1) * ax) + 2 * tg.halo_x + 2;
         tg.bh = (int)ceilf((tg.tw - 1) * ay) + 2 * tg.halo_y + 2;
-        // never stage more than the padded image itself (+1 so that the +1 corner stays inside)
-        tg.bw = min(tg.bw, min(q.win + 1, 256));
-        tg.bh = min(tg.bh, min(q.hin + 1, 256));
+        // never stage more than the padded image itself
+        tg.bw = min(tg.bw, min(q.win, 256));
+        tg.bh = min(tg.bh, min(q.hin, 256));
         if (tg.bw * tg.bh <= max_cells || reach < 0.05f) break;
     }
     return tg;

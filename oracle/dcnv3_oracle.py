@@ -217,8 +217,10 @@ def forward(x, offset, mask, kernel_size=(3, 3), strides=(1, 1), padding="SAME",
 
 
 def backward(x, offset, mask, grad_out, kernel_size=(3, 3), strides=(1, 1), padding="SAME",
-             dilation_rate=(1, 1), groups=4, group_channels=16, offset_scale=1.0):
-    """(grad_x, grad_offset, grad_mask).  d/d offset flows only through dx0 = xq - x0f etc.
+             dilation_rate=(1, 1), groups=4, group_channels=16, offset_scale=1.0, accumulate=None):
+    """(grad_x, grad_offset, grad_mask).  `accumulate=np.float64` keeps every per-tap quantity in
+    x.dtype (as the reference computes it) but sums the grad_x scatter in float64 -- the yardstick for
+    long collision chains, where an x.dtype running sum is itself ~sqrt(n)*eps off.  d/d offset flows only through dx0 = xq - x0f etc.
     (utils.py:163-166); chain factor d xq / d offset = (W_in-2)*s/W_in (op.py:85-87, utils.py:142).
     Contributions to the zero ring of the padded image are dropped (gradient of tf.pad, op.py:46)."""
     ph, pw = resolve_padding(kernel_size, padding)
@@ -244,14 +246,14 @@ def backward(x, offset, mask, grad_out, kernel_size=(3, 3), strides=(1, 1), padd
     grad_offset = np.stack([g_xq * fx, g_yq * fy], axis=-1).reshape(offset.shape).astype(dtype)
     grad_mask = grad_mask.reshape(mask.shape).astype(dtype)
 
-    gxp = np.zeros((n, hin, win, groups, group_channels), dtype=dtype)
+    gxp = np.zeros((n, hin, win, groups, group_channels), dtype=accumulate or dtype)
     nn = np.broadcast_to(np.arange(n).reshape(n, 1, 1, 1, 1), t.x0.shape)
     gg = np.broadcast_to(np.arange(groups).reshape(1, 1, 1, groups, 1), t.x0.shape)
     gs = go * m[..., None]  # [N,Ho,Wo,G,P,gc]
     for (yy, xx, w_) in ((t.y0, t.x0, wa), (t.y1, t.x0, wb), (t.y0, t.x1, wc), (t.y1, t.x1, wd)):
         np.add.at(gxp, (nn, yy, xx, gg), gs * w_[..., None])
     grad_x = gxp[:, ph:hin - ph, pw:win - pw].reshape(x.shape)
-    return np.ascontiguousarray(grad_x), grad_offset, grad_mask
+    return np.ascontiguousarray(grad_x).astype(dtype), grad_offset, grad_mask
 
 
 def mask_softmax(logits, groups):

@@ -117,7 +117,10 @@ def test_backward_bitwise_reproducible(ops):
     for _ in range(3):
         b = run_op(ops, x, off, m, go, **kw)
         assert all(np.array_equal(p, q) for p, q in zip(a, b))
-    # heavy collisions: every tap of every pixel lands in the same cell
+    # heavy collisions: every tap of every pixel lands in the same cell (~37k contributions per
+    # channel).  An fp32 running sum of that length carries ~sqrt(n)*eps error itself, so the yardstick
+    # here is the oracle with fp32 per-tap arithmetic (as the reference) but a float64 scatter sum.
+    x, off, m, go = x[:1], off[:1], m[:1], go[:1]
     off2 = np.zeros_like(off)
     off2[..., 0::2] = (30.0 - np.arange(64, dtype=np.float32)).reshape(1, 64, 1, 1) * 66 / 64
     off2[..., 1::2] = (30.0 - np.arange(64, dtype=np.float32)).reshape(1, 1, 64, 1) * 66 / 64
@@ -125,7 +128,10 @@ def test_backward_bitwise_reproducible(ops):
     b = run_op(ops, x, off2, m, go, **kw)
     assert all(np.array_equal(p, q) for p, q in zip(a, b))
     rx, roff, rm = c_oracle.backward(x, off2, m, go, **kw)
-    assert rel_err(a[1], rx) <= TOL_F32 and rel_err(a[2], roff) <= TOL_F32
+    assert rel_err(a[2], roff) <= TOL_F32 and rel_err(a[3], rm) <= TOL_F32
+    dx, _, _ = O.backward(x, off2, m, go, accumulate=np.float64, **kw)
+    assert rel_err(a[1], dx) <= 1e-6            # fixed-point accumulation: exact up to the final rounding
+    assert rel_err(rx, dx) <= 1e-4              # (the fp32 running sum of the C oracle is the loose one)
 
 
 def test_fused_softmax_matches_layer_semantics(ops):
