@@ -19,6 +19,7 @@ namespace dcnv3 {
 constexpr int kTaps = 9;
 constexpr int kGC = 16;
 constexpr int kCellBytes = 128;
+constexpr int kMaxBoxBytes = 82 * 1024;  // staged input box; with the row staging slots two CTAs fit one SM
 
 template <typename T>
 struct Chunk {
@@ -183,6 +184,110 @@ __device__ __forceinline__ void store_piece<__nv_bfloat16>(__nv_bfloat16* p, con
     r.z = pack_bf16x2(lo_of(v[2]), hi_of(v[2])); r.w = pack_bf16x2(lo_of(v[3]), hi_of(v[3]));
     *reinterpret_cast<uint4*>(p) = r;
 }
+
+// ---- per-warp row staging ------------------------------------------------------------------------
+// A warp iteration works on PXW consecutive pixels of ONE output row (x GQ groups = 32 lanes).  Their
+// offsets / mask values are [pixel][GQ groups][18 | 9] runs of 144 / 72 contiguous bytes per pixel in
+// global memory (pixel stride G*18 / G*9 elements).  Letting every lane fetch its own 72+36 bytes makes
+// each load instruction touch ~40 cache lines; instead the warp copies the runs cooperatively
+// (consecutive lanes -> consecutive 16 / 8 bytes) into a private shared-memory slot and every lane then
+// reads its own values back with conflict-free LDS (lane stride 72 B for 8-byte loads, 36 B for 4-byte).
+template <typename T>
+struct RowStage {
+    using C = Chunk<T>;
+    static constexpr int OFF_PX = C::GQ * 18 * (int)sizeof(T);  // 144 bytes per pixel
+    static constexpr int MSK_PX = C::GQ * 9 * (int)sizeof(T);   // 72
+    static constexpr int VEC_PX = C::GQ * 16 * (int)sizeof(T);  // 128
+    static constexpr int OFF_BYTES = C::PXW * OFF_PX;           // 2304 (fp32) / 1152 (bf16)
+    static constexpr int MSK_BYTES = C::PXW * MSK_PX;           // 1152 / 576
+    static constexpr int BYTES = OFF_BYTES + MSK_BYTES;         // per warp
+    static constexpr int LANE_OFF = 18 * (int)sizeof(T);        // 72 / 36: a lane's own offsets
+    static constexpr int LANE_MSK = 9 * (int)sizeof(T);         // 36 / 18
+
+    // off_row / msk_row point at the first pixel's run (element pointers); G = groups of the tensor
+    static __device__ __forceinline__ void load(unsigned char* st, const T* off_row, const T* msk_row, int G,
+                                                int npx, int lane) {
+        const int n = npx * 9;
+        const size_t off_stride = (size_t)G * 18 * sizeof(T), msk_stride = (size_t)G * 9 * sizeof(T);
+#pragma unroll
+        for (int i = 0; i < (C::PXW * 9 + 31) / 32; ++i) {
+            const int c = lane + 32 * i;
+            if (c < n) {
+                const int px = (c * 7282) >> 16, r = c - px * 9;  // c / 9 for c < 288
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+                                          reinterpret_cast<const unsigned char*>(off_row) + px * off_stride) + r);
+                *reinterpret_cast<uint4*>(st + px * OFF_PX + r * 16) = v;
+                const uint2 u = __ldg(reinterpret_cast<const uint2*>(
+                                          reinterpret_cast<const unsigned char*>(msk_row) + px * msk_stride) + r);
+                *reinterpret_cast<uint2*>(st + OFF_BYTES + px * MSK_PX + r * 8) = u;
+            }
+        }
+        __syncwarp();
+    }
+    // the lane's tap p
+    static __device__ __forceinline__ void tap(const unsigned char* st, int lane, int p, float& ox, float& oy,
+                                               float& ml) {
+        if (sizeof(T) == 4) {
+            const float2 o = *reinterpret_cast<const float2*>(st + lane * LANE_OFF + p * 8);
+            ox = o.x; oy = o.y;
+            ml = *reinterpret_cast<const float*>(st + OFF_BYTES + lane * LANE_MSK + p * 4);
+        } else {
+            const unsigned r = *reinterpret_cast<const unsigned*>(st + lane * LANE_OFF + p * 4);
+            ox = __uint_as_float(r << 16); oy = __uint_as_float(r & 0xffff0000u);
+            ml = __uint_as_float((unsigned)*reinterpret_cast<const unsigned short*>(st + OFF_BYTES + lane * LANE_MSK + p * 2) << 16);
+        }
+    }
+    static __device__ __forceinline__ void softmax_stats(const unsigned char* st, int lane, float& mx, float& inv_sum) {
+        float v[kTaps];
+#pragma unroll
+        for (int p = 0; p < kTaps; ++p) {
+            float a, b;
+            tap(st, lane, p, a, b, v[p]);
+        }
+        mx = v[0];
+#pragma unroll
+        for (int p = 1; p < kTaps; ++p) mx = fmaxf(mx, v[p]);
+        float s = 0.f;
+#pragma unroll
+        for (int p = 0; p < kTaps; ++p) s += expf(v[p] - mx);
+        inv_sum = 1.0f / s;
+    }
+    // cooperative, coalesced store of staged offset-shaped (144 B / pixel) and mask-shaped (72 B / pixel)
+    // results, e.g. grad_offset / grad_mask
+    static __device__ __forceinline__ void store_off_msk(const unsigned char* st, T* off_row, T* msk_row, int G,
+                                                         int npx, int lane) {
+        __syncwarp();
+        const int n = npx * 9;
+        const size_t off_stride = (size_t)G * 18 * sizeof(T), msk_stride = (size_t)G * 9 * sizeof(T);
+#pragma unroll
+        for (int i = 0; i < (C::PXW * 9 + 31) / 32; ++i) {
+            const int c = lane + 32 * i;
+            if (c < n) {
+                const int px = (c * 7282) >> 16, r = c - px * 9;  // c / 9 for c < 288
+                *(reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(off_row) + px * off_stride) + r) =
+                    *reinterpret_cast<const uint4*>(st + px * OFF_PX + r * 16);
+                *(reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(msk_row) + px * msk_stride) + r) =
+                    *reinterpret_cast<const uint2*>(st + OFF_BYTES + px * MSK_PX + r * 8);
+            }
+        }
+        __syncwarp();
+    }
+    // cooperative, coalesced store of the warp's [pixel][GQ][16] result slab staged at st (128 B / pixel)
+    static __device__ __forceinline__ void store_vec(const unsigned char* st, T* dst_row, int G, int npx, int lane) {
+        __syncwarp();
+        const int n = npx * 8;
+        const size_t stride = (size_t)G * 16 * sizeof(T);
+#pragma unroll
+        for (int i = 0; i < C::PXW * 8 / 32; ++i) {
+            const int c = lane + 32 * i;
+            if (c < n) {
+                const int px = c >> 3, r = c & 7;
+                *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(dst_row) + px * stride + r * 16) =
+                    *reinterpret_cast<const uint4*>(st + px * VEC_PX + r * 16);
+            }
+        }
+    }
+};
 
 // Per-tap inputs of one (pixel, group): the offset pair and the mask value (or logit) of tap p.
 template <typename T>

@@ -174,7 +174,7 @@ bool tiled_applicable(const KParams& q, int dtype) {
     const int gq = dtype == DCNV3_F32 ? 2 : 4;
     return q.P == 9 && q.kh == 3 && q.sh == 1 && q.sw == 1 && q.dh == 1 && q.dw == 1 && q.gc == kGC &&
            q.G % gq == 0 && q.ho == q.h && q.wo == q.w && q.ph == 1 && q.pw == 1 && q.scale > 0.f &&
-           q.scale <= 16.f;
+           q.scale <= 16.f && q.h <= 16384 && q.w <= 16384;
 }
 
 // Box geometry: the nominal footprint of a th x tw output tile spans (th-1)*ax columns and (tw-1)*ay
