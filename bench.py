@@ -285,35 +285,41 @@ def run_ours(args, rank, world, local_rank):
             if launches_per_step is not None:
                 launched = launches_per_step * args.steps
             res.update(ms_total=ms, launches=launched, launch=launch)
-            # ---- per-call-class durations (CUDA events on the launching stream) ----
+            # ---- per-kernel durations (CUDA events on the launching stream, recorded around every kernel:
+            #      forward from here, the four backward kernels inside the library) ----
             esize = 4 if dtype == "f32" else 2
             reps = max(1, min(args.steps, 3))
-            evs = []
+            classes = {}
+            cabi.check(lib.dcnv3_set_kernel_timing(1))
+            ms4 = (ctypes.c_float * 4)()
             for _ in range(reps):
+                evs = []
                 for l in layers:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record(stream)
                     cabi.check(lib.dcnv3_forward(*l.fwd_args, l.pref, sp))
                     e1.record(stream)
-                    evs.append((("fwd",) + l.shape, e0, e1))
+                    evs.append((("fwd_tiled",) + l.shape, e0, e1))
+                torch.cuda.synchronize()
+                for key, e0, e1 in evs:
+                    classes.setdefault(key, []).append(e0.elapsed_time(e1))
                 for l in reversed(layers):
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record(stream)
                     cabi.check(lib.dcnv3_backward(*l.bwd_args, l.ws_bytes, l.pref, sp))
-                    e1.record(stream)
-                    evs.append((("bwd",) + l.shape, e0, e1))
-            torch.cuda.synchronize()
-            classes = {}
-            for key, e0, e1 in evs:
-                classes.setdefault(key, []).append(e0.elapsed_time(e1))
+                    cabi.check(lib.dcnv3_get_kernel_timing(ms4))
+                    for name, v in zip(("bwd_gather", "bwd_scatter", "bwd_redo_hot", "bwd_merge_far"), ms4):
+                        classes.setdefault((name,) + l.shape, []).append(float(v))
+            cabi.check(lib.dcnv3_set_kernel_timing(0))
             table = []
             for key, ts in classes.items():
                 d, h, w, c, g = key
-                fb, bb = algo_bytes(h, w, c, g, esize)
-                nbytes = fb if d == "fwd" else bb
+                px = BATCH * h * w
+                # algorithmic bytes of each kernel: elements per pixel x element size
+                per_px = {"fwd_tiled": 2 * c + 3 * g * P, "bwd_gather": 2 * c + 6 * g * P,
+                          "bwd_scatter": 2 * c + 3 * g * P}.get(d, 0)
+                nbytes = px * per_px * esize
                 avg = sum(ts) / len(ts)
-                table.append({"call": f"{d} {h}x{w} C{c} G{g}", "avg_us": avg * 1e3, "calls_per_step": len(ts) // reps,
-                              "algo_bytes": nbytes, "gbs": nbytes / avg * 1e-6,
+                table.append({"kernel": f"{d} {h}x{w} C{c} G{g}", "avg_us": avg * 1e3, "launches_per_step": len(ts) // reps,
+                              "algo_bytes": nbytes, "gbs": nbytes / avg * 1e-6 if avg > 0 else 0.0,
                               "share": avg * (len(ts) // reps)})
             tot = sum(t["share"] for t in table)
             for t in table:
@@ -343,10 +349,16 @@ def run_ours(args, rank, world, local_rank):
             h2d += nb * depth
             d2h += nb * depth
 
+        nslots = int(lib.dcnv3_host_slots())
+
         def step():
+            i = 0
             for ptrs, p, depth, _ in host:
                 for _ in range(depth):
-                    cabi.check(lib.dcnv3_forward_backward_host(*ptrs, ctypes.byref(p), local_rank))
+                    # copy-in, kernels and copy-out of consecutive layers overlap on different slots
+                    cabi.check(lib.dcnv3_forward_backward_host_async(*ptrs, ctypes.byref(p), local_rank, i % nslots))
+                    i += 1
+            cabi.check(lib.dcnv3_host_sync(local_rank))  # results are in host memory from here on
 
         steps = max(1, min(args.steps, args.e2e_steps))
         for _ in range(min(args.warmup, 2)):
@@ -364,7 +376,8 @@ def run_ours(args, rank, world, local_rank):
         lib.dcnv3_release_host_scratch()
         return {"value": points_per_step() * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": dt / steps * 1e3, "steps": steps,
-                "api": "dcnv3_forward_backward_host (C ABI, pinned host buffers, per layer)"}
+                "api": "dcnv3_forward_backward_host_async + dcnv3_host_sync (C ABI, pinned host buffers, per layer, "
+                       f"{nslots} pipelined slots)"}
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     main = measure(args.dtype, sampler)
@@ -380,7 +393,7 @@ def run_ours(args, rank, world, local_rank):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tpath):
-            traffic = json.load(open(tpath)).get(f"{args.dtype}:{top['call']}")
+            traffic = json.load(open(tpath)).get(f"{args.dtype}:{top['kernel']}")
         esize = 4 if args.dtype == "f32" else 2
         step_bytes = sum(sum(algo_bytes(h, w, c, g, esize)) * d for h, w, c, g, d in STAGES)
         cpu_v, cpu_ms, cpu_info = cpu_reference_run(steps=3, warmup=1, sample_batch=1, budget_s=20.0)
@@ -393,13 +406,13 @@ def run_ours(args, rank, world, local_rank):
             "clocks": sampler.summary(),
             "e2e": e2e,
             "gpu_launches": main["launches"],
-            "roofline": {"bound": "hbm", "kernel": top["call"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": top["kernel"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
                          "frac": top["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
                          "algo_bytes_per_launch": top["algo_bytes"], "avg_launch_us": top["avg_us"],
                          "share_of_step": top["share"]},
             "step_hbm": {"algo_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms_step * 1e-3) * 1e-9,
                          "frac_of_peak": step_bytes / (ms_step * 1e-3) * 1e-9 / peak},
-            "calls": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in t.items()} for t in main["classes"]],
+            "kernels": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in t.items()} for t in main["classes"]],
             "cpu_baseline": cpu_info,
         }
         if other is not None:
@@ -407,7 +420,7 @@ def run_ours(args, rank, world, local_rank):
             ob = sum(sum(algo_bytes(h, w, c, g, 6 - esize)) * d for h, w, c, g, d in STAGES)
             line[other_dtype] = {"value": points_per_step() * world / (oms * 1e-3), "ms_per_step": oms,
                                  "achieved_gbs": ob / (oms * 1e-3) * 1e-9, "frac_of_peak": ob / (oms * 1e-3) * 1e-9 / peak,
-                                 "top_call": other["classes"][0]["call"], "top_call_gbs": other["classes"][0]["gbs"]}
+                                 "top_kernel": other["classes"][0]["kernel"], "top_kernel_gbs": other["classes"][0]["gbs"]}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -417,7 +430,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])

@@ -116,8 +116,24 @@ int dcnv3_forward_backward_host(const void* x, const void* offset, const void* m
                                 const void* grad_out, void* out, void* grad_x, void* grad_offset,
                                 void* grad_mask, const dcnv3_params* p, int device);
 
+/* Pipelined variant: enqueues copy-in, kernels and copy-out on the stream of scratch slot
+   `slot` (0 <= slot < dcnv3_host_slots()) and returns without waiting, so that consecutive calls on
+   different slots overlap H2D, compute and D2H.  Host buffers must be pinned and stay valid until
+   dcnv3_host_sync(device) (or the next call on the same slot) returns. */
+int dcnv3_forward_backward_host_async(const void* x, const void* offset, const void* mask,
+                                      const void* grad_out, void* out, void* grad_x, void* grad_offset,
+                                      void* grad_mask, const dcnv3_params* p, int device, int slot);
+int dcnv3_host_sync(int device);
+int dcnv3_host_slots(void);
+
 /* Releases the per-device scratch used by the *_host entry points. */
 int dcnv3_release_host_scratch(void);
+
+/* Measurement aid (bench.py): when enabled, the tiled dcnv3_backward brackets its four kernels
+   (gather, scatter, redo, merge) with CUDA events on the launch stream; dcnv3_get_kernel_timing waits for
+   the last backward and returns their durations in milliseconds. */
+int dcnv3_set_kernel_timing(int enable);
+int dcnv3_get_kernel_timing(float* ms4);
 
 /* Number of kernels this library has launched on behalf of the calling process (monotonic). */
 uint64_t dcnv3_kernel_launch_count(void);

@@ -55,6 +55,10 @@ def _load():
     lib.dcnv3_backward_dlpack.argtypes = [vp] * 8 + scal
     lib.dcnv3_forward_host.argtypes = [vp] * 4 + [pp, ci]
     lib.dcnv3_forward_backward_host.argtypes = [vp] * 8 + [pp, ci]
+    lib.dcnv3_forward_backward_host_async.argtypes = [vp] * 8 + [pp, ci, ci]
+    lib.dcnv3_host_sync.argtypes = [ci]
+    lib.dcnv3_set_kernel_timing.argtypes = [ci]
+    lib.dcnv3_get_kernel_timing.argtypes = [ctypes.POINTER(ctypes.c_float)]
     lib.dcnv3_kernel_launch_count.restype = ctypes.c_uint64
     if lib.dcnv3_abi_version() != 1:
         raise ImportError("libdcnv3_b200.so ABI version mismatch")

@@ -15,6 +15,11 @@ void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxe
 
 static thread_local char t_err[512] = "";
 
+KernelTiming& kernel_timing() {
+    static KernelTiming t;
+    return t;
+}
+
 static int fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -200,27 +205,44 @@ static int dl_params(const DLManagedTensor* x, const DLManagedTensor* offset, in
 }
 
 // ---- host-buffer scratch -------------------------------------------------------------------------
+// kHostSlots independent slots per device, each with its own stream, data scratch and a backward
+// workspace that is zeroed when (re)allocated and kept zeroed by dcnv3_backward itself.
+constexpr int kHostSlots = 4;
 struct HostScratch {
     void* buf = nullptr;
     size_t bytes = 0;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
     cudaStream_t stream = nullptr;
 };
 static std::mutex g_scratch_mu;
-static HostScratch g_scratch[64];
+static HostScratch g_scratch[64][kHostSlots];
 
-static int scratch_reserve(int device, size_t bytes, HostScratch** out) {
+static int scratch_reserve(int device, int slot, size_t bytes, size_t ws_bytes, HostScratch** out) {
     if (device < 0 || device >= 64) return fail(DCNV3_ERR_DEVICE, "device %d out of range", device);
-    HostScratch& s = g_scratch[device];
+    if (slot < 0 || slot >= kHostSlots) return fail(DCNV3_ERR_ARGUMENT, "slot %d out of range [0,%d)", slot, kHostSlots);
+    HostScratch& s = g_scratch[device][slot];
     cudaError_t e;
     if (s.stream == nullptr) {
         if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess)
             return cuda_fail(e, "cudaStreamCreate");
+    }
+    if (s.bytes < bytes || s.ws_bytes < ws_bytes) {
+        // the slot may still be running an earlier asynchronous call
+        if ((e = cudaStreamSynchronize(s.stream)) != cudaSuccess) return cuda_fail(e, "stream synchronize");
     }
     if (s.bytes < bytes) {
         if (s.buf) cudaFree(s.buf);
         s.buf = nullptr; s.bytes = 0;
         if ((e = cudaMalloc(&s.buf, bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
         s.bytes = bytes;
+    }
+    if (s.ws_bytes < ws_bytes) {
+        if (s.ws) cudaFree(s.ws);
+        s.ws = nullptr; s.ws_bytes = 0;
+        if ((e = cudaMalloc(&s.ws, ws_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)");
+        if ((e = cudaMemsetAsync(s.ws, 0, ws_bytes, s.stream)) != cudaSuccess) return cuda_fail(e, "memset(workspace)");
+        s.ws_bytes = ws_bytes;
     }
     *out = &s;
     return 0;
@@ -338,7 +360,7 @@ int dcnv3_backward_dlpack(const DLManagedTensor* x, const DLManagedTensor* offse
 
 static int host_run(const void* x, const void* offset, const void* mask, const void* grad_out,
                     void* out, void* grad_x, void* grad_offset, void* grad_mask,
-                    const dcnv3_params* p, int device, bool with_backward) {
+                    const dcnv3_params* p, int device, bool with_backward, int slot, bool wait) {
     int rc = check(p);
     if (rc) return rc;
     if (!x || !offset || !mask || !out || (with_backward && (!grad_out || !grad_x || !grad_offset || !grad_mask)))
@@ -354,10 +376,10 @@ static int host_run(const void* x, const void* offset, const void* mask, const v
     const size_t b_m = align_up((size_t)p->n * p->ho * p->wo * GP * es, 256);
     const size_t b_ws = with_backward ? align_up(backward_ws_bytes(p), 256) : 0;
     size_t total = b_x + b_off + b_m + b_o;
-    if (with_backward) total += b_o + b_x + b_off + b_m + b_ws;
+    if (with_backward) total += b_o + b_x + b_off + b_m;
     std::lock_guard<std::mutex> lock(g_scratch_mu);
     HostScratch* s;
-    if ((rc = scratch_reserve(device, total, &s))) return rc;
+    if ((rc = scratch_reserve(device, slot, total, b_ws, &s))) return rc;
     char* base = (char*)s->buf;
     char* d_x = base; base += b_x;
     char* d_off = base; base += b_off;
@@ -378,41 +400,94 @@ static int host_run(const void* x, const void* offset, const void* mask, const v
         char* d_gx = base; base += b_x;
         char* d_goff = base; base += b_off;
         char* d_gm = base; base += b_m;
-        char* d_ws = base;
         H2D(d_go, grad_out, n_o);
-        if ((rc = backward_impl(d_x, d_off, d_m, d_go, d_gx, d_goff, d_gm, d_ws, b_ws, p, st))) return rc;
+        dcnv3_params pb = *p;
+        pb.flags |= DCNV3_FLAG_WORKSPACE_ZEROED;  // the slot's workspace is zeroed at allocation and stays so
+        if ((rc = backward_impl(d_x, d_off, d_m, d_go, d_gx, d_goff, d_gm, s->ws, s->ws_bytes, &pb, st))) return rc;
         D2H(grad_x, d_gx, n_x);
         D2H(grad_offset, d_goff, n_off);
         D2H(grad_mask, d_gm, n_m);
     }
 #undef H2D
 #undef D2H
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "stream synchronize");
+    if (wait && (e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "stream synchronize");
     return DCNV3_OK;
 }
 
 int dcnv3_forward_host(const void* x, const void* offset, const void* mask, void* out,
                        const dcnv3_params* p, int device) {
-    return host_run(x, offset, mask, nullptr, out, nullptr, nullptr, nullptr, p, device, false);
+    return host_run(x, offset, mask, nullptr, out, nullptr, nullptr, nullptr, p, device, false, 0, true);
 }
 
 int dcnv3_forward_backward_host(const void* x, const void* offset, const void* mask,
                                 const void* grad_out, void* out, void* grad_x, void* grad_offset,
                                 void* grad_mask, const dcnv3_params* p, int device) {
-    return host_run(x, offset, mask, grad_out, out, grad_x, grad_offset, grad_mask, p, device, true);
+    return host_run(x, offset, mask, grad_out, out, grad_x, grad_offset, grad_mask, p, device, true, 0, true);
 }
+
+int dcnv3_forward_backward_host_async(const void* x, const void* offset, const void* mask,
+                                      const void* grad_out, void* out, void* grad_x, void* grad_offset,
+                                      void* grad_mask, const dcnv3_params* p, int device, int slot) {
+    {   // the slot's scratch is about to be overwritten: its previous call must have drained
+        std::lock_guard<std::mutex> lock(g_scratch_mu);
+        if (device >= 0 && device < 64 && slot >= 0 && slot < kHostSlots && g_scratch[device][slot].stream) {
+            cudaSetDevice(device);
+            cudaError_t e = cudaStreamSynchronize(g_scratch[device][slot].stream);
+            if (e != cudaSuccess) return cuda_fail(e, "stream synchronize");
+        }
+    }
+    return host_run(x, offset, mask, grad_out, out, grad_x, grad_offset, grad_mask, p, device, true, slot, false);
+}
+
+int dcnv3_host_sync(int device) {
+    if (device < 0 || device >= 64) return fail(DCNV3_ERR_DEVICE, "device %d out of range", device);
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    for (int k = 0; k < kHostSlots; ++k)
+        if (g_scratch[device][k].stream && (e = cudaStreamSynchronize(g_scratch[device][k].stream)) != cudaSuccess)
+            return cuda_fail(e, "stream synchronize");
+    return DCNV3_OK;
+}
+
+int dcnv3_host_slots(void) { return kHostSlots; }
 
 int dcnv3_release_host_scratch(void) {
     std::lock_guard<std::mutex> lock(g_scratch_mu);
-    for (int d = 0; d < 64; ++d) {
-        HostScratch& s = g_scratch[d];
-        if (s.buf || s.stream) {
-            cudaSetDevice(d);
-            if (s.buf) cudaFree(s.buf);
-            if (s.stream) cudaStreamDestroy(s.stream);
-            s = HostScratch();
+    for (int d = 0; d < 64; ++d)
+        for (int k = 0; k < kHostSlots; ++k) {
+            HostScratch& s = g_scratch[d][k];
+            if (s.buf || s.ws || s.stream) {
+                cudaSetDevice(d);
+                if (s.stream) cudaStreamSynchronize(s.stream);
+                if (s.buf) cudaFree(s.buf);
+                if (s.ws) cudaFree(s.ws);
+                if (s.stream) cudaStreamDestroy(s.stream);
+                s = HostScratch();
+            }
+        }
+    return DCNV3_OK;
+}
+
+int dcnv3_set_kernel_timing(int enable) {
+    KernelTiming& t = kernel_timing();
+    if (enable && t.ev[0] == nullptr) {
+        for (int i = 0; i < 5; ++i) {
+            cudaError_t e = cudaEventCreate(&t.ev[i]);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
         }
     }
+    t.enabled = enable != 0;
+    return DCNV3_OK;
+}
+
+int dcnv3_get_kernel_timing(float* ms4) {
+    KernelTiming& t = kernel_timing();
+    if (t.ev[0] == nullptr || ms4 == nullptr) return fail(DCNV3_ERR_ARGUMENT, "kernel timing was never enabled");
+    cudaError_t e = cudaEventSynchronize(t.ev[4]);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize");
+    for (int i = 0; i < 4; ++i)
+        if ((e = cudaEventElapsedTime(&ms4[i], t.ev[i], t.ev[i + 1])) != cudaSuccess) return cuda_fail(e, "cudaEventElapsedTime");
     return DCNV3_OK;
 }
 

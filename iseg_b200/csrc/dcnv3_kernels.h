@@ -7,6 +7,13 @@ namespace dcnv3 {
 
 void count_launch(unsigned n);
 
+// optional per-kernel timing of the tiled backward (bench.py roofline): events recorded on the launch stream
+struct KernelTiming {
+    bool enabled = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // before gather, scatter, redo, merge, after
+};
+KernelTiming& kernel_timing();
+
 // generic path (dcnv3_generic.cu)
 cudaError_t launch_fwd_generic(const void* x, const void* offset, const void* mask, void* out,
                                const KParams& q, int dtype, cudaStream_t st);

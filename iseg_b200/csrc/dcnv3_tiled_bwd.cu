@@ -581,20 +581,6 @@ merge_far_kernel(T* __restrict__ grad_x, const FarWs ws, const KParams q, size_t
     *reinterpret_cast<unsigned*>(ws.dirty + i4) = 0u;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
-amax_go_kernel(const T* __restrict__ grad_out, size_t n, WsHeader* hd) {
-    float a = 0.f;
-    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
-    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
-        const float4 v = Elem<T>::ld4(grad_out + i);  // n is a multiple of 16
-        a = fmaxf(a, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(&hd->amax_go_bits, __float_as_uint(a));
-}
-
 // ---- host side -----------------------------------------------------------------------------------
 static BwdGeom make_bwd_geom(const KParams& q) {
     BwdGeom bg;
@@ -661,6 +647,8 @@ static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const v
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }
+    KernelTiming& kt = kernel_timing();
+    if (kt.enabled) cudaEventRecord(kt.ev[0], st);
     const unsigned grid_a = (unsigned)((size_t)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
     // (also leaves max|grad_out| in the workspace header: the fixed-point scale of the scatter kernel)
     bwd_gather_kernel<T><<<grid_a, 256, (size_t)tg.bw * tg.bh * kCellBytes + 8 * kGatherStageBytes<T>, st>>>(
@@ -668,13 +656,17 @@ static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const v
         q, tg);
 
     // ---- grad_x ----
+    if (kt.enabled) cudaEventRecord(kt.ev[1], st);
     const unsigned grid_b = (unsigned)(tiles * bg.chunks);
     bwd_scatter_kernel<T><<<grid_b, threads_b, smem_b, st>>>((const T*)offset, (const T*)mask, (const T*)grad_out,
                                                              (T*)grad_x, ws, q, bg);
+    if (kt.enabled) cudaEventRecord(kt.ev[2], st);
     redo_hot_kernel<T><<<grid_b, 256, bg.wsum_ints * sizeof(int), st>>>((const T*)offset, (const T*)mask,
                                                                         (const T*)grad_out, ws, q, bg);
+    if (kt.enabled) cudaEventRecord(kt.ev[3], st);
     const size_t npg = (size_t)q.n * q.h * q.w * q.G;
     merge_far_kernel<T><<<(unsigned)((npg / 4 + 256) / 256), 256, 0, st>>>((T*)grad_x, ws, q, npg);
+    if (kt.enabled) cudaEventRecord(kt.ev[4], st);
     count_launch(4);
     return cudaGetLastError();
 }
