@@ -255,19 +255,35 @@ struct RowStage {
     // cooperative, coalesced store of staged offset-shaped (144 B / pixel) and mask-shaped (72 B / pixel)
     // results, e.g. grad_offset / grad_mask
     static __device__ __forceinline__ void store_off_msk(const unsigned char* st, T* off_row, T* msk_row, int G,
-                                                         int npx, int lane) {
+                                                         int npx, int ng, int lane) {
         __syncwarp();
-        const int n = npx * 9;
         const size_t off_stride = (size_t)G * 18 * sizeof(T), msk_stride = (size_t)G * 9 * sizeof(T);
+        if (G % C::GQ == 0) {  // every run is complete and 16-byte aligned
+            const int n = npx * 9;
 #pragma unroll
-        for (int i = 0; i < (C::PXW * 9 + 31) / 32; ++i) {
-            const int c = lane + 32 * i;
-            if (c < n) {
-                const int px = (c * 7282) >> 16, r = c - px * 9;  // c / 9 for c < 288
-                *(reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(off_row) + px * off_stride) + r) =
-                    *reinterpret_cast<const uint4*>(st + px * OFF_PX + r * 16);
-                *(reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(msk_row) + px * msk_stride) + r) =
-                    *reinterpret_cast<const uint2*>(st + OFF_BYTES + px * MSK_PX + r * 8);
+            for (int i = 0; i < (C::PXW * 9 + 31) / 32; ++i) {
+                const int c = lane + 32 * i;
+                if (c < n) {
+                    const int px = (c * 7282) >> 16, r = c - px * 9;  // c / 9 for c < 288
+                    *(reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(off_row) + px * off_stride) + r) =
+                        *reinterpret_cast<const uint4*>(st + px * OFF_PX + r * 16);
+                    *(reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(msk_row) + px * msk_stride) + r) =
+                        *reinterpret_cast<const uint2*>(st + OFF_BYTES + px * MSK_PX + r * 8);
+                }
+            }
+        } else {
+            // group count not a multiple of the chunk: runs are only element aligned and the trailing
+            // chunk has fewer real groups -> element-wise copy of the real part of every run
+            const int ro = ng * 18, rm = ng * 9;  // elements per pixel
+            for (int c = lane; c < npx * ro; c += 32) {
+                const int px = c / ro, r = c - px * ro;
+                reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(off_row) + px * off_stride)[r] =
+                    reinterpret_cast<const T*>(st + px * OFF_PX)[r];
+            }
+            for (int c = lane; c < npx * rm; c += 32) {
+                const int px = c / rm, r = c - px * rm;
+                reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(msk_row) + px * msk_stride)[r] =
+                    reinterpret_cast<const T*>(st + OFF_BYTES + px * MSK_PX)[r];
             }
         }
         __syncwarp();

@@ -200,7 +200,8 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict_
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g_l = lane % C::GQ, px_l = lane / C::GQ;
-    const int g = chunk * C::GQ + g_l;
+    const int g = min(chunk * C::GQ + g_l, q.G - 1);  // phantom groups of a trailing chunk shadow the last one
+    const int ng = min(C::GQ, q.G - chunk * C::GQ);   // real groups in this chunk
     const int rot = Slab<T>::rot_of(px_l);
     const unsigned char* sbase = smem + g_l * (kGC * (int)sizeof(T));
     // per-warp staging slot for the results (stored coalesced once per row segment) and, for the fused
@@ -309,7 +310,7 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict_
             }
         }
         RS::store_off_msk(st, grad_offset + (pix0 * q.G + chunk * C::GQ) * 18,
-                          grad_mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, npx, lane);
+                          grad_mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, npx, ng, lane);
     }
     if (!waited) mbar_wait(&bar, 0);
 #pragma unroll
@@ -346,6 +347,7 @@ __device__ __forceinline__ void scatter_pass(int* acc, int* wsum, const T* __res
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g_l = lane % kSG, px_l = lane / kSG;
     const int g = chunk * kSG + g_l;
+    if (g >= q.G) return;  // phantom group of a trailing chunk (no warp-level synchronisation in this walk)
     const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
     const int ux0 = jx << bg.tj_log2, uy0 = jy << bg.tj_log2;
     const int tjw = min(bg.tj, q.w - ux0), tjh = min(bg.tj, q.h - uy0);
@@ -502,6 +504,7 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
         const int cy = cl / tjw, cx = cl % tjw;
         const int cell = cy * bg.pitch + cx;
         const int gl = (piece * 4) / kGC;
+        if (chunk * kSG + gl >= q.G) continue;  // phantom group
         // a hot (cell, group) may have wrapped: it is zeroed here and recomputed by redo_hot_kernel
         const bool hot = wsum[cell * kSG + gl] > kBudget;
         any_hot |= hot;
@@ -590,7 +593,7 @@ static BwdGeom make_bwd_geom(const KParams& q) {
     bg.pitch = bg.tj;
     bg.tiles_x = (q.w + bg.tj - 1) / bg.tj;
     bg.tiles_y = (q.h + bg.tj - 1) / bg.tj;
-    bg.chunks = q.G / kSG;
+    bg.chunks = (q.G + kSG - 1) / kSG;
     // source pixels are searched up to ~3 offset units (+1 for the tap grid) beyond the tile
     const float r = fmaxf(q.wm2_f / q.win_f, q.hm2_f / q.hin_f) * q.scale;
     bg.margin = min((int)ceilf((1.0f + 3.0f) * r), 12);

@@ -54,7 +54,8 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict__
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g_l = lane % C::GQ, px_l = lane / C::GQ;
-    const int g = chunk * C::GQ + g_l;
+    const bool real_g = chunk * C::GQ + g_l < q.G;          // false for the phantom groups of a trailing chunk
+    const int g = min(chunk * C::GQ + g_l, q.G - 1);        // (phantom lanes shadow the last group, never store)
     const int rot = Slab<T>::rot_of(px_l);
     const unsigned char* sbase = smem + g_l * (kGC * (int)sizeof(T));
     const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
@@ -63,7 +64,7 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict__
     (void)th;
 
     for (int p0 = warp * C::PXW; p0 < npix; p0 += (blockDim.x >> 5) * C::PXW) {
-        const bool valid = p0 + px_l < npix;
+        const bool valid = real_g && p0 + px_l < npix;
         const int pix = min(p0 + px_l, npix - 1);  // idle lanes shadow the last pixel (loads stay in bounds)
         const int h = h0 + pix / tw, w = w0 + pix % tw;
         const size_t pg = (((size_t)n * q.ho + h) * q.wo + w) * q.G + g;
@@ -171,9 +172,9 @@ bool make_x_tensor_map(CUtensorMap* map, const void* x, const KParams& q, int dt
 
 // Tiled kernels serve the InternImage configuration only.
 bool tiled_applicable(const KParams& q, int dtype) {
-    const int gq = dtype == DCNV3_F32 ? 2 : 4;
+    (void)dtype;  // any group count: the last chunk may be partly empty (phantom groups are masked)
     return q.P == 9 && q.kh == 3 && q.sh == 1 && q.sw == 1 && q.dh == 1 && q.dw == 1 && q.gc == kGC &&
-           q.G % gq == 0 && q.ho == q.h && q.wo == q.w && q.ph == 1 && q.pw == 1 && q.scale > 0.f &&
+           q.ho == q.h && q.wo == q.w && q.ph == 1 && q.pw == 1 && q.scale > 0.f &&
            q.scale <= 16.f && q.h <= 16384 && q.w <= 16384;
 }
 
@@ -187,7 +188,8 @@ TileGeom make_geom(const KParams& q, int dtype, int th, int tw, float reach, int
     tg.tw = min(tw, q.wo);
     tg.tiles_h = (q.ho + tg.th - 1) / tg.th;
     tg.tiles_w = (q.wo + tg.tw - 1) / tg.tw;
-    tg.chunks = q.G / (dtype == DCNV3_F32 ? 2 : 4);
+    const int gq = dtype == DCNV3_F32 ? 2 : 4;
+    tg.chunks = (q.G + gq - 1) / gq;  // a trailing partial chunk reads zero-filled phantom groups (TMA OOB)
     const float ax = q.wm2_f / q.hin_f, ay = q.hm2_f / q.win_f;
     const float rx = q.wm2_f / q.win_f, ry = q.hm2_f / q.hin_f;
     for (;; reach *= 0.75f) {

@@ -74,7 +74,8 @@ CASES = [  # n, h, w, G, gc, sigma, offset_scale
     (1, 49, 97, 4, 16, 4.0, 1.0),      # odd, non-square (sliding-window tile shapes), wide offsets
     (1, 40, 40, 10, 16, 1.0, 2.0),     # InternImage-L style: G=10, offset_scale 2
     (1, 20, 20, 40, 32, 1.0, 2.0),     # gc = 32
-    (1, 24, 24, 7, 16, 1.0, 1.0),      # odd group count (InternImage-B)
+    (1, 24, 24, 7, 16, 1.0, 1.0),      # odd group count (InternImage-B): trailing half-empty chunk
+    (2, 40, 33, 5, 16, 2.0, 1.0),      # InternImage-S stage 1 style (G=5)
     (1, 9, 11, 3, 5, 1.5, 1.0),        # gc not a multiple of 4 -> scalar path
 ]
 
@@ -94,7 +95,7 @@ def test_random_fp32_vs_c_oracle(ops, case):
     assert rel_err(gm, rm) <= TOL_F32
 
 
-@pytest.mark.parametrize("case", CASES[:4] + CASES[5:7])
+@pytest.mark.parametrize("case", CASES[:4] + CASES[5:9])
 def test_random_bf16(ops, case):
     n, h, w, g, gc, sigma, scale = case
     x, off, m, go = make_inputs(n, h, w, g, gc, sigma=sigma, seed=7 + h)
