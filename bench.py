@@ -210,6 +210,8 @@ def run_ours(args, rank, world, local_rank):
     device = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: ONE JSON line only
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=device)

@@ -1,0 +1,4 @@
+from .intern_image import (  # noqa: F401
+    InternImage, InternImageBlock, InternImageLayer, intern_image_base, intern_image_huge, intern_image_large,
+    intern_image_small, intern_image_tiny,
+)
