@@ -233,8 +233,9 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict_
         if (logits) softmax_stats9<T>(mskp, mx, inv_sum);
         float ref0, ref1;
         ref_point(q, h, w, ref0, ref1);
-        float ox, oy, ml;
+        float ox, oy, ml, ox2, oy2, ml2;
         load_tap_inputs<T>(offp, mskp, 0, ox, oy, ml);
+        load_tap_inputs<T>(offp, mskp, 1, ox2, oy2, ml2);
         if (!waited) {
             mbar_wait(&bar, 0);
             waited = true;
@@ -243,7 +244,8 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict_
 #pragma unroll 1
         for (int p = 0; p < kTaps; ++p) {
             const float cx = ox, cy = oy, cm = ml;
-            if (p + 1 < kTaps) load_tap_inputs<T>(offp, mskp, p + 1, ox, oy, ml);
+            ox = ox2; oy = oy2; ml = ml2;
+            if (p + 2 < kTaps) load_tap_inputs<T>(offp, mskp, p + 2, ox2, oy2, ml2);  // two taps ahead
             const Tap t = make_tap(q, ref0, ref1, p, cx, cy);
             const int bx = t.x0 - cx0, by = t.y0 - cy0;
             const bool inbox = bx >= 0 && bx + 1 < tg.bw && by >= 0 && by + 1 < tg.bh;
