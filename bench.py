@@ -68,7 +68,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -110,7 +110,11 @@ def cpu_reference_run(steps, warmup, sample_batch=1, budget_s=None):
     from oracle import c_oracle
 
     c_oracle.lib(native=True)
-    threads = c_oracle.max_threads()
+    # every host thread this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm ignores it)
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
     rng = np.random.default_rng(0)
     data = []
     for h, w, c, g, depth in STAGES:
@@ -125,10 +129,10 @@ def cpu_reference_run(steps, warmup, sample_batch=1, budget_s=None):
     def one_step():
         for x, off, m, go, g, depth in data:
             for _ in range(depth):
-                c_oracle.forward(x, off, m, groups=g, group_channels=GC)
+                c_oracle.forward(x, off, m, groups=g, group_channels=GC, nthreads=threads)
         for x, off, m, go, g, depth in reversed(data):
             for _ in range(depth):
-                c_oracle.backward(x, off, m, go, groups=g, group_channels=GC)
+                c_oracle.backward(x, off, m, go, groups=g, group_channels=GC, nthreads=threads)
 
     for _ in range(warmup):
         one_step()
@@ -210,8 +214,8 @@ def run_ours(args, rank, world, local_rank):
     device = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: ONE JSON line only
+        # keep NCCL's banner / debug output off stdout: rank 0 prints ONE JSON line there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=device)
