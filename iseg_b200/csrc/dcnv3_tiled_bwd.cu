@@ -377,13 +377,21 @@ __device__ __forceinline__ void scatter_pass(int* acc, int* wsum, const T* __res
             if (logits) softmax_stats9<T>(mskp, mx, inv_sum);
             float ref0, ref1;
             ref_point(q, h, w, ref0, ref1);
-            Range covx = {0, 0}, covy = {0, 0};
+            // un-padded cell range [lo, hi] covered by the tiles whose owners visit this pixel themselves:
+            // a landing of a home pixel outside it is "far" and takes the side path
+            int cvx_lo = 0, cvx_hi = 0, cvy_lo = 0, cvy_hi = 0;
             if (is_home) {
-                covx = covering_tiles(nominal_ux(q, h), bg.tiles_x, bg.tj, bg.tj_log2, bg.margin);
-                covy = covering_tiles(nominal_uy(q, w), bg.tiles_y, bg.tj, bg.tj_log2, bg.margin);
+                const Range cx = covering_tiles(nominal_ux(q, h), bg.tiles_x, bg.tj, bg.tj_log2, bg.margin);
+                const Range cy = covering_tiles(nominal_uy(q, w), bg.tiles_y, bg.tj, bg.tj_log2, bg.margin);
+                cvx_lo = cx.lo << bg.tj_log2; cvx_hi = ((cx.hi + 1) << bg.tj_log2) - 1;
+                cvy_lo = cy.lo << bg.tj_log2; cvy_hi = ((cy.hi + 1) << bg.tj_log2) - 1;
             }
             int G[16];
             bool have_g = false;
+            if (is_home) {  // every tap of a home pixel lands: convert grad_out once, with the whole warp converged
+                load_fixed_point_go<T>(grad_out + pg * kGC, sg, px_l, G);
+                have_g = true;
+            }
             float ox, oy, ml;
             load_tap_inputs<T>(offp, mskp, 0, ox, oy, ml);
 #pragma unroll 1
@@ -403,6 +411,9 @@ __device__ __forceinline__ void scatter_pass(int* acc, int* wsum, const T* __res
                 if (!is_home && !(row0 || row1)) continue;
                 const float mm = logits ? expf(cm - mx) * inv_sum : cm;
                 const int par = (p ^ h ^ w) & 1;
+                // can a corner of this tap be far?  (only then is the out-of-tile part looked at)
+                const int ax0 = lx + ux0, ay0 = ly + uy0;
+                const bool far_possible = is_home && (ax0 < cvx_lo || ax0 + 1 > cvx_hi || ay0 < cvy_lo || ay0 + 1 > cvy_hi);
                 unsigned side_mask = 0;  // corners that need the 64-bit side path
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {  // a b c d = (y0,x0) (y1,x0) (y0,x1) (y1,x1)
@@ -410,7 +421,7 @@ __device__ __forceinline__ void scatter_pass(int* acc, int* wsum, const T* __res
                     const float wf = ((k >> 1) ? axx.d0 : axx.d1) * ((k & 1) ? axy.d0 : axy.d1) * mm;
                     if (wf == 0.f) continue;
                     if (!in_tile) {
-                        if (is_home) side_mask |= 1u << k;  // far test below
+                        if (far_possible) side_mask |= 1u << k;  // exact far test below
                         continue;
                     }
                     const int cell = (ly + (k & 1)) * bg.pitch + lx + (k >> 1);
@@ -419,8 +430,9 @@ __device__ __forceinline__ void scatter_pass(int* acc, int* wsum, const T* __res
                         if (wsum[cellg] > kBudget) side_mask |= 1u << k;
                         continue;
                     }
-                    // a raw mask beyond the fixed-point range (|Wk| >= 4) makes the cell hot by itself
-                    atomicAdd(&wsum[cellg], fabsf(wf) < 3.9f ? (int)ceilf(fabsf(wf) * 1024.f) : kBudget + 1);
+                    // a raw mask beyond the fixed-point range (|Wk| >= 3.9) makes the cell hot by itself
+                    const int wb = __float2int_ru(fabsf(wf) * 1024.f);
+                    atomicAdd(&wsum[cellg], wb < 3994 ? wb : kBudget + 1);
                     if (MODE == 1) continue;
                     if (!have_g) {
                         load_fixed_point_go<T>(grad_out + pg * kGC, sg, px_l, G);
@@ -440,9 +452,8 @@ __device__ __forceinline__ void scatter_pass(int* acc, int* wsum, const T* __res
                         const int ax = lx + (k >> 1) + ux0, ay = ly + (k & 1) + uy0;  // un-padded image coords
                         if (MODE == 0) {
                             if (ax < 0 || ax >= q.w || ay < 0 || ay >= q.h) continue;  // zero ring: gradient dropped
-                            const int tx = ax >> bg.tj_log2, ty = ay >> bg.tj_log2;
                             // the owner of that tile visits this pixel itself unless the tap is far
-                            if (tx >= covx.lo && tx <= covx.hi && ty >= covy.lo && ty <= covy.hi) continue;
+                            if (ax >= cvx_lo && ax <= cvx_hi && ay >= cvy_lo && ay <= cvy_hi) continue;
                         }
                         if (!have_g) {
                             load_fixed_point_go<T>(grad_out + pg * kGC, sg, px_l, G);
@@ -470,7 +481,7 @@ __device__ __forceinline__ void scatter_pass(int* acc, int* wsum, const T* __res
 }
 
 template <typename T>
-__global__ void __launch_bounds__(768, 1)
+__global__ void __launch_bounds__(640, 1)
 bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
                    T* __restrict__ grad_x, const FarWs ws, const KParams q, const BwdGeom bg) {
     extern __shared__ __align__(16) int acc[];  // [acc_ints] accumulator + [wsum_ints] weight counters
@@ -639,7 +650,7 @@ static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const v
     CUtensorMap map;
     if (!make_x_tensor_map(&map, x, q, dtype, tg.bw, tg.bh)) return cudaErrorNotSupported;
     const size_t smem_b = (size_t)(bg.acc_ints + bg.wsum_ints) * sizeof(int);
-    const int threads_b = bg.tj == 32 ? 768 : 256;
+    const int threads_b = bg.tj == 32 ? 640 : 256;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
