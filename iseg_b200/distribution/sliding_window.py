@@ -41,3 +41,30 @@ def stitch(tile_logits, tiles, height, width):
         acc[:, y:y + h, x:x + w] += t
         cnt[:, y:y + h, x:x + w] += 1
     return acc, cnt
+
+
+def inference_with_sliding_window(model_fn, image, crop_h=769, crop_w=769, strategy=None):
+    """Sliding-window inference with the tiles dealt over the ranks of `strategy`
+    (reference core_inference.py:230-304 runs them sequentially on one device).
+
+    image: [N, H, W, C] on this rank's device (every rank holds the full image, as every replica does in
+    the reference); model_fn maps a [N, h, w, C] tile to [N, h, w, K] logits.  Every rank returns the full
+    [N, H, W, K] result: per-rank partial sums and the count map are combined by ONE all-reduce."""
+    import torch.distributed as dist
+
+    n, height, width, _ = image.shape
+    tiles = sliding_window_tiles(height, width, crop_h, crop_w)
+    world = strategy.world_size if strategy is not None else 1
+    rank = strategy.rank if strategy is not None else 0
+    mine = shard_tiles(tiles, world, rank)
+    logits = [model_fn(image[:, y:y + h, x:x + w]) for (y, x, h, w) in mine]
+    if logits:
+        acc, cnt = stitch(logits, mine, height, width)
+    else:  # more ranks than tiles: contribute zeros of the right shape (K from a 1x1 probe is avoided)
+        k = model_fn(image[:, :tiles[0][2], :tiles[0][3]]).shape[-1]
+        acc = image.new_zeros((n, height, width, k))
+        cnt = image.new_zeros((1, height, width, 1))
+    if world > 1:
+        dist.all_reduce(acc)
+        dist.all_reduce(cnt)
+    return acc / cnt

@@ -30,6 +30,16 @@ def test_sliding_window_indices_match_reference_rule():
     assert [len(shard_tiles(tiles, 4, r)) for r in range(4)] == [2, 2, 2, 2]
 
 
+def test_sliding_window_inference_single_rank_matches_sequential_rule():
+    from iseg_b200.distribution import inference_with_sliding_window
+    torch.manual_seed(0)
+    img = torch.randn(1, 40, 70, 3)
+    wgt = torch.randn(3, 5)
+    model = lambda t: t @ wgt  # noqa: E731  (pointwise: every window must agree where they overlap)
+    out = inference_with_sliding_window(model, img, crop_h=24, crop_w=24)
+    assert torch.allclose(out, img @ wgt, atol=1e-5)
+
+
 def _worker(rank, world, port, results):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
@@ -44,6 +54,12 @@ def _worker(rank, world, port, results):
     ok = torch.equal(gathered, full * 2 + 1)  # bit-exact: images never interact
     s = all_reduce_values(torch.tensor([float(local.shape[0])]))
     ok = ok and s.item() == 5.0
+    # sliding-window tiles dealt over the two ranks, one all-reduce at the end
+    from iseg_b200.distribution import inference_with_sliding_window
+    img = torch.randn(1, 40, 70, 3)
+    wgt = torch.randn(3, 4)
+    out = inference_with_sliding_window(lambda t: t @ wgt, img, crop_h=24, crop_w=24, strategy=st)
+    ok = ok and torch.allclose(out, img @ wgt, atol=1e-5)
     results[rank] = bool(ok)
     st.close()
 
