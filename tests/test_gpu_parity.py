@@ -111,6 +111,41 @@ def test_random_bf16(ops, case):
     assert rel_err(gm, rm) <= TOL_BF16
 
 
+def test_fuzz_shapes_offsets_vs_c_oracle(ops):
+    """Seeded fuzzing over what the reference's signature admits: odd / non-square sizes, any group count,
+    gc in {4,8,16,32}, offset_scale, offset spread from 0 to far beyond the staged halo, raw (un-normalised,
+    signed) masks, VALID padding, 1x1..5x5 kernels.  Tiled and generic paths are both hit."""
+    rng = np.random.default_rng(2024)
+    for trial in range(24):
+        k = int(rng.choice([3, 3, 3, 3, 1, 5]))
+        padding = str(rng.choice(["SAME", "SAME", "SAME", "VALID"]))
+        g = int(rng.integers(1, 11))
+        gc = int(rng.choice([16, 16, 16, 4, 8, 32]))
+        n, h, w = int(rng.integers(1, 4)), int(rng.integers(k, 45)), int(rng.integers(k, 45))
+        sigma = float(rng.choice([0.0, 0.5, 1.0, 3.0, 10.0]))
+        scale = float(rng.choice([1.0, 1.0, 2.0, 0.5]))
+        ho, wo = (h, w) if padding == "SAME" else (h - k + 1, w - k + 1)
+        p = k * k
+        x = rng.standard_normal((n, h, w, g * gc), dtype=np.float32)
+        off = (sigma * rng.standard_normal((n, ho, wo, g * p * 2), dtype=np.float32)).astype(np.float32)
+        m = rng.standard_normal((n, ho, wo, g * p), dtype=np.float32)  # raw mask: any sign / magnitude
+        if trial % 3 == 0:
+            m = O.mask_softmax(m, g)
+        if trial % 5 == 0:
+            m *= 7.0  # beyond the fixed-point weight range of the fast path -> exact side path
+        go = rng.standard_normal((n, ho, wo, g * gc), dtype=np.float32) * float(rng.choice([1.0, 1e-6, 1e4]))
+        kw = dict(kernel_size=(k, k), padding=padding, groups=g, group_channels=gc, offset_scale=scale)
+        out, gx, goff, gm = run_op(ops, x, off, m, go, **kw)
+        ref_out = c_oracle.forward(x, off, m, **kw)
+        _, roff, rm = c_oracle.backward(x, off, m, go, **kw)
+        # grad_x yardstick: fp32 per-tap arithmetic (as the reference) with an exact (float64) scatter sum --
+        # with large cancelling contributions an fp32 running sum is itself several 1e-5 off
+        rx, _, _ = O.backward(x, off, m, go, accumulate=np.float64, **kw)
+        tag = (trial, n, h, w, g, gc, k, padding, sigma, scale)
+        for a, b, name in ((out, ref_out, "out"), (gx, rx, "grad_x"), (goff, roff, "grad_offset"), (gm, rm, "grad_mask")):
+            assert rel_err(a, b) <= TOL_F32 or not np.abs(b).max() > 0, (name, rel_err(a, b), tag)
+
+
 def test_backward_bitwise_reproducible(ops):
     x, off, m, go = make_inputs(4, 64, 64, 8, 16, sigma=2.0, seed=3)
     kw = dict(groups=8, group_channels=16)
