@@ -572,29 +572,40 @@ redo_hot_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const 
 }
 
 // grad_x += side buffer for the (pixel, group)s flagged in the dirty map; leaves the side buffer and
-// the map zeroed for the next call.  One thread per 4 (pixel, group)s; the map is one byte each.
+// the map zeroed for the next call.  Each warp scans 128 map bytes; flagged entries are then handled by
+// half-warps, one lane per channel (the 16 channels of a group are contiguous in both buffers).
 template <typename T>
 __global__ void __launch_bounds__(256)
 merge_far_kernel(T* __restrict__ grad_x, const FarWs ws, const KParams q, size_t count) {
+    const int lane = threadIdx.x & 31;
     const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i4 >= count) return;
-    const unsigned flags = *reinterpret_cast<const unsigned*>(ws.dirty + i4);  // map is padded to 256 bytes
-    if (flags == 0) return;
+    unsigned flags = 0;
+    if (i4 < count) flags = *reinterpret_cast<const unsigned*>(ws.dirty + i4);  // map is padded to 256 bytes
+    unsigned any = __ballot_sync(0xffffffffu, flags != 0);
+    if (any == 0) return;
     const double inv_s = ldexp(1.0, -(30 - fixed_exponent_raw(ws.hd) + kWShift - 32));
-    for (int j = 0; j < 4; ++j) {
-        if (((flags >> (8 * j)) & 0xffu) == 0 || i4 + j >= count) continue;
-        const size_t idx = (i4 + j) * kGC;
-#pragma unroll 4
-        for (int c = 0; c < kGC; ++c) {
-            const long long v = (long long)ws.acc64[idx + c];
-            if (v != 0) {
-                // |v| can exceed 2^24: go through double so that the exact total is rounded once
-                Elem<T>::st(grad_x + idx + c, Elem<T>::ld_plain(grad_x + idx + c) + (float)((double)v * inv_s));
-                ws.acc64[idx + c] = 0ull;
+    const size_t warp_base = i4 - (size_t)lane * 4;
+    while (any) {
+        const int src = __ffs(any) - 1;
+        any &= any - 1;
+        const unsigned f = __shfl_sync(0xffffffffu, flags, src);
+        // the up to four flagged entries of lane `src`: two per pass, one half-warp each
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int j = pass * 2 + (lane >> 4);
+            const size_t e = warp_base + (size_t)src * 4 + j;
+            if (((f >> (8 * j)) & 0xffu) != 0 && e < count) {
+                const size_t idx = e * kGC + (lane & 15);
+                const long long v = (long long)ws.acc64[idx];
+                if (v != 0) {
+                    // |v| can exceed 2^24: go through double so that the exact total is rounded once
+                    Elem<T>::st(grad_x + idx, Elem<T>::ld_plain(grad_x + idx) + (float)((double)v * inv_s));
+                    ws.acc64[idx] = 0ull;
+                }
             }
         }
     }
-    *reinterpret_cast<unsigned*>(ws.dirty + i4) = 0u;
+    if (flags != 0) *reinterpret_cast<unsigned*>(ws.dirty + i4) = 0u;
 }
 
 // ---- host side -----------------------------------------------------------------------------------
