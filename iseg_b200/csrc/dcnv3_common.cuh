@@ -117,6 +117,9 @@ struct Elem<float> {
     static __device__ __forceinline__ float4 ld4(const float* p) {
         return __ldg(reinterpret_cast<const float4*>(p));
     }
+    static __device__ __forceinline__ float4 ld4_plain(const float* p) {
+        return *reinterpret_cast<const float4*>(p);
+    }
     static __device__ __forceinline__ void st4(float* p, float4 v) {
         *reinterpret_cast<float4*>(p) = v;
     }
@@ -132,6 +135,15 @@ struct Elem<__nv_bfloat16> {
     }
     static __device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
         const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+        float4 v;
+        v.x = __uint_as_float(r.x << 16);
+        v.y = __uint_as_float(r.x & 0xffff0000u);
+        v.z = __uint_as_float(r.y << 16);
+        v.w = __uint_as_float(r.y & 0xffff0000u);
+        return v;
+    }
+    static __device__ __forceinline__ float4 ld4_plain(const __nv_bfloat16* p) {
+        const uint2 r = *reinterpret_cast<const uint2*>(p);
         float4 v;
         v.x = __uint_as_float(r.x << 16);
         v.y = __uint_as_float(r.x & 0xffff0000u);

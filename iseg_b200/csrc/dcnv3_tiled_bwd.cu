@@ -6,26 +6,33 @@
 //      the four dot products <grad_out, I_k> with packed FFMA2; from them the two gradients
 //      (SURVEY.md App. A.2).  No cross-lane reduction, no atomics.
 //
-//  bwd_scatter_kernel -- grad_x, OWNER COMPUTES.  One CTA = one 16x16 tile J of INPUT pixels x one group
-//      chunk.  Shared memory holds an int32 accumulator for exactly the cells of J.  The CTA walks every
-//      output pixel whose taps can plausibly reach J (home pixels + a margin) and adds
-//          q = floor(G[c] * Wk / 2^32) + b        G = grad_out, Wk = mask * bilinear weight (fixed point),
-//                                                 b = parity bit that makes the truncation unbiased
-//      with shared-memory integer atomics (ATOMS.ADD; measured 31.6 updates/clk/SM when conflict free,
-//      tools/microbench2.cu; rows and cells of the accumulator have odd pitches so that neighbouring
-//      pixels fall into different banks).  Integer addition is associative: the result is bitwise
-//      independent of warp scheduling.  Every cell of J is owned by exactly one CTA: grad_x is written
-//      once, there is no cross-CTA reduction and no float atomic anywhere.
+//  bwd_scatter_kernel -- grad_x.  One CTA = one TJ x TJ tile J of INPUT pixels x one chunk of two groups.
+//      It visits exactly the output pixels whose nominal sampling position lies in J (its HOME pixels;
+//      every output pixel is home to exactly one tile) and adds, for each of their 9 x 4 landings,
+//          q = round(G[c] * Wk / 2^32)            G = grad_out, Wk = mask * bilinear weight (fixed point)
+//      to an int32 accumulator BOX in shared memory that covers J plus a ring of a few cells (and the
+//      zero ring of tf.pad where J touches the image border, so that landings there need no test).
+//      The adds are shared-memory integer atomics (ATOMS.ADD; 31.6 updates/clk/SM when conflict free,
+//      tools/microbench2.cu): a lane owns one (pixel, group) and walks its 16 channels in an order
+//      XOR-rotated by its pixel index, so the 32 lanes of every ATOMS hit 32 different banks whatever
+//      cells they land on; the four corners of a tap share one set of rotated addresses (the box pitch
+//      is a compile-time constant, the other three corners are immediate offsets).
+//      Integer addition is associative: the sums are bitwise independent of warp scheduling.
+//      At the end the cells of J are converted and stored once (plain stores, no float atomic anywhere);
+//      the ring cells -- they belong to neighbouring tiles -- are added to a 64-bit fixed-point side
+//      buffer with integer global atomics and flagged in a dirty map; merge_far_kernel folds the side
+//      buffer into grad_x.
 //
-//  Overflow / far taps -- every landing also adds ceil(|Wk|*1024) to a per-(cell, group) counter; while
-//      that sum stays <= 8*1024 the int32 accumulator provably cannot wrap.  Cells that exceed it
-//      ("hot", only with adversarial inputs) are zeroed at flush and recomputed exactly by
-//      redo_hot_kernel with 64-bit integer global atomics; taps of home pixels that land in a tile
-//      whose owner does not visit the pixel (|offset| beyond the margin) take the same 64-bit side
-//      path directly.  The side buffer uses the SAME integers q and is merged by merge_far_kernel; which
-//      path a contribution takes is a deterministic function of the inputs.
+//  Overflow / far taps -- every tap also adds ceil(|mask| * 1025) to a counter of its anchor cell; the
+//      weight that reached a cell is bounded by the four counters around it, and while that bound stays
+//      <= 15*1024 the int32 accumulator provably cannot wrap.  Cells that exceed it ("hot", only with
+//      adversarial inputs) are skipped at flush and recomputed exactly by redo_hot_kernel straight into
+//      the 64-bit side buffer; landings beyond the box (|offset| larger than the ring) take the same
+//      side path directly.  The side buffer uses the SAME integers q; which path a contribution takes is
+//      a deterministic function of the inputs.
 //
-// The common scale comes from max|grad_out| (amax_go_kernel): G = round(go * 2^eg), 2^29 <= max|G| < 2^30.
+// The common scale comes from max|grad_out| (left in the workspace header by bwd_gather_kernel):
+// G = round(go * 2^eg), 2^29 <= max|G| < 2^30.
 #include "dcnv3_kernels.h"
 #include "dcnv3_tiled.cuh"
 
@@ -34,16 +41,28 @@ namespace dcnv3 {
 constexpr int kSG = 2;             // groups per scatter CTA (lane = pixel * kSG + group, 16 pixels per warp)
 constexpr int kSCell = kSG * kGC;   // accumulator ints per cell: exactly 32 banks wide, so the bank of an
                                    // update depends only on (group, channel) and never on the cell
-constexpr int kBudget = 8 * 1024;  // sum of ceil(|Wk| * 1024) allowed in the int32 accumulator
+constexpr int kBudget = 15 * 1024;  // 1024 * (sum of |Wk|) allowed in one int32 accumulator: |q| <= 2^27 |Wk|
 constexpr int kWShift = 29;        // Wk fixed point: round(Wk * 2^29), |Wk| < 4
+constexpr int kRingLo = 4;         // largest ring below / above a tile (cells); box pitch = TJ + 9
+constexpr int kRingHi = 5;
+
+// compile-time shape of the scatter kernel for a tile edge of TJ input cells
+template <int TJ>
+struct ScatterShape {
+    static constexpr int PITCH = TJ + kRingLo + kRingHi;   // accumulator row pitch in cells (41 / 25)
+    // pitch of the weight counters: one extra column, and odd, so that the 16 pixels of a warp -- they walk
+    // down a column of cells -- spread their counters over all banks
+    static constexpr int WPITCH = (PITCH + 1) | 1;
+    static constexpr int THREADS = TJ == 32 ? 640 : 256;
+    static constexpr int MIN_CTAS = TJ == 32 ? 1 : 2;
+};
 
 struct BwdGeom {
     int tj, tj_log2;       // input tile edge in cells (16 or 32) and its log2
-    int pitch;             // accumulator row pitch in cells
     int tiles_x, tiles_y;  // tiles of tj x tj un-padded input pixels
-    int chunks;            // G / kSG
-    int margin;            // cells by which the scatter kernel looks beyond J for source pixels
-    int acc_ints, wsum_ints;
+    int chunks;            // ceil(G / kSG)
+    int ring_lo, ring_hi;  // ring of box cells kept below / above the tile (clipped to the image + zero ring)
+    int box_rows;          // rows of the largest box (<= tj + ring_lo + ring_hi)
 };
 
 struct FarWs {
@@ -76,16 +95,8 @@ __device__ __forceinline__ int first_ge(F nominal, int n, int a, int num_scale, 
 
 struct Range { int lo, hi; };
 
-// source range along one axis for tile index j: every i with
-//   nominal(i) in [j*tj - margin, j*tj + tj + margin)   or   home(i) == j
-template <typename F>
-__device__ __forceinline__ Range window_range(F nominal, int n, int j, int ntiles, int tj, int margin, int num,
-                                              int den) {
-    Range r;
-    r.lo = (j == 0) ? 0 : first_ge(nominal, n, j * tj - margin, num, den);
-    r.hi = (j == ntiles - 1) ? n : first_ge(nominal, n, j * tj + tj + margin, num, den);
-    return r;
-}
+// home range along one axis for tile index j: every i with nominal(i) in [j*tj, j*tj + tj); the first
+// tile also takes nominal < 0 and the last one nominal >= extent
 template <typename F>
 __device__ __forceinline__ Range home_range(F nominal, int n, int j, int ntiles, int tj, int num, int den) {
     Range r;
@@ -93,30 +104,15 @@ __device__ __forceinline__ Range home_range(F nominal, int n, int j, int ntiles,
     r.hi = (j == ntiles - 1) ? n : first_ge(nominal, n, j * tj + tj, num, den);
     return r;
 }
-// tile indices j whose owner visits a source index with nominal value u: [lo, hi]  (the complement is
-// "far").  Mirrors window_range: u in [j*tj - margin, j*tj + tj + margin), the first tile also takes
-// u < 0 and the last one u >= extent.
-__device__ __forceinline__ Range covering_tiles(int u, int ntiles, int tj, int tj_log2, int margin) {
-    Range r;
-    int lo = u - tj - margin + 1;  // need j*tj >= lo  (ceil division)
-    lo = lo <= 0 ? 0 : (lo + tj - 1) >> tj_log2;
-    int hi = u + margin;           // need j*tj <= hi  (floor division)
-    hi = hi < 0 ? 0 : hi >> tj_log2;
-    r.lo = min(lo, ntiles - 1);
-    r.hi = min(hi, ntiles - 1);
-    return r;
-}
 
-// called by threads 0..3 of the CTA, one range each
+// called by threads 0 and 1 of the CTA, one range each
 __device__ __forceinline__ void tile_ranges(const KParams& q, const BwdGeom& bg, int jx, int jy, Range& home_h,
-                                            Range& home_w, Range& win_h, Range& win_w) {
+                                            Range& home_w) {
     auto nx = [&](int h) { return nominal_ux(q, h); };
     auto ny = [&](int w) { return nominal_uy(q, w); };
     // output rows h walk along input x, output columns w along input y
     if (threadIdx.x == 0) home_h = home_range(nx, q.ho, jx, bg.tiles_x, bg.tj, q.win - 2, q.hin);
     if (threadIdx.x == 1) home_w = home_range(ny, q.wo, jy, bg.tiles_y, bg.tj, q.hin - 2, q.win);
-    if (threadIdx.x == 2) win_h = window_range(nx, q.ho, jx, bg.tiles_x, bg.tj, bg.margin, q.win - 2, q.hin);
-    if (threadIdx.x == 3) win_w = window_range(ny, q.wo, jy, bg.tiles_y, bg.tj, bg.margin, q.hin - 2, q.win);
 }
 
 template <typename T>
@@ -135,11 +131,12 @@ constexpr int kGatherStageBytes = RowStage<T>::BYTES + (sizeof(T) == 4 ? 0 : 32 
 // channel c ^ rot, so the 32 lanes of one ATOMS (16 pixels x 2 groups) hit 32 different banks
 // whatever cells they land on.
 template <typename T>
-__device__ __forceinline__ void load_fixed_point_go(const T* go, float sg, int rot, int (&G)[16]) {
+__device__ __forceinline__ void load_go(const T* go, f2 (&gf)[8]) {
     using C = Chunk<T>;  // only for the 16-byte piece geometry of T
-    f2 gf[8];
 #pragma unroll
     for (int pc = 0; pc < C::NPIECE; ++pc) load_piece<T>(go + pc * C::CH_PER_PIECE, gf + pc * C::PAIRS);
+}
+__device__ __forceinline__ void fixed_point_go(const f2 (&gf)[8], float sg, int rot, int (&G)[16]) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         G[2 * c] = __float2int_rn(lo_of(gf[c]) * sg);
@@ -158,10 +155,11 @@ __device__ __forceinline__ void load_fixed_point_go(const T* go, float sg, int r
         }
     }
 }
-
-// shared-memory integer add without return value, 32-bit shared address
-__device__ __forceinline__ void red_shared_add(uint32_t addr, int v) {
-    asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+template <typename T>
+__device__ __forceinline__ void load_fixed_point_go(const T* go, float sg, int rot, int (&G)[16]) {
+    f2 gf[8];
+    load_go<T>(go, gf);
+    fixed_point_go(gf, sg, rot, G);
 }
 
 // =====================================================================================================
@@ -323,306 +321,360 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict_
 // =====================================================================================================
 // grad_x
 // =====================================================================================================
-// home pixels first, then the four margin bands of the window
-__device__ __forceinline__ void rect_of(int rect, Range wh, Range ww, Range hh, Range hw, Range& rh, Range& rw) {
-    if (rect == 0) { rh = hh; rw = hw; }                                      // home
-    else if (rect == 1) { rh.lo = wh.lo; rh.hi = hh.lo; rw = ww; }            // band below the home rows
-    else if (rect == 2) { rh.lo = hh.hi; rh.hi = wh.hi; rw = ww; }            // band above
-    else if (rect == 3) { rh = hh; rw.lo = ww.lo; rw.hi = hw.lo; }            // left band
-    else { rh = hh; rw.lo = hw.hi; rw.hi = ww.hi; }                           // right band
+// geometry of one scatter CTA (the same in the scatter and the redo kernel)
+struct TileBox {
+    int ux0, uy0, tjw, tjh;  // tile J in un-padded input coordinates
+    int bx0, by0, bw, bh;    // accumulator box: un-padded origin (-1 = the zero ring of tf.pad) and extent
+};
+__device__ __forceinline__ TileBox make_box(const KParams& q, const BwdGeom& bg, int jx, int jy) {
+    TileBox b;
+    b.ux0 = jx << bg.tj_log2;
+    b.uy0 = jy << bg.tj_log2;
+    b.tjw = min(bg.tj, q.w - b.ux0);
+    b.tjh = min(bg.tj, q.h - b.uy0);
+    b.bx0 = max(b.ux0 - bg.ring_lo, -1);
+    b.by0 = max(b.uy0 - bg.ring_lo, -1);
+    b.bw = min(b.ux0 + b.tjw + bg.ring_hi, q.w + 1) - b.bx0;
+    b.bh = min(b.uy0 + b.tjh + bg.ring_hi, q.h + 1) - b.by0;
+    return b;
 }
 
-// The scatter walk over the source pixels of tile (jx, jy).
-//   MODE 0 (scatter kernel): landings inside J -> int32 shared atomics + weight counters; far landings of
-//                            home pixels -> 64-bit side buffer
+// shared-memory integer add without return value: 32-bit shared address + immediate byte offset
+template <int OFF>
+__device__ __forceinline__ void red_shared_add(uint32_t addr, int v) {
+    asm volatile("red.shared.add.s32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(OFF) : "memory");
+}
+
+// Weight counters.  Every tap adds ceil(|m| * 1025) -- an upper bound of 1024 * (sum of its four |Wk|) --
+// to ONE counter, that of its anchor cell (y0, x0); the counter array has one extra row and column so
+// that anchors one cell outside the box can be counted.  The weight that reached cell (y, x) is then at
+// most the sum of the four counters anchored at (y, x), (y-1, x), (y, x-1), (y-1, x-1).  A raw mask beyond
+// the fixed-point range (|m| >= 3.9) makes the four cells hot by itself.
+__device__ __forceinline__ int weight_units(float mm) {
+    const int wb = __float2int_ru(fabsf(mm) * 1025.f);
+    return wb < 3994 ? wb : kBudget + 1;
+}
+template <int WP>
+__device__ __forceinline__ bool cell_is_hot(const int* wsum, int cy, int cx, int gl) {
+    const int* c = wsum + (cy * WP + cx) * kSG + gl;  // anchor (cy-1, cx-1) lives at index [cy][cx]
+    return (long long)c[0] + c[kSG] + c[WP * kSG] + c[WP * kSG + kSG] > kBudget;
+}
+// one contribution in fixed point: round(G * Wk / 2^32), ties up (a single IMAD.HI with a constant addend)
+__device__ __forceinline__ int qmul(int g, int wq) {
+    return (int)(((long long)g * wq + 0x80000000ll) >> 32);
+}
+__device__ __forceinline__ int weight_fixed(float wf) {
+    return __float2int_rn(fminf(fmaxf(wf, -3.9f), 3.9f) * (float)(1 << kWShift));
+}
+
+// one landing into the 64-bit side buffer: the same integers q as the shared-memory path; |Wk| >= 3.9
+// (raw masks only) is pre-shifted so that the product still fits
+__device__ __forceinline__ void side_add(const FarWs& ws, size_t cellg, const int (&G)[16], int px_l, float wf) {
+    int sh = 0;
+    if (!(fabsf(wf) < 3.9f)) sh = min(max((int)((__float_as_uint(wf) >> 23) & 0xffu) - 128, 0), 30);
+    const int wq = __float2int_rn(ldexpf(wf, kWShift - sh));
+    unsigned long long* dst = ws.acc64 + cellg * kGC;
+#pragma unroll
+    for (int c = 0; c < 16; ++c)  // G[c] holds channel c ^ px_l
+        atomicAdd(dst + (c ^ px_l), (unsigned long long)((long long)qmul(G[c], wq) << sh));
+    ws.dirty[cellg] = 1;
+}
+
+// The scatter walk over the home pixels of one tile.
+//   MODE 0 (scatter kernel): landings inside the box -> int32 shared atomics + weight counters; landings
+//                            beyond it (but inside the image) -> 64-bit side buffer
 //   MODE 1 (redo, pass 1)  : weight counters only
-//   MODE 2 (redo, pass 2)  : landings on hot cells of J -> 64-bit side buffer
-// Source pixels are walked rectangle by rectangle -- the home pixels first, then the four margin bands
-// -- so that a warp holds either home pixels (every tap lands) or margin pixels (almost none does).
-template <typename T, int MODE>
-__device__ __forceinline__ void scatter_pass(int* acc, int* wsum, const T* __restrict__ offset,
+//   MODE 2 (redo, pass 2)  : landings on hot cells of the box -> 64-bit side buffer
+// A work item is one block of 16 pixels x 2 groups; blocks are dealt round-robin to the warps, and the
+// blocks of the last, incomplete round are split by taps over the warps that would otherwise idle.
+template <typename T, int MODE, int TJ>
+__device__ __forceinline__ void scatter_walk(int* acc, int* wsum, const T* __restrict__ offset,
                                              const T* __restrict__ mask, const T* __restrict__ grad_out,
-                                             const FarWs& ws, const KParams& q, const BwdGeom& bg, int n, int chunk,
-                                             int jx, int jy, Range wh, Range ww, Range hh, Range hw, int eg,
-                                             int* next_item) {
+                                             const FarWs& ws, const KParams& q, const TileBox& box, int n, int chunk,
+                                             Range hh, Range hw, int eg) {
+    constexpr int PITCH = ScatterShape<TJ>::PITCH;
+    constexpr int WP = ScatterShape<TJ>::WPITCH;  // pitch of the weight counters
     constexpr int PXW = 32 / kSG;
+    constexpr int ROWB = PITCH * kSCell * 4;  // bytes between accumulator rows
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g_l = lane % kSG, px_l = lane / kSG;
     const int g = chunk * kSG + g_l;
     if (g >= q.G) return;  // phantom group of a trailing chunk (no warp-level synchronisation in this walk)
     const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
-    const int ux0 = jx << bg.tj_log2, uy0 = jy << bg.tj_log2;
-    const int tjw = min(bg.tj, q.w - ux0), tjh = min(bg.tj, q.h - uy0);
     const float sg = ldexpf(1.0f, eg);  // G = round(go * 2^eg), |G| < 2^30
     const size_t img_pixels = (size_t)q.h * q.w;
-    const uint32_t acc_s = MODE == 0 ? smem_u32(acc) : 0u;
-    int deal = 0;  // how many blocks have been dealt so far (mod nwarps)
-    (void)next_item;
+    // the lane's slab inside cell 0, pre-rotated: slab bases are 64-byte aligned, so
+    // base + ((c ^ rot) * 4) == (base ^ rot*4) ^ c*4
+    uint32_t acc_s = MODE == 0 ? ((smem_u32(acc) + (uint32_t)g_l * (kGC * 4u)) ^ ((uint32_t)px_l << 2)) : 0u;
+    // the lane's counter of anchor (-1, -1)
+    uint32_t wsum_s = MODE != 2 ? smem_u32(wsum) + (uint32_t)g_l * 4u : 0u;
+    // opaque to the compiler: otherwise it re-derives both from %tid inside the tap loop (S2R latency)
+    asm volatile("" : "+r"(acc_s), "+r"(wsum_s));
+    const int nw = hw.hi - hw.lo, npix = (hh.hi - hh.lo) * nw;
+    const int nblocks = (npix + PXW - 1) / PXW;
+    const int full_rounds = nblocks / nwarps, rest = nblocks - full_rounds * nwarps;
+    const int parts = rest ? min(kTaps, nwarps / rest) : 1;  // warps per block of the last round
 #pragma unroll 1
-    for (int rect = 0; rect < 5; ++rect) {
-        Range rh, rw;
-        rect_of(rect, wh, ww, hh, hw, rh, rw);
-        const int nw = rw.hi - rw.lo, npix = (rh.hi - rh.lo) * nw;
-        const bool is_home = MODE == 0 && rect == 0;
-        // blocks of PXW pixels are dealt round-robin, continuing across rectangles so that the warps
-        // that got one block fewer in a rectangle get the first ones of the next
-        for (int p0 = ((warp + nwarps - deal) % nwarps) * PXW; p0 < npix; p0 += nwarps * PXW) {
-            const int pix = p0 + px_l;
-            if (pix >= npix) continue;
-            const int h = rh.lo + pix / nw, w = rw.lo + pix % nw;
-            const size_t pg = (((size_t)n * q.ho + h) * q.wo + w) * q.G + g;
-            const T* offp = offset + pg * 18;
-            const T* mskp = mask + pg * 9;
-            float mx = 0.f, inv_sum = 1.f;
-            if (logits) softmax_stats9<T>(mskp, mx, inv_sum);
-            float ref0, ref1;
-            ref_point(q, h, w, ref0, ref1);
-            // un-padded cell range [lo, hi] covered by the tiles whose owners visit this pixel themselves:
-            // a landing of a home pixel outside it is "far" and takes the side path
-            int cvx_lo = 0, cvx_hi = 0, cvy_lo = 0, cvy_hi = 0;
-            if (is_home) {
-                const Range cx = covering_tiles(nominal_ux(q, h), bg.tiles_x, bg.tj, bg.tj_log2, bg.margin);
-                const Range cy = covering_tiles(nominal_uy(q, w), bg.tiles_y, bg.tj, bg.tj_log2, bg.margin);
-                cvx_lo = cx.lo << bg.tj_log2; cvx_hi = ((cx.hi + 1) << bg.tj_log2) - 1;
-                cvy_lo = cy.lo << bg.tj_log2; cvy_hi = ((cy.hi + 1) << bg.tj_log2) - 1;
-            }
-            int G[16];
-            bool have_g = false;
-            if (is_home) {  // every tap of a home pixel lands: convert grad_out once, with the whole warp converged
-                load_fixed_point_go<T>(grad_out + pg * kGC, sg, px_l, G);
-                have_g = true;
-            }
-            float ox, oy, ml;
-            load_tap_inputs<T>(offp, mskp, 0, ox, oy, ml);
+    for (int round = 0; round <= full_rounds; ++round) {
+        int blk = round * nwarps + warp, p_lo = 0, p_hi = kTaps;
+        if (round == full_rounds) {
+            if (warp >= rest * parts) break;
+            const int part = warp % parts;
+            blk = round * nwarps + warp / parts;
+            p_lo = part * kTaps / parts;
+            p_hi = (part + 1) * kTaps / parts;
+        }
+        const int pix = blk * PXW + px_l;
+        if (pix >= npix) continue;
+        const int row = pix / nw;
+        const int h = hh.lo + row, w = hw.lo + (pix - row * nw);
+        const size_t pg = (((size_t)n * q.ho + h) * q.wo + w) * q.G + g;
+        const T* offp = offset + pg * 18;
+        const T* mskp = mask + pg * 9;
+        float ox, oy, ml, ox2, oy2, ml2;
+        load_tap_inputs<T>(offp, mskp, p_lo, ox, oy, ml);
+        load_tap_inputs<T>(offp, mskp, min(p_lo + 1, kTaps - 1), ox2, oy2, ml2);
+        int G[16];
+        f2 gf[8];
+        bool have_g = false;
+        if (MODE == 0) load_go<T>(grad_out + pg * kGC, gf);
+        float mx = 0.f, inv_sum = 1.f;
+        if (logits) softmax_stats9<T>(mskp, mx, inv_sum);
+        float ref0, ref1;
+        ref_point(q, h, w, ref0, ref1);
+        if (MODE == 0) {  // every tap of a home pixel lands: convert grad_out once, with the whole warp converged
+            fixed_point_go(gf, sg, px_l, G);
+            have_g = true;
+        }
 #pragma unroll 1
-            for (int p = 0; p < kTaps; ++p) {
-                const float cxo = ox, cyo = oy, cm = ml;
-                if (p + 1 < kTaps) load_tap_inputs<T>(offp, mskp, p + 1, ox, oy, ml);
-                // one axis at a time: pixels of the margin are mostly rejected after the first coordinate
-                const Axis axx = axis_x(q, ref0, p, cxo);
-                if (!axx.alive) continue;
-                const int lx = axx.i0 - q.pw - ux0;  // corner (y0,x0) relative to J
-                const bool col0 = lx >= 0 && lx < tjw, col1 = lx + 1 >= 0 && lx + 1 < tjw;
-                if (!is_home && !(col0 || col1)) continue;
-                const Axis axy = axis_y(q, ref1, p, cyo);
-                if (!axy.alive) continue;
-                const int ly = axy.i0 - q.ph - uy0;
-                const bool row0 = ly >= 0 && ly < tjh, row1 = ly + 1 >= 0 && ly + 1 < tjh;
-                if (!is_home && !(row0 || row1)) continue;
-                const float mm = logits ? expf(cm - mx) * inv_sum : cm;
-                const int par = (p ^ h ^ w) & 1;
-                // can a corner of this tap be far?  (only then is the out-of-tile part looked at)
-                const int ax0 = lx + ux0, ay0 = ly + uy0;
-                const bool far_possible = is_home && (ax0 < cvx_lo || ax0 + 1 > cvx_hi || ay0 < cvy_lo || ay0 + 1 > cvy_hi);
-                unsigned side_mask = 0;  // corners that need the 64-bit side path
+        for (int p = p_lo; p < p_hi; ++p) {
+            const float cxo = ox, cyo = oy, cm = ml;
+            ox = ox2; oy = oy2; ml = ml2;
+            if (p + 2 < kTaps) load_tap_inputs<T>(offp, mskp, p + 2, ox2, oy2, ml2);  // two taps ahead
+            const Axis axx = axis_x(q, ref0, p, cxo);
+            const Axis axy = axis_y(q, ref1, p, cyo);
+            if (!(axx.alive && axy.alive)) continue;  // a clipped corner pair coincides: contributes exactly 0
+            const int lx = axx.i0 - q.pw - box.bx0;   // corner (y0,x0) relative to the box
+            const int ly = axy.i0 - q.ph - box.by0;
+            const float mm = logits ? expf(cm - mx) * inv_sum : cm;
+            if (mm == 0.f) continue;
+            if (MODE == 0 &&
+                __builtin_expect((unsigned)lx < (unsigned)(box.bw - 1) && (unsigned)ly < (unsigned)(box.bh - 1), 1)) {
+                // all four corners a b c d = (y0,x0) (y1,x0) (y0,x1) (y1,x1) lie in the box
+                const int cell = ly * PITCH + lx;
+                red_shared_add<(WP + 1) * kSG * 4>(wsum_s + (uint32_t)(ly * WP + lx) * (kSG * 4u), weight_units(mm));
+                const int wqa = weight_fixed(axx.d1 * axy.d1 * mm), wqb = weight_fixed(axx.d1 * axy.d0 * mm);
+                const int wqc = weight_fixed(axx.d0 * axy.d1 * mm), wqd = weight_fixed(axx.d0 * axy.d0 * mm);
+                const uint32_t base = acc_s + (uint32_t)cell * (kSCell * 4u);  // rotation bits stay put: cell*128
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {  // a b c d = (y0,x0) (y1,x0) (y0,x1) (y1,x1)
-                    const bool in_tile = ((k >> 1) ? col1 : col0) && ((k & 1) ? row1 : row0);
-                    const float wf = ((k >> 1) ? axx.d0 : axx.d1) * ((k & 1) ? axy.d0 : axy.d1) * mm;
-                    if (wf == 0.f) continue;
-                    if (!in_tile) {
-                        if (far_possible) side_mask |= 1u << k;  // exact far test below
-                        continue;
-                    }
-                    const int cell = (ly + (k & 1)) * bg.pitch + lx + (k >> 1);
-                    const int cellg = cell * kSG + g_l;
-                    if (MODE == 2) {
-                        if (wsum[cellg] > kBudget) side_mask |= 1u << k;
-                        continue;
-                    }
-                    // a raw mask beyond the fixed-point range (|Wk| >= 3.9) makes the cell hot by itself
-                    const int wb = __float2int_ru(fabsf(wf) * 1024.f);
-                    atomicAdd(&wsum[cellg], wb < 3994 ? wb : kBudget + 1);
-                    if (MODE == 1) continue;
-                    if (!have_g) {
-                        load_fixed_point_go<T>(grad_out + pg * kGC, sg, px_l, G);
-                        have_g = true;
-                    }
-                    const int wq = __float2int_rn(fminf(fmaxf(wf, -3.9f), 3.9f) * (float)(1 << kWShift));
-                    const int bb = par ^ (k & 1) ^ (k >> 1);
-                    // slab base is 64-byte aligned: base + ((c ^ rot) * 4) == (base ^ rot*4) ^ c*4
-                    const uint32_t dx = (acc_s + (uint32_t)(cell * kSCell + g_l * kGC) * 4u) ^ ((uint32_t)px_l << 2);
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) red_shared_add(dx ^ (c << 2), __mulhi(G[c], wq) + bb);
+                for (int c = 0; c < 16; ++c) {
+                    const uint32_t a = base ^ (uint32_t)(c << 2);
+                    red_shared_add<0>(a, qmul(G[c], wqa));
+                    red_shared_add<ROWB>(a, qmul(G[c], wqb));
+                    red_shared_add<kSCell * 4>(a, qmul(G[c], wqc));
+                    red_shared_add<ROWB + kSCell * 4>(a, qmul(G[c], wqd));
                 }
-                if (__builtin_expect(side_mask != 0, 0)) {
+                continue;
+            }
+            // ---- corner by corner: part of the patch leaves the box (or one of the redo passes) ----
+            const bool touches = (unsigned)(lx + 1) <= (unsigned)box.bw && (unsigned)(ly + 1) <= (unsigned)box.bh;
+            if (MODE != 2 && touches)  // some corner lies in the box
+                red_shared_add<(WP + 1) * kSG * 4>(wsum_s + (uint32_t)(ly * WP + lx) * (kSG * 4u), weight_units(mm));
 #pragma unroll 1
-                    for (int k = 0; k < 4; ++k) {
-                        if (!((side_mask >> k) & 1)) continue;
-                        const int ax = lx + (k >> 1) + ux0, ay = ly + (k & 1) + uy0;  // un-padded image coords
-                        if (MODE == 0) {
-                            if (ax < 0 || ax >= q.w || ay < 0 || ay >= q.h) continue;  // zero ring: gradient dropped
-                            // the owner of that tile visits this pixel itself unless the tap is far
-                            if (ax >= cvx_lo && ax <= cvx_hi && ay >= cvy_lo && ay <= cvy_hi) continue;
+            for (int k = 0; k < (MODE == 1 || (MODE == 2 && !touches) ? 0 : 4); ++k) {
+                const float wf = ((k >> 1) ? axx.d0 : axx.d1) * ((k & 1) ? axy.d0 : axy.d1) * mm;
+                if (wf == 0.f) continue;
+                const int cx = lx + (k >> 1), cy = ly + (k & 1);
+                const int ax = cx + box.bx0, ay = cy + box.by0;  // un-padded image coordinates
+                const bool in_image = ax >= 0 && ax < q.w && ay >= 0 && ay < q.h;
+                const size_t cellg = ((size_t)n * img_pixels + (size_t)ay * q.w + ax) * q.G + g;
+                if ((unsigned)cx < (unsigned)box.bw && (unsigned)cy < (unsigned)box.bh) {
+                    if (MODE == 2) {
+                        if (in_image && cell_is_hot<WP>(wsum, cy, cx, g_l)) {
+                            if (!have_g) {
+                                load_fixed_point_go<T>(grad_out + pg * kGC, sg, px_l, G);
+                                have_g = true;
+                            }
+                            side_add(ws, cellg, G, px_l, wf);
                         }
-                        if (!have_g) {
-                            load_fixed_point_go<T>(grad_out + pg * kGC, sg, px_l, G);
-                            have_g = true;
-                        }
-                        const float wf = ((k >> 1) ? axx.d0 : axx.d1) * ((k & 1) ? axy.d0 : axy.d1) * mm;
-                        // same integer q as the shared-memory path; |Wk| >= 4 (raw masks only) is pre-shifted
-                        int sh = 0;
-                        if (!(fabsf(wf) < 3.9f))
-                            sh = min(max((int)((__float_as_uint(wf) >> 23) & 0xffu) - 128, 0), 30);
-                        const int wq = __float2int_rn(ldexpf(wf, kWShift - sh));
-                        const int bb = par ^ (k & 1) ^ (k >> 1);
-                        unsigned long long* dst =
-                            ws.acc64 + (((size_t)n * img_pixels + (size_t)ay * q.w + ax) * q.G + g) * kGC;
-#pragma unroll
-                        for (int c = 0; c < 16; ++c)  // G[c] holds channel c ^ px_l
-                            atomicAdd(dst + (c ^ px_l), (unsigned long long)(((long long)__mulhi(G[c], wq) << sh) + bb));
-                        ws.dirty[((size_t)n * img_pixels + (size_t)ay * q.w + ax) * q.G + g] = 1;
+                        continue;
                     }
+                    const int wq = weight_fixed(wf);
+                    const uint32_t base = acc_s + (uint32_t)(cy * PITCH + cx) * (kSCell * 4u);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) red_shared_add<0>(base ^ (uint32_t)(c << 2), qmul(G[c], wq));
+                } else if (MODE == 0 && in_image) {  // beyond the ring; outside the image the gradient is dropped
+                    side_add(ws, cellg, G, px_l, wf);
                 }
             }
         }
-        deal = (deal + (npix + PXW - 1) / PXW) % nwarps;
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(640, 1)
+template <typename T, int TJ>
+__global__ void __launch_bounds__(ScatterShape<TJ>::THREADS, ScatterShape<TJ>::MIN_CTAS)
 bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
                    T* __restrict__ grad_x, const FarWs ws, const KParams q, const BwdGeom bg) {
-    extern __shared__ __align__(16) int acc[];  // [acc_ints] accumulator + [wsum_ints] weight counters
-    __shared__ Range s_home_h, s_home_w, s_win_h, s_win_w;
-    __shared__ int s_next;
-    int* wsum = acc + bg.acc_ints;
+    constexpr int PITCH = ScatterShape<TJ>::PITCH;
+    constexpr int WP = ScatterShape<TJ>::WPITCH;
+    // [box_rows][PITCH][kSCell] accumulator + [box_rows + 1][WP][kSG] weight counters
+    extern __shared__ __align__(128) int acc[];
+    __shared__ Range s_home_h, s_home_w;
+    const int acc_ints = bg.box_rows * PITCH * kSCell;
+    int* wsum = acc + acc_ints;
 
     int b = blockIdx.x;
     const int jx = b % bg.tiles_x; b /= bg.tiles_x;
     const int jy = b % bg.tiles_y; b /= bg.tiles_y;
     const int chunk = b % bg.chunks;
     const int n = b / bg.chunks;
-    const int ux0 = jx << bg.tj_log2, uy0 = jy << bg.tj_log2;
-    const int tjw = min(bg.tj, q.w - ux0), tjh = min(bg.tj, q.h - uy0);
+    const TileBox box = make_box(q, bg, jx, jy);
 
-    if (threadIdx.x < 4) tile_ranges(q, bg, jx, jy, s_home_h, s_home_w, s_win_h, s_win_w);
-    if (threadIdx.x == 0) s_next = 0;
+    if (threadIdx.x < 2) tile_ranges(q, bg, jx, jy, s_home_h, s_home_w);
     const int eg = 30 - fixed_exponent_raw(ws.hd);
-    for (int i = threadIdx.x; i < bg.acc_ints + bg.wsum_ints; i += blockDim.x) acc[i] = 0;
+    {
+        int2* z = reinterpret_cast<int2*>(acc);  // both parts have an even number of ints
+        for (int i = threadIdx.x; i < (acc_ints + (bg.box_rows + 1) * WP * kSG) / 2; i += blockDim.x)
+            z[i] = make_int2(0, 0);
+    }
     __syncthreads();
-    scatter_pass<T, 0>(acc, wsum, offset, mask, grad_out, ws, q, bg, n, chunk, jx, jy, s_win_h, s_win_w, s_home_h,
-                       s_home_w, eg, &s_next);
+    scatter_walk<T, 0, TJ>(acc, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
     __syncthreads();
 
-    // ---- flush: J is written exactly once ----
+    // ---- flush: the cells of J are written exactly once; ring cells go to the side buffer ----
     const float inv_s = ldexpf(1.0f, -(eg + kWShift - 32));  // q = value * 2^(eg + kWShift - 32)
-    constexpr int CH = kSG * kGC;    // channels of this chunk per cell
-    constexpr int QPC = CH / 4;      // 4-channel pieces per cell
-    const int ncell = tjw * tjh;
+    constexpr int QPC = kSCell / 4;  // 4-channel pieces per cell
+    const size_t img_pixels = (size_t)q.h * q.w;
     bool any_hot = false;
-    for (int i = threadIdx.x; i < ncell * QPC; i += blockDim.x) {
-        const int cl = i / QPC, piece = i % QPC;
-        const int cy = cl / tjw, cx = cl % tjw;
-        const int cell = cy * bg.pitch + cx;
+    for (int i = threadIdx.x; i < box.bh * (PITCH * QPC); i += blockDim.x) {
+        const int cy = i / (PITCH * QPC), r = i - cy * (PITCH * QPC);
+        const int cx = r / QPC, piece = r % QPC;
+        const int ax = box.bx0 + cx, ay = box.by0 + cy;
+        // beyond the box row; zero ring: gradient dropped (Pad-grad)
+        if (cx >= box.bw || ax < 0 || ax >= q.w || ay < 0 || ay >= q.h) continue;
         const int gl = (piece * 4) / kGC;
-        if (chunk * kSG + gl >= q.G) continue;  // phantom group
-        // a hot (cell, group) may have wrapped: it is zeroed here and recomputed by redo_hot_kernel
-        const bool hot = wsum[cell * kSG + gl] > kBudget;
+        const int g = chunk * kSG + gl;
+        if (g >= q.G) continue;  // phantom group
+        // a hot (cell, group) may have wrapped: it is skipped here and recomputed by redo_hot_kernel
+        const bool hot = cell_is_hot<WP>(wsum, cy, cx, gl);
         any_hot |= hot;
-        const int* src = acc + cell * kSCell + piece * 4;
-        const size_t gpix = (size_t)n * q.h * q.w + (size_t)(uy0 + cy) * q.w + (ux0 + cx);
-        const size_t gidx = gpix * ((size_t)q.G * kGC) + (size_t)chunk * CH + piece * 4;
-        float v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = hot ? 0.f : (float)src[j] * inv_s;
-        if (sizeof(T) == 4) {
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(grad_x) + gidx) = make_float4(v[0], v[1], v[2], v[3]);
-        } else {
-            uint2 r;
-            r.x = pack_bf16x2(v[0], v[1]);
-            r.y = pack_bf16x2(v[2], v[3]);
-            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(grad_x) + gidx) = r;
+        const int4 v = *reinterpret_cast<const int4*>(acc + (cy * PITCH + cx) * kSCell + piece * 4);
+        const size_t gpix = (size_t)n * img_pixels + (size_t)(ay * q.w + ax);
+        if ((unsigned)(ax - box.ux0) < (unsigned)box.tjw && (unsigned)(ay - box.uy0) < (unsigned)box.tjh) {
+            const size_t gidx = gpix * ((size_t)q.G * kGC) + (size_t)(chunk * kSCell + piece * 4);
+            const float f0 = hot ? 0.f : (float)v.x * inv_s, f1 = hot ? 0.f : (float)v.y * inv_s;
+            const float f2_ = hot ? 0.f : (float)v.z * inv_s, f3 = hot ? 0.f : (float)v.w * inv_s;
+            if (sizeof(T) == 4) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(grad_x) + gidx) = make_float4(f0, f1, f2_, f3);
+            } else {
+                uint2 r2;
+                r2.x = pack_bf16x2(f0, f1);
+                r2.y = pack_bf16x2(f2_, f3);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(grad_x) + gidx) = r2;
+            }
+        } else if (!hot && (v.x | v.y | v.z | v.w) != 0) {
+            const size_t cellg = gpix * q.G + g;
+            unsigned long long* dst = ws.acc64 + cellg * kGC + (piece * 4) % kGC;
+            if (v.x) atomicAdd(dst + 0, (unsigned long long)(long long)v.x);
+            if (v.y) atomicAdd(dst + 1, (unsigned long long)(long long)v.y);
+            if (v.z) atomicAdd(dst + 2, (unsigned long long)(long long)v.z);
+            if (v.w) atomicAdd(dst + 3, (unsigned long long)(long long)v.w);
+            ws.dirty[cellg] = 1;
         }
     }
     if (any_hot) ws.redo[blockIdx.x] = 1;
 }
 
-// Exact recomputation of the hot cells of one tile (see header): pass 1 rebuilds the weight counters,
+// Exact recomputation of the hot cells of one box (see header): pass 1 rebuilds the weight counters,
 // pass 2 adds the landings on hot cells to the 64-bit side buffer.  Exits at once unless the scatter
 // kernel flagged the CTA -- which only adversarial inputs make it do.
-template <typename T>
+template <typename T, int TJ>
 __global__ void __launch_bounds__(256)
 redo_hot_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
                 const FarWs ws, const KParams q, const BwdGeom bg) {
     if (ws.redo[blockIdx.x] == 0) return;
-    extern __shared__ __align__(16) int wsum[];  // [wsum_ints]
-    __shared__ Range s_home_h, s_home_w, s_win_h, s_win_w;
-    __shared__ int s_next;
+    constexpr int WP = ScatterShape<TJ>::WPITCH;
+    extern __shared__ __align__(16) int wsum[];  // [box_rows + 1][WP][kSG]
+    __shared__ Range s_home_h, s_home_w;
     int b = blockIdx.x;
     const int jx = b % bg.tiles_x; b /= bg.tiles_x;
     const int jy = b % bg.tiles_y; b /= bg.tiles_y;
     const int chunk = b % bg.chunks;
     const int n = b / bg.chunks;
-    if (threadIdx.x < 4) tile_ranges(q, bg, jx, jy, s_home_h, s_home_w, s_win_h, s_win_w);
-    if (threadIdx.x == 0) s_next = 0;
-    for (int i = threadIdx.x; i < bg.wsum_ints; i += blockDim.x) wsum[i] = 0;
+    const TileBox box = make_box(q, bg, jx, jy);
+    if (threadIdx.x < 2) tile_ranges(q, bg, jx, jy, s_home_h, s_home_w);
+    for (int i = threadIdx.x; i < (bg.box_rows + 1) * WP * kSG; i += blockDim.x) wsum[i] = 0;
     __syncthreads();
     const int eg = 30 - fixed_exponent_raw(ws.hd);
-    scatter_pass<T, 1>(nullptr, wsum, offset, mask, grad_out, ws, q, bg, n, chunk, jx, jy, s_win_h, s_win_w, s_home_h,
-                       s_home_w, eg, &s_next);
+    scatter_walk<T, 1, TJ>(nullptr, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
     __syncthreads();
-    if (threadIdx.x == 0) s_next = 0;
-    __syncthreads();
-    scatter_pass<T, 2>(nullptr, wsum, offset, mask, grad_out, ws, q, bg, n, chunk, jx, jy, s_win_h, s_win_w, s_home_h,
-                       s_home_w, eg, &s_next);
+    scatter_walk<T, 2, TJ>(nullptr, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
     __syncthreads();
     if (threadIdx.x == 0) ws.redo[blockIdx.x] = 0;
 }
 
 // grad_x += side buffer for the (pixel, group)s flagged in the dirty map; leaves the side buffer and
-// the map zeroed for the next call.  Each warp scans 128 map bytes; flagged entries are then handled by
-// half-warps, one lane per channel (the 16 channels of a group are contiguous in both buffers).
+// the map zeroed for the next call.  A warp scans 32 map bytes; the flagged entries are then taken eight
+// at a time, four lanes per entry and four channels per lane (coalesced 128-byte runs of the side buffer).
 template <typename T>
 __global__ void __launch_bounds__(256)
 merge_far_kernel(T* __restrict__ grad_x, const FarWs ws, const KParams q, size_t count) {
     const int lane = threadIdx.x & 31;
-    const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    unsigned flags = 0;
-    if (i4 < count) flags = *reinterpret_cast<const unsigned*>(ws.dirty + i4);  // map is padded to 256 bytes
-    unsigned any = __ballot_sync(0xffffffffu, flags != 0);
-    if (any == 0) return;
+    const size_t base = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) - lane;
+    const size_t e = base + lane;
+    const unsigned char flag = e < count ? ws.dirty[e] : (unsigned char)0;  // map is padded to 256 bytes
+    const unsigned m = __ballot_sync(0xffffffffu, flag != 0);
+    if (m == 0) return;
     const double inv_s = ldexp(1.0, -(30 - fixed_exponent_raw(ws.hd) + kWShift - 32));
-    const size_t warp_base = i4 - (size_t)lane * 4;
-    while (any) {
-        const int src = __ffs(any) - 1;
-        any &= any - 1;
-        const unsigned f = __shfl_sync(0xffffffffu, flags, src);
-        // the up to four flagged entries of lane `src`: two per pass, one half-warp each
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            const int j = pass * 2 + (lane >> 4);
-            const size_t e = warp_base + (size_t)src * 4 + j;
-            if (((f >> (8 * j)) & 0xffu) != 0 && e < count) {
-                const size_t idx = e * kGC + (lane & 15);
-                const long long v = (long long)ws.acc64[idx];
-                if (v != 0) {
-                    // |v| can exceed 2^24: go through double so that the exact total is rounded once
-                    Elem<T>::st(grad_x + idx, Elem<T>::ld_plain(grad_x + idx) + (float)((double)v * inv_s));
-                    ws.acc64[idx] = 0ull;
-                }
-            }
+    const int nset = __popc(m);
+    for (int k0 = 0; k0 < nset; k0 += 8) {
+        const int k = k0 + (lane >> 2);
+        if (k < nset) {
+            const size_t idx = (base + __fns(m, 0, k + 1)) * kGC + (lane & 3) * 4;
+            longlong4 v;
+            const longlong2 v01 = *reinterpret_cast<const longlong2*>(ws.acc64 + idx);
+            const longlong2 v23 = *reinterpret_cast<const longlong2*>(ws.acc64 + idx + 2);
+            v.x = v01.x; v.y = v01.y; v.z = v23.x; v.w = v23.y;
+            // |v| can exceed 2^24: go through double so that the exact total is rounded once
+            const float a0 = (float)((double)v.x * inv_s), a1 = (float)((double)v.y * inv_s);
+            const float a2 = (float)((double)v.z * inv_s), a3 = (float)((double)v.w * inv_s);
+            float4 gx = Elem<T>::ld4_plain(grad_x + idx);
+            gx.x += a0; gx.y += a1; gx.z += a2; gx.w += a3;
+            Elem<T>::st4(grad_x + idx, gx);
+            *reinterpret_cast<ulonglong2*>(ws.acc64 + idx) = make_ulonglong2(0ull, 0ull);
+            *reinterpret_cast<ulonglong2*>(ws.acc64 + idx + 2) = make_ulonglong2(0ull, 0ull);
         }
     }
-    if (flags != 0) *reinterpret_cast<unsigned*>(ws.dirty + i4) = 0u;
+    if (flag != 0) ws.dirty[e] = 0;
 }
 
 // ---- host side -----------------------------------------------------------------------------------
 static BwdGeom make_bwd_geom(const KParams& q) {
     BwdGeom bg;
-    // 32x32 tiles keep the margin overhead low; small images use 16x16 so that the grid still fills the GPU
-    bg.tj = (q.w >= 32 && q.h >= 32) ? 32 : 16;
+    // 32x32 tiles keep the ring small; images that fit a 16x16 tile use that (smaller box, more CTAs per SM)
+    bg.tj = (q.w > 16 || q.h > 16) ? 32 : 16;
     bg.tj_log2 = bg.tj == 32 ? 5 : 4;
-    bg.pitch = bg.tj;
     bg.tiles_x = (q.w + bg.tj - 1) / bg.tj;
     bg.tiles_y = (q.h + bg.tj - 1) / bg.tj;
     bg.chunks = (q.G + kSG - 1) / kSG;
-    // source pixels are searched up to ~3 offset units (+1 for the tap grid) beyond the tile
+    // A tap lands within [nominal - ceil(D), nominal + floor(D) + 2] of its pixel's nominal cell, D = (1 +
+    // |offset|) * scale * (dim-2)/dim.  The ring serves |offset| <= reach (reference units) from shared
+    // memory; reach starts at 3 and shrinks until the box fits the compile-time pitch.
     const float r = fmaxf(q.wm2_f / q.win_f, q.hm2_f / q.hin_f) * q.scale;
-    bg.margin = min((int)ceilf((1.0f + 3.0f) * r), 12);
-    bg.acc_ints = bg.tj * bg.pitch * kSCell;
-    bg.wsum_ints = bg.tj * bg.pitch * kSG;
+    for (float reach = 3.0f;; reach *= 0.75f) {
+        const float d = (1.0f + reach) * r;
+        bg.ring_lo = max((int)ceilf(d), 1);
+        bg.ring_hi = (int)floorf(d) + 2;
+        if ((bg.ring_lo <= kRingLo && bg.ring_hi <= kRingHi) || reach < 1e-3f) break;
+    }
+    bg.ring_lo = min(bg.ring_lo, kRingLo);
+    bg.ring_hi = min(bg.ring_hi, kRingHi);
+    bg.box_rows = 0;
+    for (int jy = 0; jy < bg.tiles_y; ++jy) {
+        const int uy0 = jy * bg.tj, tjh = min(bg.tj, q.h - uy0);
+        const int by0 = max(uy0 - bg.ring_lo, -1);
+        bg.box_rows = max(bg.box_rows, min(uy0 + tjh + bg.ring_hi, q.h + 1) - by0);
+    }
     return bg;
 }
 
@@ -634,6 +686,35 @@ size_t bwd_tiled_workspace_bytes(const KParams& q) {
     const size_t chunks = (size_t)(q.G + 1) / 2;
     return sizeof(WsHeader) + dirty_bytes(q) + flag_bytes(tiles * chunks) +
            sizeof(long long) * (size_t)q.n * q.h * q.w * q.G * q.gc;
+}
+
+// accumulator [rows][PITCH][kSCell] + weight counters [rows + 1][WPITCH][kSG]
+template <int TJ>
+static size_t scatter_smem_bytes(int rows) {
+    using S = ScatterShape<TJ>;
+    return ((size_t)rows * S::PITCH * kSCell + (size_t)(rows + 1) * S::WPITCH * kSG) * sizeof(int);
+}
+
+template <typename T, int TJ>
+static cudaError_t launch_scatter(const T* offset, const T* mask, const T* grad_out, T* grad_x, const FarWs& ws,
+                                  const KParams& q, const BwdGeom& bg, unsigned grid, cudaStream_t st) {
+    using S = ScatterShape<TJ>;
+    const size_t smem = scatter_smem_bytes<TJ>(bg.box_rows);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(bwd_scatter_kernel<T, TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)scatter_smem_bytes<TJ>(S::PITCH));
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63] = true;
+    }
+    KernelTiming& kt = kernel_timing();
+    bwd_scatter_kernel<T, TJ><<<grid, S::THREADS, smem, st>>>(offset, mask, grad_out, grad_x, ws, q, bg);
+    if (kt.enabled) cudaEventRecord(kt.ev[2], st);
+    redo_hot_kernel<T, TJ><<<grid, 256, (size_t)(bg.box_rows + 1) * S::WPITCH * kSG * sizeof(int), st>>>(
+        offset, mask, grad_out, ws, q, bg);
+    return cudaSuccess;
 }
 
 template <typename T>
@@ -660,17 +741,12 @@ static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const v
     if (tg.bw * tg.bh > max_cells) return cudaErrorInvalidConfiguration;
     CUtensorMap map;
     if (!make_x_tensor_map(&map, x, q, dtype, tg.bw, tg.bh)) return cudaErrorNotSupported;
-    const size_t smem_b = (size_t)(bg.acc_ints + bg.wsum_ints) * sizeof(int);
-    const int threads_b = bg.tj == 32 ? 640 : 256;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
         e = cudaFuncSetAttribute(bwd_gather_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kMaxBoxBytes + 8 * kGatherStageBytes<T>);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(bwd_scatter_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (32 * 32 * (kSCell + kSG)) * (int)sizeof(int));
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }
@@ -685,14 +761,14 @@ static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const v
     // ---- grad_x ----
     if (kt.enabled) cudaEventRecord(kt.ev[1], st);
     const unsigned grid_b = (unsigned)(tiles * bg.chunks);
-    bwd_scatter_kernel<T><<<grid_b, threads_b, smem_b, st>>>((const T*)offset, (const T*)mask, (const T*)grad_out,
-                                                             (T*)grad_x, ws, q, bg);
-    if (kt.enabled) cudaEventRecord(kt.ev[2], st);
-    redo_hot_kernel<T><<<grid_b, 256, bg.wsum_ints * sizeof(int), st>>>((const T*)offset, (const T*)mask,
-                                                                        (const T*)grad_out, ws, q, bg);
+    e = bg.tj == 32 ? launch_scatter<T, 32>((const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_x, ws, q, bg,
+                                            grid_b, st)
+                    : launch_scatter<T, 16>((const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_x, ws, q, bg,
+                                            grid_b, st);
+    if (e != cudaSuccess) return e;
     if (kt.enabled) cudaEventRecord(kt.ev[3], st);
     const size_t npg = (size_t)q.n * q.h * q.w * q.G;
-    merge_far_kernel<T><<<(unsigned)((npg / 4 + 256) / 256), 256, 0, st>>>((T*)grad_x, ws, q, npg);
+    merge_far_kernel<T><<<(unsigned)((npg + 255) / 256), 256, 0, st>>>((T*)grad_x, ws, q, npg);
     if (kt.enabled) cudaEventRecord(kt.ev[4], st);
     count_launch(4);
     return cudaGetLastError();

@@ -157,17 +157,19 @@ def test_backward_bitwise_reproducible(ops):
     # channel).  An fp32 running sum of that length carries ~sqrt(n)*eps error itself, so the yardstick
     # here is the oracle with fp32 per-tap arithmetic (as the reference) but a float64 scatter sum.
     x, off, m, go = x[:1], off[:1], m[:1], go[:1]
-    off2 = np.zeros_like(off)
-    off2[..., 0::2] = (30.0 - np.arange(64, dtype=np.float32)).reshape(1, 64, 1, 1) * 66 / 64
-    off2[..., 1::2] = (30.0 - np.arange(64, dtype=np.float32)).reshape(1, 1, 64, 1) * 66 / 64
-    a = run_op(ops, x, off2, m, go, **kw)
-    b = run_op(ops, x, off2, m, go, **kw)
-    assert all(np.array_equal(p, q) for p, q in zip(a, b))
-    rx, roff, rm = c_oracle.backward(x, off2, m, go, **kw)
-    assert rel_err(a[2], roff) <= TOL_F32 and rel_err(a[3], rm) <= TOL_F32
-    dx, _, _ = O.backward(x, off2, m, go, accumulate=np.float64, **kw)
-    assert rel_err(a[1], dx) <= 1e-6            # fixed-point accumulation: exact up to the final rounding
-    assert rel_err(rx, dx) <= 1e-4              # (the fp32 running sum of the C oracle is the loose one)
+    # target cell inside a 32x32 scatter tile, in the ring just across a tile border, and at the image corner
+    for target in (30.0, 33.0, 1.0):
+        off2 = np.zeros_like(off)
+        off2[..., 0::2] = (target - np.arange(64, dtype=np.float32)).reshape(1, 64, 1, 1) * 66 / 64
+        off2[..., 1::2] = (target - np.arange(64, dtype=np.float32)).reshape(1, 1, 64, 1) * 66 / 64
+        a = run_op(ops, x, off2, m, go, **kw)
+        b = run_op(ops, x, off2, m, go, **kw)
+        assert all(np.array_equal(p, q) for p, q in zip(a, b))
+        rx, roff, rm = c_oracle.backward(x, off2, m, go, **kw)
+        assert rel_err(a[2], roff) <= TOL_F32 and rel_err(a[3], rm) <= TOL_F32
+        dx, _, _ = O.backward(x, off2, m, go, accumulate=np.float64, **kw)
+        assert rel_err(a[1], dx) <= 1e-6        # fixed-point accumulation: exact up to the final rounding
+        assert rel_err(rx, dx) <= 1e-4          # (the fp32 running sum of the C oracle is the loose one)
 
 
 def test_fused_softmax_matches_layer_semantics(ops):
