@@ -591,7 +591,7 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
 template <typename T, int TJ>
 __global__ void __launch_bounds__(256)
 redo_hot_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
-                const FarWs ws, const KParams q, const BwdGeom bg) {
+                T* __restrict__ grad_x, const FarWs ws, const KParams q, const BwdGeom bg) {
     if (ws.redo[blockIdx.x] == 0) return;
     constexpr int WP = ScatterShape<TJ>::WPITCH;
     extern __shared__ __align__(16) int wsum[];  // [box_rows + 1][WP][kSG]
@@ -611,6 +611,28 @@ redo_hot_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const 
     scatter_walk<T, 2, TJ>(nullptr, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
     __syncthreads();
     if (threadIdx.x == 0) ws.redo[blockIdx.x] = 0;
+    if (bg.tiles_x * bg.tiles_y != 1) return;  // merge_far_kernel folds the side buffer into grad_x
+    // The tile is the whole image: nobody else contributes to its cells (no ring, no far landings), so
+    // there is no merge launch and this CTA converts its hot cells itself.
+    __threadfence();
+    __syncthreads();
+    constexpr int PITCH = ScatterShape<TJ>::PITCH;
+    const size_t img_pixels = (size_t)q.h * q.w;
+    const double inv_d = ldexp(1.0, -(eg + kWShift - 32));
+    for (int i = threadIdx.x; i < box.bh * (PITCH * kSCell); i += blockDim.x) {
+        const int cy = i / (PITCH * kSCell), r = i - cy * (PITCH * kSCell);
+        const int cx = r / kSCell, ch = r % kSCell, gl = ch / kGC;
+        const int ax = box.bx0 + cx, ay = box.by0 + cy, g = chunk * kSG + gl;
+        if (cx >= box.bw || ax < 0 || ax >= q.w || ay < 0 || ay >= q.h || g >= q.G) continue;
+        if (!cell_is_hot<WP>(wsum, cy, cx, gl)) continue;
+        const size_t cellg = ((size_t)n * img_pixels + (size_t)(ay * q.w + ax)) * q.G + g;
+        const size_t idx = cellg * kGC + ch % kGC;
+        const long long v = (long long)__ldcg(ws.acc64 + idx);
+        // |v| can exceed 2^24: go through double so that the exact total is rounded once
+        Elem<T>::st(grad_x + idx, (float)((double)v * inv_d));
+        ws.acc64[idx] = 0ull;
+        ws.dirty[cellg] = 0;
+    }
 }
 
 // grad_x += side buffer for the (pixel, group)s flagged in the dirty map; leaves the side buffer and
@@ -713,7 +735,7 @@ static cudaError_t launch_scatter(const T* offset, const T* mask, const T* grad_
     bwd_scatter_kernel<T, TJ><<<grid, S::THREADS, smem, st>>>(offset, mask, grad_out, grad_x, ws, q, bg);
     if (kt.enabled) cudaEventRecord(kt.ev[2], st);
     redo_hot_kernel<T, TJ><<<grid, 256, (size_t)(bg.box_rows + 1) * S::WPITCH * kSG * sizeof(int), st>>>(
-        offset, mask, grad_out, ws, q, bg);
+        offset, mask, grad_out, grad_x, ws, q, bg);
     return cudaSuccess;
 }
 
@@ -767,10 +789,14 @@ static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const v
                                             grid_b, st);
     if (e != cudaSuccess) return e;
     if (kt.enabled) cudaEventRecord(kt.ev[3], st);
-    const size_t npg = (size_t)q.n * q.h * q.w * q.G;
-    merge_far_kernel<T><<<(unsigned)((npg + 255) / 256), 256, 0, st>>>((T*)grad_x, ws, q, npg);
+    // a single tile owns every cell of its image: no ring, no far landings, nothing to merge
+    const bool merge = bg.tiles_x * bg.tiles_y > 1;
+    if (merge) {
+        const size_t npg = (size_t)q.n * q.h * q.w * q.G;
+        merge_far_kernel<T><<<(unsigned)((npg + 255) / 256), 256, 0, st>>>((T*)grad_x, ws, q, npg);
+    }
     if (kt.enabled) cudaEventRecord(kt.ev[4], st);
-    count_launch(4);
+    count_launch(merge ? 4 : 3);
     return cudaGetLastError();
 }
 

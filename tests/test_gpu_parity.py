@@ -170,6 +170,20 @@ def test_backward_bitwise_reproducible(ops):
         dx, _, _ = O.backward(x, off2, m, go, accumulate=np.float64, **kw)
         assert rel_err(a[1], dx) <= 1e-6        # fixed-point accumulation: exact up to the final rounding
         assert rel_err(rx, dx) <= 1e-4          # (the fp32 running sum of the C oracle is the loose one)
+    # the same on an image that is a single scatter tile (hot cells are converted by the scatter CTA itself)
+    x, off, m, go = make_inputs(2, 32, 32, 3, 16, sigma=1.0, seed=5)
+    kw = dict(groups=3, group_channels=16)
+    off2 = np.zeros_like(off)
+    off2[..., 0::2] = (12.0 - np.arange(32, dtype=np.float32)).reshape(1, 32, 1, 1) * 34 / 32
+    off2[..., 1::2] = (20.0 - np.arange(32, dtype=np.float32)).reshape(1, 1, 32, 1) * 34 / 32
+    a = run_op(ops, x, off2, m, go, **kw)
+    b = run_op(ops, x, off2, m, go, **kw)
+    assert all(np.array_equal(p, q) for p, q in zip(a, b))
+    dx, _, _ = O.backward(x, off2, m, go, accumulate=np.float64, **kw)
+    assert rel_err(a[1], dx) <= 1e-6
+    c = run_op(ops, x, off, m, go, **kw)   # the workspace is left clean: an ordinary call right after
+    rx, _, _ = c_oracle.backward(x, off, m, go, **kw)
+    assert rel_err(c[1], rx) <= TOL_F32
 
 
 def test_fused_softmax_matches_layer_semantics(ops):
