@@ -205,30 +205,48 @@ static int dl_params(const DLManagedTensor* x, const DLManagedTensor* offset, in
 }
 
 // ---- host-buffer scratch -------------------------------------------------------------------------
-// kHostSlots independent slots per device, each with its own stream, data scratch and a backward
-// workspace that is zeroed when (re)allocated and kept zeroed by dcnv3_backward itself.
+// Per device: one copy-in stream and one copy-out stream, so that each PCIe direction carries one copy at a
+// time at full rate; kHostSlots slots, each with its own compute stream, data scratch and a backward
+// workspace that is zeroed when (re)allocated and kept zeroed by dcnv3_backward itself.  Events chain
+// copy-in -> kernels -> copy-out per slot; nothing blocks the host until dcnv3_host_sync.
 constexpr int kHostSlots = 4;
 struct HostScratch {
     void* buf = nullptr;
     size_t bytes = 0;
     void* ws = nullptr;
     size_t ws_bytes = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;                  // kernels of this slot
+    cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;  // inputs resident / kernels done / outputs copied
+};
+struct DevicePipes {
+    cudaStream_t in = nullptr, out = nullptr;
 };
 static std::mutex g_scratch_mu;
 static HostScratch g_scratch[64][kHostSlots];
+static DevicePipes g_pipes[64];
 
 static int scratch_reserve(int device, int slot, size_t bytes, size_t ws_bytes, HostScratch** out) {
     if (device < 0 || device >= 64) return fail(DCNV3_ERR_DEVICE, "device %d out of range", device);
     if (slot < 0 || slot >= kHostSlots) return fail(DCNV3_ERR_ARGUMENT, "slot %d out of range [0,%d)", slot, kHostSlots);
     HostScratch& s = g_scratch[device][slot];
+    DevicePipes& dp = g_pipes[device];
     cudaError_t e;
+    if (dp.in == nullptr) {
+        if ((e = cudaStreamCreateWithFlags(&dp.in, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&dp.out, cudaStreamNonBlocking)) != cudaSuccess)
+            return cuda_fail(e, "cudaStreamCreate");
+    }
     if (s.stream == nullptr) {
         if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess)
             return cuda_fail(e, "cudaStreamCreate");
+        if ((e = cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming)) != cudaSuccess)
+            return cuda_fail(e, "cudaEventCreate");
     }
     if (s.bytes < bytes || s.ws_bytes < ws_bytes) {
-        // the slot may still be running an earlier asynchronous call
+        // the slot may still be running an earlier asynchronous call (its copy-out comes last)
+        if ((e = cudaEventSynchronize(s.ev_out)) != cudaSuccess) return cuda_fail(e, "event synchronize");
         if ((e = cudaStreamSynchronize(s.stream)) != cudaSuccess) return cuda_fail(e, "stream synchronize");
     }
     if (s.bytes < bytes) {
@@ -385,32 +403,45 @@ static int host_run(const void* x, const void* offset, const void* mask, const v
     char* d_off = base; base += b_off;
     char* d_m = base; base += b_m;
     char* d_out = base; base += b_o;
-    cudaStream_t st = s->stream;
-#define H2D(dst, src, bytes) if ((e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D copy")
-#define D2H(dst, src, bytes) if ((e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H copy")
+    cudaStream_t st = s->stream, sin = g_pipes[device].in, sout = g_pipes[device].out;
+#define CK(call, what) if ((e = (call)) != cudaSuccess) return cuda_fail(e, what)
+#define H2D(dst, src, bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, sin), "H2D copy")
+#define D2H(dst, src, bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, sout), "D2H copy")
     const size_t n_x = (size_t)p->n * p->h * p->w * C * es, n_o = (size_t)p->n * p->ho * p->wo * C * es;
     const size_t n_off = (size_t)p->n * p->ho * p->wo * GP * 2 * es, n_m = n_off / 2;
+    char* d_go = base; base += with_backward ? b_o : 0;
+    char* d_gx = base; base += with_backward ? b_x : 0;
+    char* d_goff = base; base += with_backward ? b_off : 0;
+    char* d_gm = base;
+    // copy-in: after the slot's previous outputs have left the scratch (never-recorded event = no wait)
+    CK(cudaStreamWaitEvent(sin, s->ev_out, 0), "cudaStreamWaitEvent");
     H2D(d_x, x, n_x);
     H2D(d_off, offset, n_off);
     H2D(d_m, mask, n_m);
+    if (with_backward) H2D(d_go, grad_out, n_o);
+    CK(cudaEventRecord(s->ev_in, sin), "cudaEventRecord");
+    // kernels
+    CK(cudaStreamWaitEvent(st, s->ev_in, 0), "cudaStreamWaitEvent");
     if ((rc = forward_impl(d_x, d_off, d_m, d_out, p, st))) return rc;
-    D2H(out, d_out, n_o);
     if (with_backward) {
-        char* d_go = base; base += b_o;
-        char* d_gx = base; base += b_x;
-        char* d_goff = base; base += b_off;
-        char* d_gm = base; base += b_m;
-        H2D(d_go, grad_out, n_o);
         dcnv3_params pb = *p;
         pb.flags |= DCNV3_FLAG_WORKSPACE_ZEROED;  // the slot's workspace is zeroed at allocation and stays so
         if ((rc = backward_impl(d_x, d_off, d_m, d_go, d_gx, d_goff, d_gm, s->ws, s->ws_bytes, &pb, st))) return rc;
+    }
+    CK(cudaEventRecord(s->ev_comp, st), "cudaEventRecord");
+    // copy-out
+    CK(cudaStreamWaitEvent(sout, s->ev_comp, 0), "cudaStreamWaitEvent");
+    D2H(out, d_out, n_o);
+    if (with_backward) {
         D2H(grad_x, d_gx, n_x);
         D2H(grad_offset, d_goff, n_off);
         D2H(grad_mask, d_gm, n_m);
     }
+    CK(cudaEventRecord(s->ev_out, sout), "cudaEventRecord");
 #undef H2D
 #undef D2H
-    if (wait && (e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "stream synchronize");
+    if (wait) CK(cudaStreamSynchronize(sout), "stream synchronize");
+#undef CK
     return DCNV3_OK;
 }
 
@@ -428,14 +459,8 @@ int dcnv3_forward_backward_host(const void* x, const void* offset, const void* m
 int dcnv3_forward_backward_host_async(const void* x, const void* offset, const void* mask,
                                       const void* grad_out, void* out, void* grad_x, void* grad_offset,
                                       void* grad_mask, const dcnv3_params* p, int device, int slot) {
-    {   // the slot's scratch is about to be overwritten: its previous call must have drained
-        std::lock_guard<std::mutex> lock(g_scratch_mu);
-        if (device >= 0 && device < 64 && slot >= 0 && slot < kHostSlots && g_scratch[device][slot].stream) {
-            cudaSetDevice(device);
-            cudaError_t e = cudaStreamSynchronize(g_scratch[device][slot].stream);
-            if (e != cudaSuccess) return cuda_fail(e, "stream synchronize");
-        }
-    }
+    // (the slot's scratch is reused once its previous outputs have been copied out: the copy-in stream
+    //  waits for that on the device, the host does not block)
     return host_run(x, offset, mask, grad_out, out, grad_x, grad_offset, grad_mask, p, device, true, slot, false);
 }
 
@@ -444,9 +469,13 @@ int dcnv3_host_sync(int device) {
     std::lock_guard<std::mutex> lock(g_scratch_mu);
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    if (g_pipes[device].in && (e = cudaStreamSynchronize(g_pipes[device].in)) != cudaSuccess)
+        return cuda_fail(e, "stream synchronize");
     for (int k = 0; k < kHostSlots; ++k)
         if (g_scratch[device][k].stream && (e = cudaStreamSynchronize(g_scratch[device][k].stream)) != cudaSuccess)
             return cuda_fail(e, "stream synchronize");
+    if (g_pipes[device].out && (e = cudaStreamSynchronize(g_pipes[device].out)) != cudaSuccess)
+        return cuda_fail(e, "stream synchronize");
     return DCNV3_OK;
 }
 
@@ -454,18 +483,33 @@ int dcnv3_host_slots(void) { return kHostSlots; }
 
 int dcnv3_release_host_scratch(void) {
     std::lock_guard<std::mutex> lock(g_scratch_mu);
-    for (int d = 0; d < 64; ++d)
+    for (int d = 0; d < 64; ++d) {
+        DevicePipes& dp = g_pipes[d];
+        if (dp.in) {
+            cudaSetDevice(d);
+            cudaStreamSynchronize(dp.in);
+        }
         for (int k = 0; k < kHostSlots; ++k) {
             HostScratch& s = g_scratch[d][k];
             if (s.buf || s.ws || s.stream) {
                 cudaSetDevice(d);
                 if (s.stream) cudaStreamSynchronize(s.stream);
+                if (dp.out) cudaStreamSynchronize(dp.out);
                 if (s.buf) cudaFree(s.buf);
                 if (s.ws) cudaFree(s.ws);
                 if (s.stream) cudaStreamDestroy(s.stream);
+                if (s.ev_in) cudaEventDestroy(s.ev_in);
+                if (s.ev_comp) cudaEventDestroy(s.ev_comp);
+                if (s.ev_out) cudaEventDestroy(s.ev_out);
                 s = HostScratch();
             }
         }
+        if (dp.in) {
+            cudaStreamDestroy(dp.in);
+            cudaStreamDestroy(dp.out);
+            dp = DevicePipes();
+        }
+    }
     return DCNV3_OK;
 }
 
