@@ -85,6 +85,23 @@ __device__ __forceinline__ Axis make_axis(float coord, float max_f /* dim-1 */) 
     a.d1 = a.alive ? __fsub_rn(c1, coord) : 0.0f;
     return a;
 }
+// The same for callers that skip dead taps altogether: for a live axis the clips are identities
+// (0 <= f and f + 1 <= dim-1), so the deltas are formed from f directly -- bit-identical to make_axis.
+__device__ __forceinline__ Axis make_axis_live(float coord, float max_f /* dim-1 */) {
+    Axis a;
+    const float f = floorf(coord);
+    a.alive = (f >= 0.0f) && (f < max_f);
+    a.i0 = (int)f;
+    a.d0 = __fsub_rn(coord, f);
+    a.d1 = __fsub_rn(f + 1.0f, coord);
+    return a;
+}
+__device__ __forceinline__ Axis axis_x_live(const KParams& q, float ref0, int p, float offx) {
+    return make_axis_live(pixel_coord(ref0, q.gs0[p], offx, q.scale, q.win_f, q.rwin_f, q.wm2_f), q.wm2_f + 1.0f);
+}
+__device__ __forceinline__ Axis axis_y_live(const KParams& q, float ref1, int p, float offy) {
+    return make_axis_live(pixel_coord(ref1, q.gs1[p], offy, q.scale, q.hin_f, q.rhin_f, q.hm2_f), q.hm2_f + 1.0f);
+}
 __device__ __forceinline__ Axis axis_x(const KParams& q, float ref0, int p, float offx) {
     return make_axis(pixel_coord(ref0, q.gs0[p], offx, q.scale, q.win_f, q.rwin_f, q.wm2_f), q.wm2_f + 1.0f);
 }

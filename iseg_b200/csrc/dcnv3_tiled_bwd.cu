@@ -451,8 +451,8 @@ __device__ __forceinline__ void scatter_walk(int* acc, int* wsum, const T* __res
             const float cxo = ox, cyo = oy, cm = ml;
             ox = ox2; oy = oy2; ml = ml2;
             if (p + 2 < kTaps) load_tap_inputs<T>(offp, mskp, p + 2, ox2, oy2, ml2);  // two taps ahead
-            const Axis axx = axis_x(q, ref0, p, cxo);
-            const Axis axy = axis_y(q, ref1, p, cyo);
+            const Axis axx = axis_x_live(q, ref0, p, cxo);
+            const Axis axy = axis_y_live(q, ref1, p, cyo);
             if (!(axx.alive && axy.alive)) continue;  // a clipped corner pair coincides: contributes exactly 0
             const int lx = axx.i0 - q.pw - box.bx0;   // corner (y0,x0) relative to the box
             const int ly = axy.i0 - q.ph - box.by0;

@@ -276,21 +276,26 @@ def test_layer_matches_reference_layer(ops):
             assert rel_err(y, z["y"]) <= 5e-5, (name, fuse)  # dense / conv / LN around the op are cuBLAS / cuDNN
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_full_size_properties(ops, dtype):
-    """BASELINE config 2, stage 1 at full size (batch 16, 128x128, C=64, G=4): properties that need no
-    oracle.  out is linear in x and in mask, so with L = <out, go>:
+@pytest.mark.parametrize("dtype,shape,scale", [
+    (torch.float32, (16, 128, 128, 4, 16), 1.0),   # BASELINE config 2, stage 1, batch 16
+    (torch.bfloat16, (16, 128, 128, 4, 16), 1.0),
+    (torch.bfloat16, (4, 160, 160, 10, 16), 2.0),  # config 4: InternImage-L stage 1 at a 640 crop, offset_scale 2
+    (torch.bfloat16, (2, 193, 193, 4, 16), 1.0),   # config 5: one 769x769 sliding-window tile, stage 1
+])
+def test_full_size_properties(ops, dtype, shape, scale):
+    """BASELINE configs at full size: properties that need no oracle.  out is linear in x and in mask, so
+    with L = <out, go>:
         <x, grad_x> = L          (adjoint identity ties forward and backward scatter)
         <mask, grad_mask> = L
     and the forward is linear in x."""
     iseg, _ = ops
-    n, h, w, g, gc = 16, 128, 128, 4, 16
+    n, h, w, g, gc = shape
     gen = torch.Generator(device="cuda").manual_seed(0)
     r = lambda *s: torch.randn(*s, device="cuda", generator=gen)  # noqa: E731
     x, x2, off, go = r(n, h, w, g * gc), r(n, h, w, g * gc), r(n, h, w, g * 18), r(n, h, w, g * gc)
     mask = torch.softmax(r(n, h, w, g, 9), -1).reshape(n, h, w, g * 9)
     x, x2, off, go, mask = (t.to(dtype) for t in (x, x2, off, go, mask))
-    args = ([3, 3], [1, 1], "SAME", [1, 1], g, gc, 1.0)
+    args = ([3, 3], [1, 1], "SAME", [1, 1], g, gc, scale)
     xr, orq, mr = x.clone().requires_grad_(), off.clone().requires_grad_(), mask.clone().requires_grad_()
     out = iseg.dcnv3_op(xr, orq, mr, *args)
     out.backward(go)

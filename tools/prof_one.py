@@ -14,6 +14,7 @@ batch = int(sys.argv[5]) if len(sys.argv) > 5 else 16
 dtype = sys.argv[6] if len(sys.argv) > 6 else "f32"
 reps = int(sys.argv[7]) if len(sys.argv) > 7 else 3
 sigma = float(os.environ.get("OFFSET_SIGMA", "1.0"))
+scale = float(os.environ.get("OFFSET_SCALE", "1.0"))
 tdt = torch.float32 if dtype == "f32" else torch.bfloat16
 gen = torch.Generator(device="cuda").manual_seed(0)
 r = lambda *s: torch.randn(*s, device="cuda", generator=gen)  # noqa: E731
@@ -22,7 +23,7 @@ off = (sigma * r(batch, h, w, g * 18)).to(tdt)
 mask = torch.softmax(r(batch, h, w, g, 9), -1).reshape(batch, h, w, g * 9).to(tdt)
 go = r(batch, h, w, c).to(tdt)
 out, gx, goff, gm = torch.empty_like(x), torch.empty_like(x), torch.empty_like(off), torch.empty_like(mask)
-p = cabi.make_params(x.shape, (h, w), (3, 3), (1, 1), (1, 1), (1, 1), g, c // g, 1.0,
+p = cabi.make_params(x.shape, (h, w), (3, 3), (1, 1), (1, 1), (1, 1), g, c // g, scale,
                      cabi.F32 if dtype == "f32" else cabi.BF16, cabi.FLAG_WORKSPACE_ZEROED)
 wsb = int(cabi.lib.dcnv3_backward_workspace_bytes(ctypes.byref(p)))
 ws = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
@@ -42,4 +43,4 @@ for i in range(reps):
     torch.cuda.synchronize()
     tf.append(e[0].elapsed_time(e[1]) * 1e3)
     tb.append(e[1].elapsed_time(e[2]) * 1e3)
-print(f"{h}x{w} C{c} G{g} b{batch} {dtype}: fwd {min(tf):.1f} us  bwd {min(tb):.1f} us")
+print(f"{h}x{w} C{c} G{g} b{batch} {dtype} sigma={sigma} scale={scale}: fwd {min(tf):.1f} us  bwd {min(tb):.1f} us")
