@@ -77,8 +77,15 @@ def launch_list(path, dst):
     tot = sum(a[1] for a in agg.values())
     md = [f"# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare shares) -- {path}",
           "", "| kernel | launches | total us | share |", "|---|---|---|---|"]
+    ours = {k: v for k, v in agg.items() if k.startswith(("fwd_", "bwd_", "merge_", "redo_", "amax_", "fixed_"))}
+    tot_ours = sum(v[1] for v in ours.values()) or 1.0
     for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         md.append(f"| {name} | {n} | {us:.1f} | {100 * us / tot:.1f}% |")
+    md += ["", "The `at::` / softmax / fill kernels are torch generating the synthetic inputs, outside the timed region.",
+           "Shares among the library's own kernels (the ones inside the timed step):", "",
+           "| kernel | share of the step's kernels |", "|---|---|"]
+    for name, (n, us) in sorted(ours.items(), key=lambda kv: -kv[1][1]):
+        md.append(f"| {name} | {100 * us / tot_ours:.1f}% |")
     open(dst + ".md", "w").write("\n".join(md) + "\n")
 
 
