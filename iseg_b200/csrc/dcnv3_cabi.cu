@@ -216,7 +216,8 @@ struct HostScratch {
     void* ws = nullptr;
     size_t ws_bytes = 0;
     cudaStream_t stream = nullptr;                  // kernels of this slot
-    cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;  // inputs resident / kernels done / outputs copied
+    // forward inputs resident / grad_out resident / forward done / backward done / outputs copied
+    cudaEvent_t ev_in = nullptr, ev_go = nullptr, ev_fwd = nullptr, ev_comp = nullptr, ev_out = nullptr;
 };
 struct DevicePipes {
     cudaStream_t in = nullptr, out = nullptr;
@@ -240,6 +241,8 @@ static int scratch_reserve(int device, int slot, size_t bytes, size_t ws_bytes, 
         if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess)
             return cuda_fail(e, "cudaStreamCreate");
         if ((e = cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&s.ev_go, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&s.ev_fwd, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming)) != cudaSuccess)
             return cuda_fail(e, "cudaEventCreate");
@@ -418,21 +421,24 @@ static int host_run(const void* x, const void* offset, const void* mask, const v
     H2D(d_x, x, n_x);
     H2D(d_off, offset, n_off);
     H2D(d_m, mask, n_m);
-    if (with_backward) H2D(d_go, grad_out, n_o);
     CK(cudaEventRecord(s->ev_in, sin), "cudaEventRecord");
-    // kernels
+    if (with_backward) {
+        H2D(d_go, grad_out, n_o);
+        CK(cudaEventRecord(s->ev_go, sin), "cudaEventRecord");
+    }
+    // forward as soon as its three inputs are resident; its output leaves while grad_out still arrives
     CK(cudaStreamWaitEvent(st, s->ev_in, 0), "cudaStreamWaitEvent");
     if ((rc = forward_impl(d_x, d_off, d_m, d_out, p, st))) return rc;
+    CK(cudaEventRecord(s->ev_fwd, st), "cudaEventRecord");
+    CK(cudaStreamWaitEvent(sout, s->ev_fwd, 0), "cudaStreamWaitEvent");
+    D2H(out, d_out, n_o);
     if (with_backward) {
+        CK(cudaStreamWaitEvent(st, s->ev_go, 0), "cudaStreamWaitEvent");
         dcnv3_params pb = *p;
         pb.flags |= DCNV3_FLAG_WORKSPACE_ZEROED;  // the slot's workspace is zeroed at allocation and stays so
         if ((rc = backward_impl(d_x, d_off, d_m, d_go, d_gx, d_goff, d_gm, s->ws, s->ws_bytes, &pb, st))) return rc;
-    }
-    CK(cudaEventRecord(s->ev_comp, st), "cudaEventRecord");
-    // copy-out
-    CK(cudaStreamWaitEvent(sout, s->ev_comp, 0), "cudaStreamWaitEvent");
-    D2H(out, d_out, n_o);
-    if (with_backward) {
+        CK(cudaEventRecord(s->ev_comp, st), "cudaEventRecord");
+        CK(cudaStreamWaitEvent(sout, s->ev_comp, 0), "cudaStreamWaitEvent");
         D2H(grad_x, d_gx, n_x);
         D2H(grad_offset, d_goff, n_off);
         D2H(grad_mask, d_gm, n_m);
@@ -499,6 +505,8 @@ int dcnv3_release_host_scratch(void) {
                 if (s.ws) cudaFree(s.ws);
                 if (s.stream) cudaStreamDestroy(s.stream);
                 if (s.ev_in) cudaEventDestroy(s.ev_in);
+                if (s.ev_go) cudaEventDestroy(s.ev_go);
+                if (s.ev_fwd) cudaEventDestroy(s.ev_fwd);
                 if (s.ev_comp) cudaEventDestroy(s.ev_comp);
                 if (s.ev_out) cudaEventDestroy(s.ev_out);
                 s = HostScratch();
