@@ -137,7 +137,8 @@ static int backward_impl(const void* x, const void* offset, const void* mask, co
     cudaError_t e =
         tiled ? launch_bwd_tiled(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, p->dtype,
                                  (p->flags & DCNV3_FLAG_WORKSPACE_ZEROED) != 0, st)
-              : launch_bwd_generic(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, p->dtype, st);
+              : launch_bwd_generic(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, p->dtype,
+                                   (p->flags & DCNV3_FLAG_WORKSPACE_ZEROED) != 0, st);
     if (e != cudaSuccess) return cuda_fail(e, "dcnv3_backward launch");
     return DCNV3_OK;
 }

@@ -189,12 +189,14 @@ bwd_generic_kernel(const T* __restrict__ x, const T* __restrict__ offset, const 
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-fixed_to_float_kernel(const long long* __restrict__ acc64, const WsHeader* __restrict__ hd,
+fixed_to_float_kernel(long long* __restrict__ acc64, const WsHeader* __restrict__ hd,
                       T* __restrict__ grad_x, size_t count, unsigned flags) {
     const int e = fixed_exponent(hd, flags & DCNV3_FLAG_MASK_LOGITS);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
         Elem<T>::st(grad_x + i, (float)ldexp((double)acc64[i], -e));
+        acc64[i] = 0;  // the workspace is left all-zero (DCNV3_FLAG_WORKSPACE_ZEROED contract, shared with the tiled path)
+    }
 }
 
 // ---- launchers -----------------------------------------------------------------------------------
@@ -234,10 +236,11 @@ size_t bwd_generic_workspace_bytes(const KParams& q) {
 template <typename T>
 cudaError_t launch_bwd_generic_t(const void* x, const void* offset, const void* mask,
                                  const void* grad_out, void* grad_x, void* grad_offset,
-                                 void* grad_mask, void* ws, const KParams& q, cudaStream_t st) {
+                                 void* grad_mask, void* ws, const KParams& q, bool ws_clean, cudaStream_t st) {
     const size_t n_x = (size_t)q.n * q.h * q.w * q.G * q.gc;
     const size_t pg = (size_t)q.n * q.ho * q.wo * q.G;
-    cudaError_t err = cudaMemsetAsync(ws, 0, bwd_generic_workspace_bytes(q), st);
+    // (the header is rewritten by every call; the accumulators are re-zeroed by fixed_to_float_kernel)
+    cudaError_t err = cudaMemsetAsync(ws, 0, ws_clean ? sizeof(WsHeader) : bwd_generic_workspace_bytes(q), st);
     if (err != cudaSuccess) return err;
     WsHeader* hd = (WsHeader*)ws;
     unsigned long long* acc = (unsigned long long*)((char*)ws + sizeof(WsHeader));
@@ -253,7 +256,7 @@ cudaError_t launch_bwd_generic_t(const void* x, const void* offset, const void* 
     }
     if (n_x > 0) {
         const unsigned nb = (unsigned)min((size_t)148 * 16, (n_x + 255) / 256);
-        fixed_to_float_kernel<T><<<nb, 256, 0, st>>>((const long long*)acc, hd, (T*)grad_x, n_x, q.flags);
+        fixed_to_float_kernel<T><<<nb, 256, 0, st>>>((long long*)acc, hd, (T*)grad_x, n_x, q.flags);
         count_launch(1);
     }
     return cudaGetLastError();
@@ -261,10 +264,10 @@ cudaError_t launch_bwd_generic_t(const void* x, const void* offset, const void* 
 
 cudaError_t launch_bwd_generic(const void* x, const void* offset, const void* mask,
                                const void* grad_out, void* grad_x, void* grad_offset, void* grad_mask,
-                               void* ws, const KParams& q, int dtype, cudaStream_t st) {
+                               void* ws, const KParams& q, int dtype, bool ws_clean, cudaStream_t st) {
     return dtype == DCNV3_F32
-               ? launch_bwd_generic_t<float>(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, st)
-               : launch_bwd_generic_t<__nv_bfloat16>(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, st);
+               ? launch_bwd_generic_t<float>(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, ws_clean, st)
+               : launch_bwd_generic_t<__nv_bfloat16>(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, ws_clean, st);
 }
 
 }  // namespace dcnv3

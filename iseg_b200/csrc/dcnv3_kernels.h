@@ -20,7 +20,7 @@ cudaError_t launch_fwd_generic(const void* x, const void* offset, const void* ma
 size_t bwd_generic_workspace_bytes(const KParams& q);
 cudaError_t launch_bwd_generic(const void* x, const void* offset, const void* mask,
                                const void* grad_out, void* grad_x, void* grad_offset, void* grad_mask,
-                               void* ws, const KParams& q, int dtype, cudaStream_t st);
+                               void* ws, const KParams& q, int dtype, bool ws_clean, cudaStream_t st);
 
 // tiled path (dcnv3_tiled_*.cu): k=3, s=1, d=1, SAME, 16 channels per group
 bool tiled_applicable(const KParams& q, int dtype);

@@ -19,7 +19,8 @@ namespace dcnv3 {
 constexpr int kTaps = 9;
 constexpr int kGC = 16;
 constexpr int kCellBytes = 128;
-constexpr int kMaxBoxBytes = 82 * 1024;  // staged input box; with the row staging slots two CTAs fit one SM
+constexpr int kMaxBoxBytes = 82 * 1024;  // staged input box of the gather kernel; with the row staging slots two CTAs fit one SM
+constexpr int kFwdBoxBytes = 100 * 1024; // staged input box of the forward kernel (no staging slots): two CTAs per SM
 
 template <typename T>
 struct Chunk {

@@ -172,19 +172,11 @@ bool make_x_tensor_map(CUtensorMap* map, const void* x, const KParams& q, int dt
     return r == CUDA_SUCCESS;
 }
 
-// Tiled kernels serve the InternImage configuration only.
-bool tiled_applicable(const KParams& q, int dtype) {
-    (void)dtype;  // any group count: the last chunk may be partly empty (phantom groups are masked)
-    return q.P == 9 && q.kh == 3 && q.sh == 1 && q.sw == 1 && q.dh == 1 && q.dw == 1 && q.gc == kGC &&
-           q.ho == q.h && q.wo == q.w && q.ph == 1 && q.pw == 1 && q.scale > 0.f &&
-           q.scale <= 16.f && q.h <= 16384 && q.w <= 16384;
-}
-
 // Box geometry: the nominal footprint of a th x tw output tile spans (th-1)*ax columns and (tw-1)*ay
 // rows (ax = (W_in-2)/H_in, ay = (H_in-2)/W_in); taps add (1 + |offset|)*scale*(dim-2)/dim on each side
 // and the bilinear patch one more cell.  `reach` is the |offset| (reference units) served from shared
 // memory; beyond it the global fallback takes over.
-TileGeom make_geom(const KParams& q, int dtype, int th, int tw, float reach, int max_cells) {
+static TileGeom geom_at(const KParams& q, int dtype, int th, int tw, float reach) {
     TileGeom tg;
     tg.th = min(th, q.ho);
     tg.tw = min(tw, q.wo);
@@ -194,23 +186,63 @@ TileGeom make_geom(const KParams& q, int dtype, int th, int tw, float reach, int
     tg.chunks = (q.G + gq - 1) / gq;  // a trailing partial chunk reads zero-filled phantom groups (TMA OOB)
     const float ax = q.wm2_f / q.hin_f, ay = q.hm2_f / q.win_f;
     const float rx = q.wm2_f / q.win_f, ry = q.hm2_f / q.hin_f;
-    for (;; reach *= 0.75f) {
-        tg.halo_x = (int)ceilf((1.0f + reach) * fabsf(q.scale) * rx);
-        tg.halo_y = (int)ceilf((1.0f + reach) * fabsf(q.scale) * ry);
-        tg.bw = (int)ceilf((tg.th - 1) * ax) + 2 * tg.halo_x + 2;
-        tg.bh = (int)ceilf((tg.tw - 1) * ay) + 2 * tg.halo_y + 2;
-        // never stage more than the padded image itself
-        tg.bw = min(tg.bw, min(q.win, 256));
-        tg.bh = min(tg.bh, min(q.hin, 256));
-        if (tg.bw * tg.bh <= max_cells || reach < 0.05f) break;
-    }
+    tg.halo_x = (int)ceilf((1.0f + reach) * fabsf(q.scale) * rx);
+    tg.halo_y = (int)ceilf((1.0f + reach) * fabsf(q.scale) * ry);
+    tg.bw = (int)ceilf((tg.th - 1) * ax) + 2 * tg.halo_x + 2;
+    tg.bh = (int)ceilf((tg.tw - 1) * ay) + 2 * tg.halo_y + 2;
+    // never stage more than the padded image itself
+    tg.bw = min(tg.bw, min(q.win, 256));
+    tg.bh = min(tg.bh, min(q.hin, 256));
     return tg;
+}
+
+// 16 x 16 output tiles with the largest reach <= `reach` whose box fits.  The reference pairs output rows
+// with input columns, so on strongly non-square images a 16-row tile spans 16*W/H columns,
+// and a large offset_scale widens every halo: when the square tile cannot keep a reach of 1 offset unit,
+// tile shape (rows down to 1, columns up to 128) and reach are chosen together by a simple cost model --
+// pixels per staged cell, discounted by the share of taps (offsets ~ N(0,1)) that would miss the box and
+// take the ~10x slower global path.  If nothing fits, bw * bh > max_cells in the result and the caller
+// uses the generic kernels.
+TileGeom make_geom(const KParams& q, int dtype, int th, int tw, float reach, int max_cells) {
+    TileGeom tg;
+    for (float r = reach; r >= 1.0f; r *= 0.75f) {
+        tg = geom_at(q, dtype, th, tw, r);
+        if (tg.bw * tg.bh <= max_cells) return tg;
+    }
+    TileGeom best = geom_at(q, dtype, th, tw, reach);
+    float best_score = -1.0f;
+    for (int h = 16; h >= 1; h >>= 1)
+        for (int w = 16; w <= 128; w <<= 1)
+            for (float r = reach; r >= 0.05f; r *= 0.75f) {
+                const TileGeom c = geom_at(q, dtype, h, w, r);
+                if (c.bw * c.bh > max_cells) continue;
+                const float miss = 1.0f - erff(r * 0.70710678f);
+                const float score = (float)(c.th * c.tw) / (float)(c.bw * c.bh) / (1.0f + 10.0f * miss);
+                if (score > best_score) {
+                    best_score = score;
+                    best = c;
+                }
+                break;  // smaller reaches of this shape only score lower
+            }
+    return best;
+}
+
+// Tiled kernels serve the InternImage configuration only -- and only images whose tile boxes fit shared
+// memory (everything but extreme aspect ratios at large offset_scale); the rest runs the generic kernels.
+bool tiled_applicable(const KParams& q, int dtype) {
+    // any group count: the last chunk may be partly empty (phantom groups are masked)
+    if (!(q.P == 9 && q.kh == 3 && q.sh == 1 && q.sw == 1 && q.dh == 1 && q.dw == 1 && q.gc == kGC && q.ho == q.h &&
+          q.wo == q.w && q.ph == 1 && q.pw == 1 && q.scale > 0.f && q.scale <= 16.f && q.h <= 16384 && q.w <= 16384))
+        return false;
+    const int fwd_cells = kFwdBoxBytes / kCellBytes, bwd_cells = kMaxBoxBytes / kCellBytes;
+    const TileGeom a = make_geom(q, dtype, 16, 16, 3.0f, fwd_cells), b = make_geom(q, dtype, 16, 16, 3.0f, bwd_cells);
+    return a.bw * a.bh <= fwd_cells && b.bw * b.bh <= bwd_cells;
 }
 
 template <typename T>
 static cudaError_t launch_fwd_tiled_t(const void* x, const void* offset, const void* mask, void* out,
                                       const KParams& q, int dtype, cudaStream_t st) {
-    const int max_cells = 100 * 1024 / kCellBytes;  // two CTAs per SM
+    const int max_cells = kFwdBoxBytes / kCellBytes;  // two CTAs per SM
     const TileGeom tg = make_geom(q, dtype, 16, 16, 3.0f, max_cells);
     if (tg.bw * tg.bh > max_cells) return cudaErrorInvalidConfiguration;
     CUtensorMap map;
@@ -221,7 +253,7 @@ static cudaError_t launch_fwd_tiled_t(const void* x, const void* offset, const v
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {  // per device: the attribute lives in the context
         cudaError_t e = cudaFuncSetAttribute(fwd_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             100 * 1024);
+                                             kFwdBoxBytes);
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }

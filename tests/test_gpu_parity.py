@@ -146,6 +146,46 @@ def test_fuzz_shapes_offsets_vs_c_oracle(ops):
             assert rel_err(a, b) <= TOL_F32 or not np.abs(b).max() > 0, (name, rel_err(a, b), tag)
 
 
+@pytest.mark.parametrize("shape", [(1, 20, 300, 4), (1, 130, 70, 6), (2, 97, 49, 2), (1, 257, 33, 3), (1, 33, 257, 2)])
+@pytest.mark.parametrize("scale,sigma", [(1.0, 1.0), (2.0, 1.5), (0.5, 6.0)])
+def test_wide_and_tall_images(ops, shape, scale, sigma):
+    """Strongly non-square images: the reference pairs output rows with input columns, so the
+    scatter tiles see very different numbers of home pixels per tile, partial tiles on both axes, rings
+    clipped by the image and -- at sigma = 6 -- many landings beyond the ring (64-bit side path)."""
+    n, h, w, g = shape
+    x, off, m, go = make_inputs(n, h, w, g, 16, sigma=sigma, seed=h * 7 + w)
+    kw = dict(groups=g, group_channels=16, offset_scale=scale)
+    out, gx, goff, gm = run_op(ops, x, off, m, go, **kw)
+    ref_out = c_oracle.forward(x, off, m, **kw)
+    rx, roff, rm = c_oracle.backward(x, off, m, go, **kw)
+    assert rel_err(out, ref_out) <= TOL_F32
+    assert rel_err(gx, rx) <= TOL_F32
+    assert rel_err(goff, roff) <= TOL_F32
+    assert rel_err(gm, rm) <= TOL_F32
+    again = run_op(ops, x, off, m, go, **kw)
+    assert np.array_equal(gx, again[1])
+
+
+def test_workspace_stays_zeroed_across_generic_and_tiled(ops):
+    """Both backward paths share one cached, zeroed-once workspace (DCNV3_FLAG_WORKSPACE_ZEROED): whichever
+    ran last must leave it all-zero, including after far landings and hot cells."""
+    _, cabi = ops
+    n, h, w, g, gc = 2, 40, 70, 4, 16
+    x, off, m, go = make_inputs(n, h, w, g, gc, sigma=5.0, seed=11)
+    rx, roff, rm = c_oracle.backward(x, off, m, go, groups=g, group_channels=gc)
+    t = [torch.from_numpy(a).cuda() for a in (x, off, m, go)]
+    cfg = ((3, 3), (1, 1), (1, 1), (1, 1), g, gc, 1.0)
+    for flags in (cabi.FLAG_FORCE_GENERIC, 0, cabi.FLAG_FORCE_GENERIC, 0, 0):
+        gx, goff, gm = cabi.backward(*t, *cfg, flags=flags)
+        assert rel_err(gx.cpu().numpy(), rx) <= TOL_F32, flags
+        assert rel_err(goff.cpu().numpy(), roff) <= TOL_F32 and rel_err(gm.cpu().numpy(), rm) <= TOL_F32
+    import ctypes
+    prm = cabi.make_params(x.shape, (h, w), *cfg[:4], g, gc, 1.0, cabi.F32)
+    ws = cabi._workspace(t[0].device, int(cabi.lib.dcnv3_backward_workspace_bytes(ctypes.byref(prm))))  # the cached one
+    torch.cuda.synchronize()
+    assert int(ws[256:].count_nonzero()) == 0  # everything but the 256-byte header
+
+
 def test_backward_bitwise_reproducible(ops):
     x, off, m, go = make_inputs(4, 64, 64, 8, 16, sigma=2.0, seed=3)
     kw = dict(groups=8, group_channels=16)
