@@ -77,6 +77,8 @@ CASES = [  # n, h, w, G, gc, sigma, offset_scale
     (1, 24, 24, 7, 16, 1.0, 1.0),      # odd group count (InternImage-B): trailing half-empty chunk
     (2, 40, 33, 5, 16, 2.0, 1.0),      # InternImage-S stage 1 style (G=5)
     (1, 9, 11, 3, 5, 1.5, 1.0),        # gc not a multiple of 4 -> scalar path
+    (1, 20, 20, 80, 16, 1.0, 2.0),     # InternImage-L stage 4: G = 80, offset_scale 2
+    (3, 64, 64, 2, 16, 8.0, 1.0),      # most landings beyond the scatter ring (64-bit side path)
 ]
 
 
@@ -95,7 +97,8 @@ def test_random_fp32_vs_c_oracle(ops, case):
     assert rel_err(gm, rm) <= TOL_F32
 
 
-@pytest.mark.parametrize("case", CASES[:4] + CASES[5:9])
+@pytest.mark.parametrize("case", CASES[:4] + CASES[5:9] + [(1, 20, 300, 4, 16, 1.0, 1.0), (1, 130, 70, 6, 16, 3.0, 2.0),
+                                                          (1, 20, 20, 80, 16, 1.0, 2.0)])
 def test_random_bf16(ops, case):
     n, h, w, g, gc, sigma, scale = case
     x, off, m, go = make_inputs(n, h, w, g, gc, sigma=sigma, seed=7 + h)
@@ -226,9 +229,11 @@ def test_backward_bitwise_reproducible(ops):
     assert rel_err(c[1], rx) <= TOL_F32
 
 
-def test_fused_softmax_matches_layer_semantics(ops):
-    n, h, w, g, gc = 2, 24, 20, 4, 16
-    x, off, _, go = make_inputs(n, h, w, g, gc, seed=11)
+@pytest.mark.parametrize("shape,sigma", [((2, 24, 20, 4, 16), 1.0), ((1, 70, 45, 5, 16), 4.0)])
+def test_fused_softmax_matches_layer_semantics(ops, shape, sigma):
+    """(second case: several scatter tiles, odd group count, landings beyond the ring)"""
+    n, h, w, g, gc = shape
+    x, off, _, go = make_inputs(n, h, w, g, gc, sigma=sigma, seed=11)
     logits = np.random.default_rng(5).standard_normal((n, h, w, g * 9)).astype(np.float32) * 2
     kw = dict(groups=g, group_channels=gc)
     out, gx, goff, gl = run_op(ops, x, off, logits, go, mask_is_logits=True, **kw)
