@@ -116,10 +116,12 @@ int dcnv3_forward_backward_host(const void* x, const void* offset, const void* m
                                 const void* grad_out, void* out, void* grad_x, void* grad_offset,
                                 void* grad_mask, const dcnv3_params* p, int device);
 
-/* Pipelined variant: enqueues copy-in, kernels and copy-out on the stream of scratch slot
-   `slot` (0 <= slot < dcnv3_host_slots()) and returns without waiting, so that consecutive calls on
-   different slots overlap H2D, compute and D2H.  Host buffers must be pinned and stay valid until
-   dcnv3_host_sync(device) (or the next call on the same slot) returns. */
+/* Pipelined variant: enqueues copy-in (on the device's copy-in stream), kernels (on the stream of scratch
+   slot `slot`, 0 <= slot < dcnv3_host_slots()) and copy-out (on the device's copy-out stream), chained by
+   events, and returns without waiting, so that consecutive calls on different slots overlap H2D, compute
+   and D2H at full PCIe rate in both directions.  A slot's scratch is reused as soon as its previous outputs
+   have been copied out (the wait happens on the device).  Host buffers must be pinned and stay valid --
+   inputs unmodified, outputs unread -- until dcnv3_host_sync(device) returns. */
 int dcnv3_forward_backward_host_async(const void* x, const void* offset, const void* mask,
                                       const void* grad_out, void* out, void* grad_x, void* grad_offset,
                                       void* grad_mask, const dcnv3_params* p, int device, int slot);
