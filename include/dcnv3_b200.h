@@ -80,6 +80,15 @@ const char* dcnv3_build_info(void);
 /* Validates a parameter block the way the reference's reshapes would. */
 int dcnv3_check_params(const dcnv3_params* p);
 
+/* Introspection (no GPU needed; tests/test_cabi_cpu.py): how a call with these parameters would be tiled.
+   plan25[0]      1 = shared-memory tiled kernels, 0 = generic kernels (the rest is then 0)
+   plan25[1..8]   forward:  tile rows, tile cols, box width, box height (cells of 128 B), halo x, halo y,
+                  CTAs, dynamic shared memory bytes
+   plan25[9..16]  grad_offset / grad_mask kernel: the same eight numbers
+   plan25[17..24] grad_x scatter kernel: tile edge (input cells), ring below, ring above, box rows, CTAs,
+                  dynamic shared memory bytes, threads per CTA, 1 if the side-buffer merge kernel is launched */
+int dcnv3_launch_plan(const dcnv3_params* p, int* plan25);
+
 /* ---- device-pointer entry points (replace op.py:16 and its autodiff gradient) ---- */
 int dcnv3_forward(const void* x, const void* offset, const void* mask, void* out,
                   const dcnv3_params* p, void* cuda_stream);

@@ -46,6 +46,7 @@ def _load():
     lib.dcnv3_last_error.restype = ctypes.c_char_p
     lib.dcnv3_build_info.restype = ctypes.c_char_p
     lib.dcnv3_check_params.argtypes = [pp]
+    lib.dcnv3_launch_plan.argtypes = [pp, ctypes.POINTER(ctypes.c_int)]
     lib.dcnv3_forward.argtypes = [vp] * 4 + [pp, vp]
     lib.dcnv3_backward_workspace_bytes.argtypes = [pp]
     lib.dcnv3_backward_workspace_bytes.restype = ctypes.c_size_t
@@ -86,6 +87,16 @@ def check(rc):
         if rc == ERR_DTYPE:
             raise TypeError(f"dcnv3_b200: {msg}")
         raise DCNv3Error(rc, msg)
+
+
+def launch_plan(params):
+    """dcnv3_launch_plan as a dict (CPU-only introspection of the tiling)."""
+    buf = (ctypes.c_int * 25)()
+    check(lib.dcnv3_launch_plan(ctypes.byref(params), buf))
+    v = list(buf)
+    keys = ("th", "tw", "bw", "bh", "halo_x", "halo_y", "ctas", "smem")
+    return {"tiled": bool(v[0]), "forward": dict(zip(keys, v[1:9])), "gather": dict(zip(keys, v[9:17])),
+            "scatter": dict(zip(("tj", "ring_lo", "ring_hi", "box_rows", "ctas", "smem", "threads", "merge"), v[17:25]))}
 
 
 def launch_count():

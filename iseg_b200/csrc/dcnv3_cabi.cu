@@ -291,6 +291,20 @@ const char* dcnv3_build_info(void) {
 
 int dcnv3_check_params(const dcnv3_params* p) { return check(p); }
 
+int dcnv3_launch_plan(const dcnv3_params* p, int* plan25) {
+    int rc = check(p);
+    if (rc) return rc;
+    if (plan25 == nullptr) return fail(DCNV3_ERR_ARGUMENT, "NULL plan buffer");
+    const KParams q = derive(p);
+    for (int i = 0; i < 25; ++i) plan25[i] = 0;
+    plan25[0] = tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC);
+    if (plan25[0]) {
+        fwd_tiled_plan(q, p->dtype, plan25 + 1);
+        bwd_tiled_plan(q, p->dtype, plan25 + 9);
+    }
+    return DCNV3_OK;
+}
+
 int dcnv3_forward(const void* x, const void* offset, const void* mask, void* out,
                   const dcnv3_params* p, void* cuda_stream) {
     return forward_impl(x, offset, mask, out, p, (cudaStream_t)cuda_stream);

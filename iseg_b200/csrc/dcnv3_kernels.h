@@ -27,6 +27,9 @@ bool tiled_applicable(const KParams& q, int dtype);
 cudaError_t launch_fwd_tiled(const void* x, const void* offset, const void* mask, void* out,
                              const KParams& q, int dtype, cudaStream_t st);
 
+// launch plans as plain numbers (dcnv3_launch_plan: CPU-side tests of the tiling logic)
+void fwd_tiled_plan(const KParams& q, int dtype, int out[8]);   // th tw bw bh halo_x halo_y grid smem_bytes
+void bwd_tiled_plan(const KParams& q, int dtype, int out[16]);  // gather: as above; scatter: tj ring_lo ring_hi box_rows grid smem_bytes threads merge
 size_t bwd_tiled_workspace_bytes(const KParams& q);
 cudaError_t launch_bwd_tiled(const void* x, const void* offset, const void* mask, const void* grad_out,
                              void* grad_x, void* grad_offset, void* grad_mask, void* ws, const KParams& q,

@@ -43,6 +43,7 @@ struct TileGeom {
 // host helpers implemented in dcnv3_tiled_fwd.cu
 TileGeom make_geom(const KParams& q, int dtype, int th, int tw, float reach, int max_cells);
 bool make_x_tensor_map(CUtensorMap* map, const void* x, const KParams& q, int dtype, int bw, int bh);
+void gather_tiled_plan(const KParams& q, int dtype, int stage_bytes, int out[8]);
 
 // Nominal sampling position of output row h / column w (zero offset, centre tap), reference
 // arithmetic collapsed: xq = ((h + 1.5) / H_in) * (W_in - 2)  -- note H_in under h: the reference

@@ -800,6 +800,16 @@ static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const v
     return cudaGetLastError();
 }
 
+void bwd_tiled_plan(const KParams& q, int dtype, int out[16]) {
+    gather_tiled_plan(q, dtype, 8 * (dtype == DCNV3_F32 ? kGatherStageBytes<float> : kGatherStageBytes<__nv_bfloat16>), out);
+    const BwdGeom bg = make_bwd_geom(q);
+    out[8] = bg.tj; out[9] = bg.ring_lo; out[10] = bg.ring_hi; out[11] = bg.box_rows;
+    out[12] = (int)((long long)q.n * bg.tiles_x * bg.tiles_y * bg.chunks);
+    out[13] = (int)(bg.tj == 32 ? scatter_smem_bytes<32>(bg.box_rows) : scatter_smem_bytes<16>(bg.box_rows));
+    out[14] = bg.tj == 32 ? ScatterShape<32>::THREADS : ScatterShape<16>::THREADS;
+    out[15] = bg.tiles_x * bg.tiles_y > 1;
+}
+
 cudaError_t launch_bwd_tiled(const void* x, const void* offset, const void* mask, const void* grad_out,
                              void* grad_x, void* grad_offset, void* grad_mask, void* ws, const KParams& q,
                              int dtype, bool ws_clean, cudaStream_t st) {

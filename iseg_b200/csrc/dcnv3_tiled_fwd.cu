@@ -263,6 +263,22 @@ static cudaError_t launch_fwd_tiled_t(const void* x, const void* offset, const v
     return cudaGetLastError();
 }
 
+static void geom_numbers(const KParams& q, const TileGeom& tg, long long smem, int out[8]) {
+    out[0] = tg.th; out[1] = tg.tw; out[2] = tg.bw; out[3] = tg.bh; out[4] = tg.halo_x; out[5] = tg.halo_y;
+    out[6] = (int)((long long)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
+    out[7] = (int)smem;
+}
+
+void fwd_tiled_plan(const KParams& q, int dtype, int out[8]) {
+    const TileGeom tg = make_geom(q, dtype, 16, 16, 3.0f, kFwdBoxBytes / kCellBytes);
+    geom_numbers(q, tg, (long long)tg.bw * tg.bh * kCellBytes, out);
+}
+
+void gather_tiled_plan(const KParams& q, int dtype, int stage_bytes, int out[8]) {
+    const TileGeom tg = make_geom(q, dtype, 16, 16, 3.0f, kMaxBoxBytes / kCellBytes);
+    geom_numbers(q, tg, (long long)tg.bw * tg.bh * kCellBytes + stage_bytes, out);
+}
+
 cudaError_t launch_fwd_tiled(const void* x, const void* offset, const void* mask, void* out,
                              const KParams& q, int dtype, cudaStream_t st) {
     return dtype == DCNV3_F32 ? launch_fwd_tiled_t<float>(x, offset, mask, out, q, dtype, st)

@@ -94,3 +94,51 @@ def test_layer_signature_matches_reference():
     assert names == {"dw_conv", "dw_conv_norm", "offset", "mask", "input_proj", "output_proj",
                      "center_feature_scale_proj"}  # dcn_v3.py:62-102
     assert not layer.offset.weight.any() and not layer.mask.weight.any()  # zero init, :74-86
+
+
+def test_launch_plans_fit_the_hardware_for_any_shape(cabi):
+    """dcnv3_launch_plan (no GPU): whatever the image shape, group count, dtype and offset_scale, a tiled
+    plan must fit an SM's shared memory (227 KB per CTA, two forward / gather CTAs per SM) and keep its
+    geometry consistent; strongly non-square images used to fail at launch time (the reference pairs output
+    rows with input columns, so a 16-row tile spans 16*W/H columns)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    shapes = [(128, 128), (64, 64), (32, 32), (16, 16), (160, 160), (80, 80), (40, 40), (20, 20), (193, 193), (97, 97),
+              (49, 49), (25, 25), (256, 512), (512, 256), (20, 300), (300, 20), (257, 33), (33, 257), (3, 3), (3, 1000),
+              (1000, 3), (1024, 2048), (7, 64)]
+    shapes += [(int(rng.integers(3, 700)), int(rng.integers(3, 700))) for _ in range(300)]
+    n_tiled = 0
+    for h, w in shapes:
+        for scale in (0.25, 0.5, 1.0, 2.0, 4.0):
+            for dtype, g in ((cabi.F32, 4), (cabi.BF16, 5), (cabi.F32, 1)):
+                p = cabi.make_params((2, h, w, g * 16), (h, w), (3, 3), (1, 1), (1, 1), (1, 1), g, 16, scale, dtype)
+                plan = cabi.launch_plan(p)
+                if not plan["tiled"]:
+                    continue
+                n_tiled += 1
+                f, ga, sc = plan["forward"], plan["gather"], plan["scatter"]
+                for k in (f, ga):
+                    assert 1 <= k["th"] <= 16 and 1 <= k["tw"] <= 128, (h, w, scale, k)
+                    assert 2 <= k["bw"] <= min(w + 2, 256) and 2 <= k["bh"] <= min(h + 2, 256), (h, w, scale, k)
+                    assert k["halo_x"] >= 1 and k["halo_y"] >= 1 and k["ctas"] >= 1
+                assert f["smem"] == f["bw"] * f["bh"] * 128 <= 100 * 1024, (h, w, scale, f)
+                assert ga["bw"] * ga["bh"] * 128 <= 82 * 1024 and 2 * ga["smem"] <= 227 * 1024, (h, w, scale, ga)
+                pitch = sc["tj"] + 9
+                assert sc["tj"] in (16, 32) and 1 <= sc["ring_lo"] <= 4 and 2 <= sc["ring_hi"] <= 5
+                assert 1 <= sc["box_rows"] <= pitch and sc["smem"] <= 227 * 1024 and sc["ctas"] >= 1
+                assert sc["merge"] == (h > sc["tj"] or w > sc["tj"])
+    assert n_tiled > 3000
+    # the shapes InternImage runs (square-ish, offset_scale 1 or 2): always tiled, full 16 x 16 tiles, and
+    # at offset_scale 1 a forward reach of 3 offset units (halo 4)
+    for h, w, g, scale in ((128, 128, 4, 1.0), (32, 32, 16, 1.0), (193, 193, 4, 1.0), (160, 160, 10, 2.0),
+                           (256, 512, 4, 1.0), (25, 49, 32, 1.0)):
+        p = cabi.make_params((16, h, w, g * 16), (h, w), (3, 3), (1, 1), (1, 1), (1, 1), g, 16, scale, cabi.F32)
+        plan = cabi.launch_plan(p)
+        assert plan["tiled"] and plan["forward"]["th"] == 16 and plan["forward"]["tw"] == 16, (h, w, plan)
+        if scale == 1.0:
+            assert plan["forward"]["halo_x"] == 4 and plan["scatter"]["ring_lo"] == 4 and plan["scatter"]["ring_hi"] == 5
+    # other kernel sizes / strides / channel counts are served by the generic kernels
+    p = cabi.make_params((2, 32, 32, 64), (32, 32), (5, 5), (1, 1), (2, 2), (1, 1), 4, 16, 1.0, cabi.F32)
+    assert not cabi.launch_plan(p)["tiled"]
+    p = cabi.make_params((2, 32, 32, 32), (32, 32), (3, 3), (1, 1), (1, 1), (1, 1), 4, 8, 1.0, cabi.F32)
+    assert not cabi.launch_plan(p)["tiled"]
