@@ -225,8 +225,6 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict_
 #pragma unroll
         for (int pc = 0; pc < C::NPIECE; ++pc)
             load_piece<T>(grad_out + pg * kGC + Slab<T>::chan_of(pc, rot), go + pc * C::PAIRS);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) amax = fmaxf(amax, fmaxf(fabsf(lo_of(go[c])), fabsf(hi_of(go[c]))));
         float mx = 0.f, inv_sum = 1.f;
         if (logits) softmax_stats9<T>(mskp, mx, inv_sum);
         float ref0, ref1;
@@ -299,6 +297,10 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict_
             if (logits || sizeof(T) == 4) park[lane * kTaps + p] = g_m;
             else *reinterpret_cast<__nv_bfloat16*>(st + RS::OFF_BYTES + lane * RS::LANE_MSK + p * 2) = __float2bfloat16_rn(g_m);
         }
+        // (max |grad_out| is taken here, after the taps: the first use of the freshly loaded grad_out is then
+        //  the first tap's dot products, behind its coordinate arithmetic and shared-memory loads)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) amax = fmaxf(amax, fmaxf(fabsf(lo_of(go[c])), fabsf(hi_of(go[c]))));
         if (logits) {
             // softmax Jacobian needs sum_p m_p*dL/dm_p: second sweep over this lane's own 9 values
 #pragma unroll 1
