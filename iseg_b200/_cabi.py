@@ -118,16 +118,23 @@ def _stream(t):
 _ws_cache = {}
 
 
+def _ws_key(device, nbytes):
+    return (device.index, torch.cuda.current_stream(device).cuda_stream, int(nbytes))
+
+
 def _workspace(device, nbytes):
     """Backward workspace, zeroed once and kept per (device, stream, size): dcnv3_backward leaves it
-    zeroed, so later calls on the same stream skip the memset (DCNV3_FLAG_WORKSPACE_ZEROED)."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream, int(nbytes))
+    zeroed, so later calls on the same stream skip the memset (DCNV3_FLAG_WORKSPACE_ZEROED).
+    A workspace first needed during CUDA-graph capture lives in the graph's private pool: it is handed
+    out zeroed but never cached.  A failed backward drops its cache entry (see backward())."""
+    key = _ws_key(device, nbytes)
     ws = _ws_cache.get(key)
     if ws is None:
-        if len(_ws_cache) >= 64:
-            _ws_cache.clear()
         ws = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-        _ws_cache[key] = ws
+        if not torch.cuda.is_current_stream_capturing():
+            if len(_ws_cache) >= 64:
+                _ws_cache.clear()
+            _ws_cache[key] = ws
     return ws
 
 
@@ -157,11 +164,16 @@ def backward(x, offset, mask, grad_out, kernel_size, strides, pad, dilation_rate
                     group_channels, offset_scale, dt, flags)
     ws_bytes = int(lib.dcnv3_backward_workspace_bytes(ctypes.byref(p)))
     ws = _workspace(x.device, ws_bytes)
-    caps = [_dl(t) for t in (x, offset, mask, grad_out, gx, goff, gm, ws)]
-    with torch.cuda.device(x.device):
-        rc = lib.dcnv3_backward_dlpack(
-            *[c[1] for c in caps], kernel_size[0], kernel_size[1], strides[0], strides[1], pad[0],
-            pad[1], dilation_rate[0], dilation_rate[1], groups, group_channels, float(offset_scale),
-            flags | FLAG_WORKSPACE_ZEROED, _stream(x))
+    rc = None
+    try:
+        caps = [_dl(t) for t in (x, offset, mask, grad_out, gx, goff, gm, ws)]
+        with torch.cuda.device(x.device):
+            rc = lib.dcnv3_backward_dlpack(
+                *[c[1] for c in caps], kernel_size[0], kernel_size[1], strides[0], strides[1], pad[0],
+                pad[1], dilation_rate[0], dilation_rate[1], groups, group_channels, float(offset_scale),
+                flags | FLAG_WORKSPACE_ZEROED, _stream(x))
+    finally:
+        if rc != 0:  # error or exception: the workspace may be dirty -- the next call starts from a fresh one
+            _ws_cache.pop(_ws_key(x.device, ws_bytes), None)
     check(rc)
     return gx, goff, gm

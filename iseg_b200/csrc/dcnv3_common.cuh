@@ -179,18 +179,31 @@ struct Elem<__nv_bfloat16> {
 };
 
 // ---- fixed-point accumulation (order-independent => bitwise reproducible scatter) ----------------
-// Workspace header written by the amax pre-pass.
+// Workspace prefix shared by the generic and the tiled backward:
+//   [WsHeader, 256 B][per-image maxima: 2 x N unsigned, padded to 256 B]
+// The fixed-point scale of an image comes from the maximum |grad_out| of THAT image only, so an image's
+// grad_x never depends on what else is in the batch.  Maxima are kept as the bit pattern of |v| and compared
+// as unsigned integers: order independent, and NaN > Inf > every finite value, so a non-finite grad_out is
+// seen (and the image's grad_x becomes NaN) instead of being swallowed by fmaxf / float -> int conversion.
 struct WsHeader {
-    unsigned amax_go_bits;  // max |grad_out| as float bits
-    unsigned amax_m_bits;   // max |mask|     as float bits
-    unsigned pad[62];
+    unsigned done;      // tiled path: CTAs of the last kernel that have finished (reset by the last one)
+    unsigned pad[63];
 };
+struct ImgMax {
+    unsigned go_bits;   // max |grad_out| of the image, float bits
+    unsigned m_bits;    // max |mask| of the image (generic path, raw masks), float bits
+};
+__host__ __device__ __forceinline__ size_t img_max_bytes(int n) {
+    return ((size_t)n * sizeof(ImgMax) + 255) / 256 * 256;
+}
+__device__ __forceinline__ unsigned abs_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
+__device__ __forceinline__ bool bits_nonfinite(unsigned b) { return b >= 0x7f800000u; }
 
 // Exponent e such that every contribution |v| <= amax_go*amax_m maps to |v * 2^e| <= 2^46, leaving
 // 2^16 accumulations of headroom in an int64.
-__device__ __forceinline__ int fixed_exponent(const WsHeader* hd, bool mask_is_prob) {
-    const float a = __uint_as_float(hd->amax_go_bits);
-    const float m = mask_is_prob ? 1.0f : __uint_as_float(hd->amax_m_bits);
+__device__ __forceinline__ int fixed_exponent(const ImgMax& im, bool mask_is_prob) {
+    const float a = __uint_as_float(im.go_bits);
+    const float m = mask_is_prob ? 1.0f : __uint_as_float(im.m_bits);
     const float bound = a * m;
     if (!(bound > 0.0f) || !(bound < 3.0e38f)) return 0;
     int ex;
@@ -201,8 +214,8 @@ __device__ __forceinline__ int fixed_exponent(const WsHeader* hd, bool mask_is_p
 
 // frexp exponent of max|grad_out| (amax < 2^ex), clamped so that every derived power of two is a
 // normal float; 30 (=> unit scale) when the maximum is 0 or not finite.
-__device__ __forceinline__ int fixed_exponent_raw(const WsHeader* hd) {
-    const float a = __uint_as_float(hd->amax_go_bits);
+__device__ __forceinline__ int fixed_exponent_raw(unsigned go_bits) {
+    const float a = __uint_as_float(go_bits);
     if (!(a > 0.0f) || !(a < 3.0e38f)) return 30;
     int ex;
     frexpf(a, &ex);
@@ -212,7 +225,5 @@ __device__ __forceinline__ int fixed_exponent_raw(const WsHeader* hd) {
 __device__ __forceinline__ long long to_fixed(float v, int e) {
     return __float2ll_rn(ldexpf(v, e));  // exact scaling, exact conversion (24-bit mantissa)
 }
-
-
 
 }  // namespace dcnv3

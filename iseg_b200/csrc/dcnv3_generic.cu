@@ -91,34 +91,38 @@ fwd_generic_kernel(const T* __restrict__ x, const T* __restrict__ offset, const 
     }
 }
 
-// max |grad_out| and max |mask| -> workspace header (atomicMax on the float bit pattern of |v| is
-// order independent)
+// per image: max |grad_out| and max |mask| -> workspace (atomicMax on the bit pattern of |v| is order
+// independent and lets NaN / Inf through; dcnv3_common.cuh).  grid = (blocks per image, N).
 template <typename T>
 __global__ void __launch_bounds__(256)
 amax_kernel(const T* __restrict__ grad_out, size_t n_go, const T* __restrict__ mask, size_t n_m,
-            WsHeader* hd) {
-    float a = 0.f, b = 0.f;
+            ImgMax* __restrict__ img_max, int n_images) {
+  for (int n = blockIdx.y; n < n_images; n += gridDim.y) {
+    unsigned a = 0u, b = 0u;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const T* go = grad_out + (size_t)n * n_go;
+    const T* mk = mask + (size_t)n * n_m;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_go; i += stride)
-        a = fmaxf(a, fabsf(Elem<T>::ld(grad_out + i)));
+        a = max(a, abs_bits(Elem<T>::ld(go + i)));
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_m; i += stride)
-        b = fmaxf(b, fabsf(Elem<T>::ld(mask + i)));
+        b = max(b, abs_bits(Elem<T>::ld(mk + i)));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
-        b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+        a = max(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicMax(&hd->amax_go_bits, __float_as_uint(a));
-        atomicMax(&hd->amax_m_bits, __float_as_uint(b));
+        atomicMax(&img_max[n].go_bits, a);
+        atomicMax(&img_max[n].m_bits, b);
     }
+  }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(128)
 bwd_generic_kernel(const T* __restrict__ x, const T* __restrict__ offset, const T* __restrict__ mask,
                    const T* __restrict__ grad_out, T* __restrict__ grad_offset,
-                   T* __restrict__ grad_mask, const WsHeader* __restrict__ hd,
+                   T* __restrict__ grad_mask, const ImgMax* __restrict__ img_max,
                    unsigned long long* __restrict__ acc64, const KParams q) {
     const size_t total = (size_t)q.n * q.ho * q.wo * q.G;
     const size_t pg = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -129,7 +133,7 @@ bwd_generic_kernel(const T* __restrict__ x, const T* __restrict__ offset, const 
     const int h = (int)((pix / q.wo) % q.ho);
     const int n = (int)(pix / ((size_t)q.wo * q.ho));
     const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
-    const int e = fixed_exponent(hd, logits);
+    const int e = fixed_exponent(img_max[n], logits);  // the image's own scale: batch invariant
     float ref0, ref1;
     ref_point(q, h, w, ref0, ref1);
     const T* off = offset + pg * q.P * 2;
@@ -189,14 +193,22 @@ bwd_generic_kernel(const T* __restrict__ x, const T* __restrict__ offset, const 
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-fixed_to_float_kernel(long long* __restrict__ acc64, const WsHeader* __restrict__ hd,
-                      T* __restrict__ grad_x, size_t count, unsigned flags) {
-    const int e = fixed_exponent(hd, flags & DCNV3_FLAG_MASK_LOGITS);
+fixed_to_float_kernel(long long* __restrict__ acc64, const ImgMax* __restrict__ img_max,
+                      T* __restrict__ grad_x, size_t per_image, unsigned flags, int n_images) {
+  // grid = (blocks per image, min(N, 65535))
+  for (int n = blockIdx.y; n < n_images; n += gridDim.y) {
+    const ImgMax im = img_max[n];
+    const int e = fixed_exponent(im, flags & DCNV3_FLAG_MASK_LOGITS);
+    // a non-finite grad_out (or raw mask) cannot be represented in fixed point: the image's grad_x is NaN
+    const bool bad = bits_nonfinite(im.go_bits) || (!(flags & DCNV3_FLAG_MASK_LOGITS) && bits_nonfinite(im.m_bits));
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-        Elem<T>::st(grad_x + i, (float)ldexp((double)acc64[i], -e));
-        acc64[i] = 0;  // the workspace is left all-zero (DCNV3_FLAG_WORKSPACE_ZEROED contract, shared with the tiled path)
+    long long* a = acc64 + (size_t)n * per_image;
+    T* gx = grad_x + (size_t)n * per_image;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_image; i += stride) {
+        Elem<T>::st(gx + i, bad ? __int_as_float(0x7fc00000) : (float)ldexp((double)a[i], -e));
+        a[i] = 0;  // the workspace is left all-zero (DCNV3_FLAG_WORKSPACE_ZEROED contract, shared with the tiled path)
     }
+  }
 }
 
 // ---- launchers -----------------------------------------------------------------------------------
@@ -230,7 +242,7 @@ cudaError_t launch_fwd_generic(const void* x, const void* offset, const void* ma
 }
 
 size_t bwd_generic_workspace_bytes(const KParams& q) {
-    return sizeof(WsHeader) + sizeof(long long) * (size_t)q.n * q.h * q.w * q.G * q.gc;
+    return sizeof(WsHeader) + img_max_bytes(q.n) + sizeof(long long) * (size_t)q.n * q.h * q.w * q.G * q.gc;
 }
 
 template <typename T>
@@ -239,26 +251,32 @@ cudaError_t launch_bwd_generic_t(const void* x, const void* offset, const void* 
                                  void* grad_mask, void* ws, const KParams& q, bool ws_clean, cudaStream_t st) {
     const size_t n_x = (size_t)q.n * q.h * q.w * q.G * q.gc;
     const size_t pg = (size_t)q.n * q.ho * q.wo * q.G;
-    // (the header is rewritten by every call; the accumulators are re-zeroed by fixed_to_float_kernel)
-    cudaError_t err = cudaMemsetAsync(ws, 0, ws_clean ? sizeof(WsHeader) : bwd_generic_workspace_bytes(q), st);
-    if (err != cudaSuccess) return err;
-    WsHeader* hd = (WsHeader*)ws;
-    unsigned long long* acc = (unsigned long long*)((char*)ws + sizeof(WsHeader));
+    // (header and per-image maxima are rewritten by every call; the accumulators are re-zeroed by
+    //  fixed_to_float_kernel)
+    const size_t prefix = sizeof(WsHeader) + img_max_bytes(q.n);
+    cudaError_t err = cudaSuccess;
+    if (!ws_clean && (err = cudaMemsetAsync(ws, 0, bwd_generic_workspace_bytes(q), st)) != cudaSuccess) return err;
+    ImgMax* img_max = (ImgMax*)((char*)ws + sizeof(WsHeader));
+    unsigned long long* acc = (unsigned long long*)((char*)ws + prefix);
     if (pg > 0) {
-        const size_t n_go = pg * q.gc, n_m = pg * q.P;
-        const unsigned nb = (unsigned)min((size_t)148 * 8, (n_go + 255) / 256);
-        amax_kernel<T><<<nb, 256, 0, st>>>((const T*)grad_out, n_go, (const T*)mask,
-                                           (q.flags & DCNV3_FLAG_MASK_LOGITS) ? 0 : n_m, hd);
+        const size_t n_go = pg / q.n * q.gc, n_m = pg / q.n * q.P;  // per image
+        const unsigned nb = (unsigned)max((size_t)1, min((size_t)148 * 8 / q.n + 1, (n_go + 255) / 256));
+        amax_kernel<T><<<dim3(nb, min(q.n, 65535)), 256, 0, st>>>((const T*)grad_out, n_go, (const T*)mask,
+                                                                  (q.flags & DCNV3_FLAG_MASK_LOGITS) ? 0 : n_m, img_max, q.n);
         bwd_generic_kernel<T><<<blocks_for(pg, 128), 128, 0, st>>>(
             (const T*)x, (const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_offset,
-            (T*)grad_mask, hd, acc, q);
+            (T*)grad_mask, img_max, acc, q);
         count_launch(2);
     }
     if (n_x > 0) {
-        const unsigned nb = (unsigned)min((size_t)148 * 16, (n_x + 255) / 256);
-        fixed_to_float_kernel<T><<<nb, 256, 0, st>>>((long long*)acc, hd, (T*)grad_x, n_x, q.flags);
+        const size_t per_image = n_x / q.n;
+        const unsigned nb = (unsigned)max((size_t)1, min((size_t)148 * 16 / q.n + 1, (per_image + 255) / 256));
+        fixed_to_float_kernel<T><<<dim3(nb, min(q.n, 65535)), 256, 0, st>>>((long long*)acc, img_max, (T*)grad_x, per_image,
+                                                                            q.flags, q.n);
         count_launch(1);
     }
+    // leave the prefix (per-image maxima) zeroed as well: the workspace is all-zero between calls
+    if ((err = cudaMemsetAsync(ws, 0, prefix, st)) != cudaSuccess) return err;
     return cudaGetLastError();
 }
 

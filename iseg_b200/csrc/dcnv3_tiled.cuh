@@ -19,8 +19,9 @@ namespace dcnv3 {
 constexpr int kTaps = 9;
 constexpr int kGC = 16;
 constexpr int kCellBytes = 128;
-constexpr int kMaxBoxBytes = 82 * 1024;  // staged input box of the gather kernel; with the row staging slots two CTAs fit one SM
-constexpr int kFwdBoxBytes = 100 * 1024; // staged input box of the forward kernel (no staging slots): two CTAs per SM
+constexpr int kMaxBoxBytes = 82 * 1024;  // staged input box of the forward / gather kernels; with the per-warp side slots two CTAs fit one SM
+constexpr int kFwdBoxBytes = 100 * 1024; // forward box when the side inputs are not staged (no slots): two CTAs per SM
+constexpr int kTiledWarps = 8;           // warps per forward / gather CTA
 
 template <typename T>
 struct Chunk {
@@ -43,6 +44,29 @@ struct TileGeom {
 // host helpers implemented in dcnv3_tiled_fwd.cu
 TileGeom make_geom(const KParams& q, int dtype, int th, int tw, float reach, int max_cells);
 bool make_x_tensor_map(CUtensorMap* map, const void* x, const KParams& q, int dtype, int bw, int bh);
+// [N*Ho][Wo][G*per_group] view of offset / mask (and their gradients), box = one warp iteration of one chunk
+bool side_stageable(const KParams& q, int dtype);
+bool make_side_tensor_map(CUtensorMap* map, const void* base, const KParams& q, int dtype, int per_group);
+// raises a kernel's dynamic shared-memory limit once per (kernel, device); safe to call from any thread
+cudaError_t ensure_max_smem(const void* kernel, int bytes);
+
+// Launch with programmatic stream serialisation: the kernel may be scheduled while its predecessor in the
+// stream is still draining (its CTAs then wait in pdl_wait() before they touch global memory).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
+                                     cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 void gather_tiled_plan(const KParams& q, int dtype, int stage_bytes, int out[8]);
 
 // Nominal sampling position of output row h / column w (zero offset, centre tap), reference
@@ -95,6 +119,34 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+
+// 3-D tiled load / store of the per-pixel side tensors, viewed as [N*Ho rows][Wo][channels]: coordinates
+// (channel, w, row).  Loads zero-fill and stores drop whatever lies beyond Wo, so a row segment that is cut
+// by the right image edge needs no special casing.
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+// 8-byte asynchronous global -> shared copy (SASS LDGSTS)
+__device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores of this thread have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ---- programmatic dependent launch (sm_90+): the next kernel of the stream may start its prologue while
+//      this one drains; it must not touch global memory before pdl_wait() ------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- packed fp32 pairs: Blackwell issues two fp32 FMAs per instruction (PTX fma.rn.f32x2, SASS FFMA2) ----
 typedef unsigned long long f2;  // {lo, hi} = two consecutive channels
@@ -187,43 +239,74 @@ __device__ __forceinline__ void store_piece<__nv_bfloat16>(__nv_bfloat16* p, con
     *reinterpret_cast<uint4*>(p) = r;
 }
 
-// ---- per-warp row staging ------------------------------------------------------------------------
+// ---- per-warp side slot ---------------------------------------------------------------------------
 // A warp iteration works on PXW consecutive pixels of ONE output row (x GQ groups = 32 lanes).  Their
 // offsets / mask values are [pixel][GQ groups][18 | 9] runs of 144 / 72 contiguous bytes per pixel in
 // global memory (pixel stride G*18 / G*9 elements).  Letting every lane fetch its own 72+36 bytes makes
-// each load instruction touch ~40 cache lines; instead the warp copies the runs cooperatively
-// (consecutive lanes -> consecutive 16 / 8 bytes) into a private shared-memory slot and every lane then
-// reads its own values back with conflict-free LDS (lane stride 72 B for 8-byte loads, 36 B for 4-byte).
+// each load instruction touch ~18 cache lines (a third of the L1 data-pipe wavefronts of the round-1
+// kernels); instead the offsets arrive as one TMA box [PXW pixels][144 B] and the mask as 8-byte cp.async pieces, densely
+// in a private shared-memory slot, and every lane reads its own values back with conflict-free LDS (lane
+// stride 72 B for 8-byte loads, 36 B for 4-byte).  The gather kernel writes grad_offset / grad_mask over the
+// values it has consumed (identical layout) and hands the slot to a TMA store.
+// Needs 16-byte aligned offset runs and 8-byte aligned mask runs, i.e. G % GQ == 0 (side_stageable); other
+// group counts keep the per-lane loads and the cooperative store below.
 template <typename T>
 struct RowStage {
     using C = Chunk<T>;
     static constexpr int OFF_PX = C::GQ * 18 * (int)sizeof(T);  // 144 bytes per pixel
     static constexpr int MSK_PX = C::GQ * 9 * (int)sizeof(T);   // 72
-    static constexpr int VEC_PX = C::GQ * 16 * (int)sizeof(T);  // 128
     static constexpr int OFF_BYTES = C::PXW * OFF_PX;           // 2304 (fp32) / 1152 (bf16)
     static constexpr int MSK_BYTES = C::PXW * MSK_PX;           // 1152 / 576
-    static constexpr int BYTES = OFF_BYTES + MSK_BYTES;         // per warp
+    static constexpr int BYTES = (OFF_BYTES + MSK_BYTES + 127) / 128 * 128;  // per warp: 3456 / 1792 (TMA: 128-byte aligned)
     static constexpr int LANE_OFF = 18 * (int)sizeof(T);        // 72 / 36: a lane's own offsets
     static constexpr int LANE_MSK = 9 * (int)sizeof(T);         // 36 / 18
 
-    // off_row / msk_row point at the first pixel's run (element pointers); G = groups of the tensor
-    static __device__ __forceinline__ void load(unsigned char* st, const T* off_row, const T* msk_row, int G,
-                                                int npx, int lane) {
+    // Fill the slot with the side inputs of the PXW pixels starting at column w of row `row` (= n*Ho + h):
+    // lane 0 asks the TMA unit for the offsets box (arrives on `bar`); the mask runs are 72 bytes per pixel --
+    // not a legal TMA box width -- and travel as 8-byte cp.async pieces, consecutive lanes taking consecutive
+    // pieces (completion: cp_async_wait_all + __syncwarp).  msk_row = first pixel's run of this chunk.
+    static __device__ __forceinline__ void request(unsigned char* st, uint64_t* bar, const CUtensorMap* offmap,
+                                                   const T* msk_row, int G, int chunk, int w, int row, int npx,
+                                                   int lane) {
+        if (lane == 0) {
+            mbar_expect_tx(bar, (uint32_t)OFF_BYTES);
+            tma_load_3d(st, offmap, bar, chunk * C::GQ * 18, w, row);
+        }
         const int n = npx * 9;
-        const size_t off_stride = (size_t)G * 18 * sizeof(T), msk_stride = (size_t)G * 9 * sizeof(T);
+        const size_t msk_stride = (size_t)G * 9 * sizeof(T);
 #pragma unroll
         for (int i = 0; i < (C::PXW * 9 + 31) / 32; ++i) {
             const int c = lane + 32 * i;
             if (c < n) {
                 const int px = (c * 7282) >> 16, r = c - px * 9;  // c / 9 for c < 288
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(
-                                          reinterpret_cast<const unsigned char*>(off_row) + px * off_stride) + r);
-                *reinterpret_cast<uint4*>(st + px * OFF_PX + r * 16) = v;
-                const uint2 u = __ldg(reinterpret_cast<const uint2*>(
-                                          reinterpret_cast<const unsigned char*>(msk_row) + px * msk_stride) + r);
-                *reinterpret_cast<uint2*>(st + OFF_BYTES + px * MSK_PX + r * 8) = u;
+                cp_async_8(st + OFF_BYTES + px * MSK_PX + r * 8,
+                           reinterpret_cast<const unsigned char*>(msk_row) + px * msk_stride + r * 8);
             }
         }
+    }
+    // results written over the consumed inputs: grad_offset leaves through a TMA store (one lane; returns once
+    // the slot may be overwritten), grad_mask through 8-byte pieces, consecutive lanes -> consecutive pieces
+    static __device__ __forceinline__ void store_results(const unsigned char* st, const CUtensorMap* goffmap,
+                                                         T* gmsk_row, int G, int chunk, int w, int row, int npx,
+                                                         int lane) {
+        fence_proxy_async();  // this lane's generic-proxy writes -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_3d(goffmap, st, chunk * C::GQ * 18, w, row);
+            bulk_commit();
+        }
+        const int n = npx * 9;
+        const size_t msk_stride = (size_t)G * 9 * sizeof(T);
+#pragma unroll
+        for (int i = 0; i < (C::PXW * 9 + 31) / 32; ++i) {
+            const int c = lane + 32 * i;
+            if (c < n) {
+                const int px = (c * 7282) >> 16, r = c - px * 9;
+                *(reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(gmsk_row) + px * msk_stride) + r) =
+                    *reinterpret_cast<const uint2*>(st + OFF_BYTES + px * MSK_PX + r * 8);
+            }
+        }
+        if (lane == 0) bulk_wait_read();
         __syncwarp();
     }
     // the lane's tap p
@@ -239,23 +322,22 @@ struct RowStage {
             ml = __uint_as_float((unsigned)*reinterpret_cast<const unsigned short*>(st + OFF_BYTES + lane * LANE_MSK + p * 2) << 16);
         }
     }
+    static __device__ __forceinline__ float mask_at(const unsigned char* st, int lane, int p) {
+        if (sizeof(T) == 4) return *reinterpret_cast<const float*>(st + OFF_BYTES + lane * LANE_MSK + p * 4);
+        return __uint_as_float((unsigned)*reinterpret_cast<const unsigned short*>(st + OFF_BYTES + lane * LANE_MSK + p * 2) << 16);
+    }
+    // softmax over the lane's 9 staged logits (dcn_v3.py:120-123): max and 1/sum
     static __device__ __forceinline__ void softmax_stats(const unsigned char* st, int lane, float& mx, float& inv_sum) {
-        float v[kTaps];
+        mx = -INFINITY;
 #pragma unroll
-        for (int p = 0; p < kTaps; ++p) {
-            float a, b;
-            tap(st, lane, p, a, b, v[p]);
-        }
-        mx = v[0];
-#pragma unroll
-        for (int p = 1; p < kTaps; ++p) mx = fmaxf(mx, v[p]);
+        for (int p = 0; p < kTaps; ++p) mx = fmaxf(mx, mask_at(st, lane, p));
         float s = 0.f;
 #pragma unroll
-        for (int p = 0; p < kTaps; ++p) s += expf(v[p] - mx);
+        for (int p = 0; p < kTaps; ++p) s += expf(mask_at(st, lane, p) - mx);
         inv_sum = 1.0f / s;
     }
     // cooperative, coalesced store of staged offset-shaped (144 B / pixel) and mask-shaped (72 B / pixel)
-    // results, e.g. grad_offset / grad_mask
+    // results, e.g. grad_offset / grad_mask (group counts the TMA store cannot serve)
     static __device__ __forceinline__ void store_off_msk(const unsigned char* st, T* off_row, T* msk_row, int G,
                                                          int npx, int ng, int lane) {
         __syncwarp();
@@ -289,21 +371,6 @@ struct RowStage {
             }
         }
         __syncwarp();
-    }
-    // cooperative, coalesced store of the warp's [pixel][GQ][16] result slab staged at st (128 B / pixel)
-    static __device__ __forceinline__ void store_vec(const unsigned char* st, T* dst_row, int G, int npx, int lane) {
-        __syncwarp();
-        const int n = npx * 8;
-        const size_t stride = (size_t)G * 16 * sizeof(T);
-#pragma unroll
-        for (int i = 0; i < C::PXW * 8 / 32; ++i) {
-            const int c = lane + 32 * i;
-            if (c < n) {
-                const int px = c >> 3, r = c & 7;
-                *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(dst_row) + px * stride + r * 16) =
-                    *reinterpret_cast<const uint4*>(st + px * VEC_PX + r * 16);
-            }
-        }
     }
 };
 

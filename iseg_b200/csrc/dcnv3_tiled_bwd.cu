@@ -67,6 +67,7 @@ struct BwdGeom {
 
 struct FarWs {
     WsHeader* hd;
+    ImgMax* img_max;              // [N]  per-image max |grad_out| (bit pattern), written by the gather kernel
     unsigned char* dirty;         // [N][H][W][G]  (pixel, group) has side-buffer contributions
     int* redo;                    // [N][chunks][tiles_y][tiles_x]  scatter CTA found hot cells
     unsigned long long* acc64;    // [N][H][W][C] fixed point, zero outside a call
@@ -125,6 +126,24 @@ __device__ __forceinline__ const T* global_slab_b(const T* x, const KParams& q, 
 // per-warp staging bytes of the gather kernel: results + (bf16 only) a separate fp32 park
 template <typename T>
 constexpr int kGatherStageBytes = RowStage<T>::BYTES + (sizeof(T) == 4 ? 0 : 32 * kTaps * 4);
+static_assert(kGatherStageBytes<float> % 128 == 0 && kGatherStageBytes<__nv_bfloat16> % 128 == 0, "TMA slots are 128-byte aligned");
+
+// The kernel that runs last in a backward call leaves the workspace prefix zeroed for the next call: its
+// last CTA to finish clears the per-image maxima and the counter itself (the launch needs no memset node,
+// which would break the programmatic-launch chain).
+__device__ __forceinline__ void finalize_workspace(const FarWs& ws, int n_images) {
+    __shared__ bool s_last;
+    __syncthreads();  // every thread of this CTA is done reading the maxima
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&ws.hd->done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    unsigned* m = reinterpret_cast<unsigned*>(ws.img_max);
+    for (int i = threadIdx.x; i < 2 * n_images; i += blockDim.x) m[i] = 0u;
+    if (threadIdx.x == 0) ws.hd->done = 0u;
+}
 
 // grad_out of one (pixel, group) in fixed point: G[c] = round(go[c] * 2^eg)
 // ... XOR-permuted by the lane's pixel index: G[c] holds channel c ^ rot.  At step c every lane updates
@@ -165,16 +184,19 @@ __device__ __forceinline__ void load_fixed_point_go(const T* go, float sg, int r
 // =====================================================================================================
 // grad_offset / grad_mask
 // =====================================================================================================
-template <typename T>
-__global__ void __launch_bounds__(256, 2)
-bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict__ x,
+template <typename T, bool STAGED>
+__global__ void __launch_bounds__(kTiledWarps * 32, 2)
+bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap offmap,
+                  const __grid_constant__ CUtensorMap goffmap, const T* __restrict__ x,
                   const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
-                  T* __restrict__ grad_offset, T* __restrict__ grad_mask, WsHeader* __restrict__ hd, const KParams q,
+                  T* __restrict__ grad_offset, T* __restrict__ grad_mask, ImgMax* __restrict__ img_max, const KParams q,
                   const TileGeom tg) {
     using C = Chunk<T>;
     using RS = RowStage<T>;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t sbar[kTiledWarps];
+    pdl_launch_dependents();
 
     int b = blockIdx.x;
     const int tx = b % tg.tiles_w; b /= tg.tiles_w;
@@ -188,32 +210,45 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict_
 
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
+#pragma unroll
+        for (int i = 0; i < kTiledWarps; ++i) mbar_init(&sbar[i], 1);
         fence_mbar_init();
     }
     __syncthreads();
+    pdl_wait();
     if (threadIdx.x == 0) {
         mbar_expect_tx(&bar, (uint32_t)(tg.bw * tg.bh * kCellBytes));
         tma_load_4d(smem, &xmap, &bar, chunk * C::GQ * kGC, cx0 - q.pw, cy0 - q.ph, n);
     }
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g_l = lane % C::GQ, px_l = lane / C::GQ;
     const int g = min(chunk * C::GQ + g_l, q.G - 1);  // phantom groups of a trailing chunk shadow the last one
     const int ng = min(C::GQ, q.G - chunk * C::GQ);   // real groups in this chunk
     const int rot = Slab<T>::rot_of(px_l);
     const unsigned char* sbase = smem + g_l * (kGC * (int)sizeof(T));
-    // per-warp staging slot for the results (stored coalesced once per row segment) and, for the fused
-    // soft-max path, an fp32 park for dL/dm_p (it aliases the mask slot when T is fp32)
+    // The warp's slot: side inputs in (STAGED), results out -- every result overwrites the input value of the
+    // same tap (identical layout), and the slot is stored once per row segment.  For the fused soft-max path an
+    // fp32 park holds dL/dm_p (it aliases the mask part when T is fp32).
     unsigned char* st = smem + (size_t)tg.bw * tg.bh * kCellBytes + warp * kGatherStageBytes<T>;
     float* park = sizeof(T) == 4 ? reinterpret_cast<float*>(st + RS::OFF_BYTES)
                                  : reinterpret_cast<float*>(st + RS::BYTES);
     const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
-    const int colblocks = (tw + C::PXW - 1) / C::PXW;
+    const int colblocks = (tw + C::PXW - 1) / C::PXW, nit = th * colblocks;
     bool waited = false;
-    float amax = 0.f;  // max |grad_out| seen by this thread: the fixed-point scale of the scatter kernel
+    uint32_t sphase = 0;
+    unsigned amax = 0u;  // max |grad_out| bits seen by this thread: the fixed-point scale of the scatter kernel
+
+    auto request = [&](int it) {
+        const int h = h0 + it / colblocks, wb = w0 + (it % colblocks) * C::PXW;
+        const size_t pix0 = ((size_t)n * q.ho + h) * q.wo + wb;
+        RS::request(st, &sbar[warp], &offmap, mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, chunk, wb, n * q.ho + h,
+                    min(C::PXW, w0 + tw - wb), lane);
+    };
+    if (STAGED && warp < nit) request(warp);
 
     // one warp iteration = PXW consecutive pixels of one output row
-    for (int it = warp; it < th * colblocks; it += nwarps) {
+    for (int it = warp; it < nit; it += kTiledWarps) {
         const int h = h0 + it / colblocks, wb = w0 + (it % colblocks) * C::PXW;
         const int npx = min(C::PXW, w0 + tw - wb);
         const int w = wb + min(px_l, npx - 1);  // idle lanes shadow the last pixel (their slots are never stored)
@@ -225,13 +260,26 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict_
 #pragma unroll
         for (int pc = 0; pc < C::NPIECE; ++pc)
             load_piece<T>(grad_out + pg * kGC + Slab<T>::chan_of(pc, rot), go + pc * C::PAIRS);
-        float mx = 0.f, inv_sum = 1.f;
-        if (logits) softmax_stats9<T>(mskp, mx, inv_sum);
         float ref0, ref1;
         ref_point(q, h, w, ref0, ref1);
-        float ox, oy, ml, ox2, oy2, ml2;
-        load_tap_inputs<T>(offp, mskp, 0, ox, oy, ml);
-        load_tap_inputs<T>(offp, mskp, 1, ox2, oy2, ml2);
+        if (STAGED) {
+            cp_async_wait_all();
+            __syncwarp();
+            mbar_wait(&sbar[warp], sphase);
+            sphase ^= 1;
+        }
+        float mx = 0.f, inv_sum = 1.f;
+        if (logits) {
+            if (STAGED) RS::softmax_stats(st, lane, mx, inv_sum);
+            else softmax_stats9<T>(mskp, mx, inv_sum);
+        }
+        float ox, oy, ml, ox2 = 0.f, oy2 = 0.f, ml2 = 0.f;
+        if (STAGED) {
+            RS::tap(st, lane, 0, ox, oy, ml);
+        } else {
+            load_tap_inputs<T>(offp, mskp, 0, ox, oy, ml);
+            load_tap_inputs<T>(offp, mskp, 1, ox2, oy2, ml2);
+        }
         if (!waited) {
             mbar_wait(&bar, 0);
             waited = true;
@@ -240,8 +288,12 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict_
 #pragma unroll 1
         for (int p = 0; p < kTaps; ++p) {
             const float cx = ox, cy = oy, cm = ml;
-            ox = ox2; oy = oy2; ml = ml2;
-            if (p + 2 < kTaps) load_tap_inputs<T>(offp, mskp, p + 2, ox2, oy2, ml2);  // two taps ahead
+            if (STAGED) {
+                if (p + 1 < kTaps) RS::tap(st, lane, p + 1, ox, oy, ml);  // (read before tap p's results land)
+            } else {
+                ox = ox2; oy = oy2; ml = ml2;
+                if (p + 2 < kTaps) load_tap_inputs<T>(offp, mskp, p + 2, ox2, oy2, ml2);  // two taps ahead
+            }
             const Tap t = make_tap(q, ref0, ref1, p, cx, cy);
             const int bx = t.x0 - cx0, by = t.y0 - cy0;
             const bool inbox = bx >= 0 && bx + 1 < tg.bw && by >= 0 && by + 1 < tg.bh;
@@ -288,7 +340,7 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict_
             const float gxq = mm * (t.dy1 * (d2 - d0) + t.dy0 * (d3 - d1));
             const float gyq = mm * (t.dx1 * (d1 - d0) + t.dx0 * (d3 - d2));
             gm_dot_m += g_m * mm;
-            // results go to the lane's staging slot (lane stride 72 / 36 bytes: conflict free)
+            // results go to the lane's slot positions (lane stride 72 / 36 bytes: conflict free)
             if (sizeof(T) == 4) {
                 *reinterpret_cast<float2*>(st + lane * RS::LANE_OFF + p * 8) = make_float2(gxq * q.fx, gyq * q.fy);
             } else {
@@ -300,24 +352,33 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict_
         // (max |grad_out| is taken here, after the taps: the first use of the freshly loaded grad_out is then
         //  the first tap's dot products, behind its coordinate arithmetic and shared-memory loads)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) amax = fmaxf(amax, fmaxf(fabsf(lo_of(go[c])), fabsf(hi_of(go[c]))));
+        for (int c = 0; c < 8; ++c) amax = max(amax, max(abs_bits(lo_of(go[c])), abs_bits(hi_of(go[c]))));
         if (logits) {
-            // softmax Jacobian needs sum_p m_p*dL/dm_p: second sweep over this lane's own 9 values
+            // softmax Jacobian needs sum_p m_p*dL/dm_p: second sweep over this lane's own 9 values.  The logits
+            // are still in the slot when T is bf16 (the park is a separate area); for fp32 the park has
+            // overwritten them and they are read again from global memory (L1 / L2 hits)
 #pragma unroll 1
             for (int p = 0; p < kTaps; ++p) {
-                const float mm = expf(Elem<T>::ld(mskp + p) - mx) * inv_sum;
+                const float lg = (STAGED && sizeof(T) == 2) ? RS::mask_at(st, lane, p) : Elem<T>::ld(mskp + p);
+                const float mm = expf(lg - mx) * inv_sum;
                 const float v = mm * (park[lane * kTaps + p] - gm_dot_m);
                 if (sizeof(T) == 4) park[lane * kTaps + p] = v;
                 else *reinterpret_cast<__nv_bfloat16*>(st + RS::OFF_BYTES + lane * RS::LANE_MSK + p * 2) = __float2bfloat16_rn(v);
             }
         }
-        RS::store_off_msk(st, grad_offset + (pix0 * q.G + chunk * C::GQ) * 18,
-                          grad_mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, npx, ng, lane);
+        if (STAGED) {
+            RS::store_results(st, &goffmap, grad_mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, chunk, wb, n * q.ho + h,
+                              npx, lane);
+            if (it + kTiledWarps < nit) request(it + kTiledWarps);  // the slot is free again
+        } else {
+            RS::store_off_msk(st, grad_offset + (pix0 * q.G + chunk * C::GQ) * 18,
+                              grad_mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, npx, ng, lane);
+        }
     }
     if (!waited) mbar_wait(&bar, 0);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    if (lane == 0) atomicMax(&hd->amax_go_bits, __float_as_uint(amax));
+    for (int o = 16; o > 0; o >>= 1) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0) atomicMax(&img_max[n].go_bits, amax);
 }
 
 // =====================================================================================================
@@ -532,15 +593,21 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
     const int n = b / bg.chunks;
     const TileBox box = make_box(q, bg, jx, jy);
 
+    pdl_launch_dependents();
+    // prologue without global memory traffic (overlaps the tail of the gather kernel): home ranges, zeroed box
     if (threadIdx.x < 2) tile_ranges(q, bg, jx, jy, s_home_h, s_home_w);
-    const int eg = 30 - fixed_exponent_raw(ws.hd);
     {
         int2* z = reinterpret_cast<int2*>(acc);  // both parts have an even number of ints
         for (int i = threadIdx.x; i < (acc_ints + (bg.box_rows + 1) * WP * kSG) / 2; i += blockDim.x)
             z[i] = make_int2(0, 0);
     }
     __syncthreads();
-    scatter_walk<T, 0, TJ>(acc, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+    pdl_wait();  // the gather kernel has left the image's max |grad_out| in the workspace
+    const unsigned go_bits = ws.img_max[n].go_bits;
+    const bool nonfinite = bits_nonfinite(go_bits);  // NaN / Inf in this image's grad_out: its grad_x is NaN
+    const int eg = 30 - fixed_exponent_raw(go_bits);
+    if (!nonfinite)
+        scatter_walk<T, 0, TJ>(acc, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
     __syncthreads();
 
     // ---- flush: the cells of J are written exactly once; ring cells go to the side buffer ----
@@ -564,8 +631,9 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
         const size_t gpix = (size_t)n * img_pixels + (size_t)(ay * q.w + ax);
         if ((unsigned)(ax - box.ux0) < (unsigned)box.tjw && (unsigned)(ay - box.uy0) < (unsigned)box.tjh) {
             const size_t gidx = gpix * ((size_t)q.G * kGC) + (size_t)(chunk * kSCell + piece * 4);
-            const float f0 = hot ? 0.f : (float)v.x * inv_s, f1 = hot ? 0.f : (float)v.y * inv_s;
-            const float f2_ = hot ? 0.f : (float)v.z * inv_s, f3 = hot ? 0.f : (float)v.w * inv_s;
+            const float qnan = __int_as_float(0x7fc00000);
+            const float f0 = nonfinite ? qnan : hot ? 0.f : (float)v.x * inv_s, f1 = nonfinite ? qnan : hot ? 0.f : (float)v.y * inv_s;
+            const float f2_ = nonfinite ? qnan : hot ? 0.f : (float)v.z * inv_s, f3 = nonfinite ? qnan : hot ? 0.f : (float)v.w * inv_s;
             if (sizeof(T) == 4) {
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(grad_x) + gidx) = make_float4(f0, f1, f2_, f3);
             } else {
@@ -593,48 +661,53 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
 template <typename T, int TJ>
 __global__ void __launch_bounds__(256)
 redo_hot_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
-                T* __restrict__ grad_x, const FarWs ws, const KParams q, const BwdGeom bg) {
-    if (ws.redo[blockIdx.x] == 0) return;
+                T* __restrict__ grad_x, const FarWs ws, const KParams q, const BwdGeom bg, const int is_last) {
     constexpr int WP = ScatterShape<TJ>::WPITCH;
     extern __shared__ __align__(16) int wsum[];  // [box_rows + 1][WP][kSG]
     __shared__ Range s_home_h, s_home_w;
-    int b = blockIdx.x;
-    const int jx = b % bg.tiles_x; b /= bg.tiles_x;
-    const int jy = b % bg.tiles_y; b /= bg.tiles_y;
-    const int chunk = b % bg.chunks;
-    const int n = b / bg.chunks;
-    const TileBox box = make_box(q, bg, jx, jy);
-    if (threadIdx.x < 2) tile_ranges(q, bg, jx, jy, s_home_h, s_home_w);
-    for (int i = threadIdx.x; i < (bg.box_rows + 1) * WP * kSG; i += blockDim.x) wsum[i] = 0;
-    __syncthreads();
-    const int eg = 30 - fixed_exponent_raw(ws.hd);
-    scatter_walk<T, 1, TJ>(nullptr, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
-    __syncthreads();
-    scatter_walk<T, 2, TJ>(nullptr, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
-    __syncthreads();
-    if (threadIdx.x == 0) ws.redo[blockIdx.x] = 0;
-    if (bg.tiles_x * bg.tiles_y != 1) return;  // merge_far_kernel folds the side buffer into grad_x
-    // The tile is the whole image: nobody else contributes to its cells (no ring, no far landings), so
-    // there is no merge launch and this CTA converts its hot cells itself.
-    __threadfence();
-    __syncthreads();
-    constexpr int PITCH = ScatterShape<TJ>::PITCH;
-    const size_t img_pixels = (size_t)q.h * q.w;
-    const double inv_d = ldexp(1.0, -(eg + kWShift - 32));
-    for (int i = threadIdx.x; i < box.bh * (PITCH * kSCell); i += blockDim.x) {
-        const int cy = i / (PITCH * kSCell), r = i - cy * (PITCH * kSCell);
-        const int cx = r / kSCell, ch = r % kSCell, gl = ch / kGC;
-        const int ax = box.bx0 + cx, ay = box.by0 + cy, g = chunk * kSG + gl;
-        if (cx >= box.bw || ax < 0 || ax >= q.w || ay < 0 || ay >= q.h || g >= q.G) continue;
-        if (!cell_is_hot<WP>(wsum, cy, cx, gl)) continue;
-        const size_t cellg = ((size_t)n * img_pixels + (size_t)(ay * q.w + ax)) * q.G + g;
-        const size_t idx = cellg * kGC + ch % kGC;
-        const long long v = (long long)__ldcg(ws.acc64 + idx);
-        // |v| can exceed 2^24: go through double so that the exact total is rounded once
-        Elem<T>::st(grad_x + idx, (float)((double)v * inv_d));
-        ws.acc64[idx] = 0ull;
-        ws.dirty[cellg] = 0;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (ws.redo[blockIdx.x] != 0) {  // (uniform per CTA)
+        int b = blockIdx.x;
+        const int jx = b % bg.tiles_x; b /= bg.tiles_x;
+        const int jy = b % bg.tiles_y; b /= bg.tiles_y;
+        const int chunk = b % bg.chunks;
+        const int n = b / bg.chunks;
+        const TileBox box = make_box(q, bg, jx, jy);
+        if (threadIdx.x < 2) tile_ranges(q, bg, jx, jy, s_home_h, s_home_w);
+        for (int i = threadIdx.x; i < (bg.box_rows + 1) * WP * kSG; i += blockDim.x) wsum[i] = 0;
+        __syncthreads();
+        const int eg = 30 - fixed_exponent_raw(ws.img_max[n].go_bits);
+        scatter_walk<T, 1, TJ>(nullptr, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+        __syncthreads();
+        scatter_walk<T, 2, TJ>(nullptr, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+        __syncthreads();
+        if (threadIdx.x == 0) ws.redo[blockIdx.x] = 0;
+        if (bg.tiles_x * bg.tiles_y == 1) {  // (otherwise merge_far_kernel folds the side buffer into grad_x)
+            // The tile is the whole image: nobody else contributes to its cells (no ring, no far landings), so
+            // there is no merge launch and this CTA converts its hot cells itself.
+            __threadfence();
+            __syncthreads();
+            constexpr int PITCH = ScatterShape<TJ>::PITCH;
+            const size_t img_pixels = (size_t)q.h * q.w;
+            const double inv_d = ldexp(1.0, -(eg + kWShift - 32));
+            for (int i = threadIdx.x; i < box.bh * (PITCH * kSCell); i += blockDim.x) {
+                const int cy = i / (PITCH * kSCell), r = i - cy * (PITCH * kSCell);
+                const int cx = r / kSCell, ch = r % kSCell, gl = ch / kGC;
+                const int ax = box.bx0 + cx, ay = box.by0 + cy, g = chunk * kSG + gl;
+                if (cx >= box.bw || ax < 0 || ax >= q.w || ay < 0 || ay >= q.h || g >= q.G) continue;
+                if (!cell_is_hot<WP>(wsum, cy, cx, gl)) continue;
+                const size_t cellg = ((size_t)n * img_pixels + (size_t)(ay * q.w + ax)) * q.G + g;
+                const size_t idx = cellg * kGC + ch % kGC;
+                const long long v = (long long)__ldcg(ws.acc64 + idx);
+                // |v| can exceed 2^24: go through double so that the exact total is rounded once
+                Elem<T>::st(grad_x + idx, (float)((double)v * inv_d));
+                ws.acc64[idx] = 0ull;
+                ws.dirty[cellg] = 0;
+            }
+        }
     }
+    if (is_last) finalize_workspace(ws, q.n);
 }
 
 // grad_x += side buffer for the (pixel, group)s flagged in the dirty map; leaves the side buffer and
@@ -643,33 +716,40 @@ redo_hot_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const 
 template <typename T>
 __global__ void __launch_bounds__(256)
 merge_far_kernel(T* __restrict__ grad_x, const FarWs ws, const KParams q, size_t count) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const size_t base = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) - lane;
     const size_t e = base + lane;
     const unsigned char flag = e < count ? ws.dirty[e] : (unsigned char)0;  // map is padded to 256 bytes
     const unsigned m = __ballot_sync(0xffffffffu, flag != 0);
-    if (m == 0) return;
-    const double inv_s = ldexp(1.0, -(30 - fixed_exponent_raw(ws.hd) + kWShift - 32));
-    const int nset = __popc(m);
-    for (int k0 = 0; k0 < nset; k0 += 8) {
-        const int k = k0 + (lane >> 2);
-        if (k < nset) {
-            const size_t idx = (base + __fns(m, 0, k + 1)) * kGC + (lane & 3) * 4;
-            longlong4 v;
-            const longlong2 v01 = *reinterpret_cast<const longlong2*>(ws.acc64 + idx);
-            const longlong2 v23 = *reinterpret_cast<const longlong2*>(ws.acc64 + idx + 2);
-            v.x = v01.x; v.y = v01.y; v.z = v23.x; v.w = v23.y;
-            // |v| can exceed 2^24: go through double so that the exact total is rounded once
-            const float a0 = (float)((double)v.x * inv_s), a1 = (float)((double)v.y * inv_s);
-            const float a2 = (float)((double)v.z * inv_s), a3 = (float)((double)v.w * inv_s);
-            float4 gx = Elem<T>::ld4_plain(grad_x + idx);
-            gx.x += a0; gx.y += a1; gx.z += a2; gx.w += a3;
-            Elem<T>::st4(grad_x + idx, gx);
-            *reinterpret_cast<ulonglong2*>(ws.acc64 + idx) = make_ulonglong2(0ull, 0ull);
-            *reinterpret_cast<ulonglong2*>(ws.acc64 + idx + 2) = make_ulonglong2(0ull, 0ull);
+    if (m != 0) {
+        const size_t per_image = (size_t)q.h * q.w * q.G;  // (pixel, group) entries of one image
+        const int nset = __popc(m);
+        for (int k0 = 0; k0 < nset; k0 += 8) {
+            const int k = k0 + (lane >> 2);
+            if (k < nset) {
+                const size_t ent = base + __fns(m, 0, k + 1);
+                const size_t idx = ent * kGC + (lane & 3) * 4;
+                // the image's own fixed-point scale (a warp's 32 entries may straddle two images)
+                const double inv_s = ldexp(1.0, -(30 - fixed_exponent_raw(ws.img_max[ent / per_image].go_bits) + kWShift - 32));
+                longlong4 v;
+                const longlong2 v01 = *reinterpret_cast<const longlong2*>(ws.acc64 + idx);
+                const longlong2 v23 = *reinterpret_cast<const longlong2*>(ws.acc64 + idx + 2);
+                v.x = v01.x; v.y = v01.y; v.z = v23.x; v.w = v23.y;
+                // |v| can exceed 2^24: go through double so that the exact total is rounded once
+                const float a0 = (float)((double)v.x * inv_s), a1 = (float)((double)v.y * inv_s);
+                const float a2 = (float)((double)v.z * inv_s), a3 = (float)((double)v.w * inv_s);
+                float4 gx = Elem<T>::ld4_plain(grad_x + idx);
+                gx.x += a0; gx.y += a1; gx.z += a2; gx.w += a3;
+                Elem<T>::st4(grad_x + idx, gx);
+                *reinterpret_cast<ulonglong2*>(ws.acc64 + idx) = make_ulonglong2(0ull, 0ull);
+                *reinterpret_cast<ulonglong2*>(ws.acc64 + idx + 2) = make_ulonglong2(0ull, 0ull);
+            }
         }
+        if (flag != 0) ws.dirty[e] = 0;
     }
-    if (flag != 0) ws.dirty[e] = 0;
+    finalize_workspace(ws, q.n);  // always the last kernel of a call when it is launched
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -708,7 +788,7 @@ static size_t dirty_bytes(const KParams& q) { return ((size_t)q.n * q.h * q.w * 
 size_t bwd_tiled_workspace_bytes(const KParams& q) {
     const size_t tiles = (size_t)q.n * ((q.w + 15) / 16) * ((q.h + 15) / 16);  // upper bound (16x16 tiles)
     const size_t chunks = (size_t)(q.G + 1) / 2;
-    return sizeof(WsHeader) + dirty_bytes(q) + flag_bytes(tiles * chunks) +
+    return sizeof(WsHeader) + img_max_bytes(q.n) + dirty_bytes(q) + flag_bytes(tiles * chunks) +
            sizeof(long long) * (size_t)q.n * q.h * q.w * q.G * q.gc;
 }
 
@@ -721,24 +801,33 @@ static size_t scatter_smem_bytes(int rows) {
 
 template <typename T, int TJ>
 static cudaError_t launch_scatter(const T* offset, const T* mask, const T* grad_out, T* grad_x, const FarWs& ws,
-                                  const KParams& q, const BwdGeom& bg, unsigned grid, cudaStream_t st) {
+                                  const KParams& q, const BwdGeom& bg, unsigned grid, bool redo_is_last, cudaStream_t st) {
     using S = ScatterShape<TJ>;
     const size_t smem = scatter_smem_bytes<TJ>(bg.box_rows);
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(bwd_scatter_kernel<T, TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)scatter_smem_bytes<TJ>(S::PITCH));
-        if (e != cudaSuccess) return e;
-        attr_set[dev & 63] = true;
-    }
+    cudaError_t e = ensure_max_smem((const void*)bwd_scatter_kernel<T, TJ>, (int)scatter_smem_bytes<TJ>(S::PITCH));
+    if (e != cudaSuccess) return e;
     KernelTiming& kt = kernel_timing();
-    bwd_scatter_kernel<T, TJ><<<grid, S::THREADS, smem, st>>>(offset, mask, grad_out, grad_x, ws, q, bg);
+    e = launch_pdl(bwd_scatter_kernel<T, TJ>, grid, S::THREADS, smem, st, offset, mask, grad_out, grad_x, ws, q, bg);
+    if (e != cudaSuccess) return e;
     if (kt.enabled) cudaEventRecord(kt.ev[2], st);
-    redo_hot_kernel<T, TJ><<<grid, 256, (size_t)(bg.box_rows + 1) * S::WPITCH * kSG * sizeof(int), st>>>(
-        offset, mask, grad_out, grad_x, ws, q, bg);
-    return cudaSuccess;
+    return launch_pdl(redo_hot_kernel<T, TJ>, grid, 256, (size_t)(bg.box_rows + 1) * S::WPITCH * kSG * sizeof(int), st,
+                      offset, mask, grad_out, grad_x, ws, q, bg, (int)redo_is_last);
+}
+
+template <typename T, bool STAGED>
+static cudaError_t launch_gather_variant(const CUtensorMap& map, const CUtensorMap& offmap, const CUtensorMap& goffmap,
+                                         const void* x, const void* offset, const void* mask, const void* grad_out,
+                                         void* grad_offset, void* grad_mask, ImgMax* img_max, const KParams& q,
+                                         const TileGeom& tg, cudaStream_t st) {
+    cudaError_t e = ensure_max_smem((const void*)bwd_gather_kernel<T, STAGED>,
+                                    kMaxBoxBytes + kTiledWarps * kGatherStageBytes<T>);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((size_t)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
+    // (also leaves the per-image max |grad_out| in the workspace: the fixed-point scale of the scatter kernel)
+    return launch_pdl(bwd_gather_kernel<T, STAGED>, grid, kTiledWarps * 32,
+                      (size_t)tg.bw * tg.bh * kCellBytes + kTiledWarps * kGatherStageBytes<T>, st, map, offmap, goffmap,
+                      (const T*)x, (const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_offset, (T*)grad_mask,
+                      img_max, q, tg);
 }
 
 template <typename T>
@@ -751,51 +840,51 @@ static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const v
     const size_t chunks_ub = (size_t)(q.G + 1) / 2;
     FarWs ws;
     char* base = (char*)wsp;
-    ws.hd = (WsHeader*)base;
-    ws.dirty = (unsigned char*)(base + sizeof(WsHeader));
-    ws.redo = (int*)(base + sizeof(WsHeader) + dirty_bytes(q));
-    ws.acc64 = (unsigned long long*)(base + sizeof(WsHeader) + dirty_bytes(q) + flag_bytes(tiles_ub * chunks_ub));
-    // flags and side buffer must be zero on entry; redo / merge kernels leave them zero on exit
-    cudaError_t e = cudaMemsetAsync(wsp, 0, ws_clean ? sizeof(WsHeader) : bwd_tiled_workspace_bytes(q), st);
-    if (e != cudaSuccess) return e;
+    ws.hd = (WsHeader*)base; base += sizeof(WsHeader);
+    ws.img_max = (ImgMax*)base; base += img_max_bytes(q.n);
+    ws.dirty = (unsigned char*)base; base += dirty_bytes(q);
+    ws.redo = (int*)base; base += flag_bytes(tiles_ub * chunks_ub);
+    ws.acc64 = (unsigned long long*)base;
+    // The whole workspace must be zero on entry.  Every call leaves it zero on exit (the last kernel's last CTA
+    // clears the prefix, the redo / merge kernels the rest), so a caller that keeps it says so and no memset
+    // node interrupts the chain of programmatically dependent launches.
+    cudaError_t e;
+    if (!ws_clean && (e = cudaMemsetAsync(wsp, 0, bwd_tiled_workspace_bytes(q), st)) != cudaSuccess) return e;
 
     // ---- grad_offset / grad_mask ----
     const int max_cells = kMaxBoxBytes / kCellBytes;
     const TileGeom tg = make_geom(q, dtype, 16, 16, 3.0f, max_cells);
     if (tg.bw * tg.bh > max_cells) return cudaErrorInvalidConfiguration;
-    CUtensorMap map;
+    CUtensorMap map, offmap, goffmap;
     if (!make_x_tensor_map(&map, x, q, dtype, tg.bw, tg.bh)) return cudaErrorNotSupported;
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_set[dev & 63]) {
-        e = cudaFuncSetAttribute(bwd_gather_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kMaxBoxBytes + 8 * kGatherStageBytes<T>);
-        if (e != cudaSuccess) return e;
-        attr_set[dev & 63] = true;
-    }
+    const bool staged = side_stageable(q, dtype);
+    if (staged && !(make_side_tensor_map(&offmap, offset, q, dtype, 18) &&
+                    make_side_tensor_map(&goffmap, grad_offset, q, dtype, 18)))
+        return cudaErrorNotSupported;
+    if (!staged) offmap = goffmap = map;  // unused by the kernel variant
     KernelTiming& kt = kernel_timing();
     if (kt.enabled) cudaEventRecord(kt.ev[0], st);
-    const unsigned grid_a = (unsigned)((size_t)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
-    // (also leaves max|grad_out| in the workspace header: the fixed-point scale of the scatter kernel)
-    bwd_gather_kernel<T><<<grid_a, 256, (size_t)tg.bw * tg.bh * kCellBytes + 8 * kGatherStageBytes<T>, st>>>(
-        map, (const T*)x, (const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_offset, (T*)grad_mask, ws.hd,
-        q, tg);
+    e = staged ? launch_gather_variant<T, true>(map, offmap, goffmap, x, offset, mask, grad_out, grad_offset, grad_mask,
+                                                ws.img_max, q, tg, st)
+               : launch_gather_variant<T, false>(map, offmap, goffmap, x, offset, mask, grad_out, grad_offset, grad_mask,
+                                                 ws.img_max, q, tg, st);
+    if (e != cudaSuccess) return e;
 
     // ---- grad_x ----
     if (kt.enabled) cudaEventRecord(kt.ev[1], st);
     const unsigned grid_b = (unsigned)(tiles * bg.chunks);
-    e = bg.tj == 32 ? launch_scatter<T, 32>((const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_x, ws, q, bg,
-                                            grid_b, st)
-                    : launch_scatter<T, 16>((const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_x, ws, q, bg,
-                                            grid_b, st);
-    if (e != cudaSuccess) return e;
-    if (kt.enabled) cudaEventRecord(kt.ev[3], st);
     // a single tile owns every cell of its image: no ring, no far landings, nothing to merge
     const bool merge = bg.tiles_x * bg.tiles_y > 1;
+    e = bg.tj == 32 ? launch_scatter<T, 32>((const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_x, ws, q, bg,
+                                            grid_b, !merge, st)
+                    : launch_scatter<T, 16>((const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_x, ws, q, bg,
+                                            grid_b, !merge, st);
+    if (e != cudaSuccess) return e;
+    if (kt.enabled) cudaEventRecord(kt.ev[3], st);
     if (merge) {
         const size_t npg = (size_t)q.n * q.h * q.w * q.G;
-        merge_far_kernel<T><<<(unsigned)((npg + 255) / 256), 256, 0, st>>>((T*)grad_x, ws, q, npg);
+        e = launch_pdl(merge_far_kernel<T>, (unsigned)((npg + 255) / 256), 256, 0, st, (T*)grad_x, ws, q, npg);
+        if (e != cudaSuccess) return e;
     }
     if (kt.enabled) cudaEventRecord(kt.ev[4], st);
     count_launch(merge ? 4 : 3);
@@ -803,7 +892,7 @@ static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const v
 }
 
 void bwd_tiled_plan(const KParams& q, int dtype, int out[16]) {
-    gather_tiled_plan(q, dtype, 8 * (dtype == DCNV3_F32 ? kGatherStageBytes<float> : kGatherStageBytes<__nv_bfloat16>), out);
+    gather_tiled_plan(q, dtype, kTiledWarps * (dtype == DCNV3_F32 ? kGatherStageBytes<float> : kGatherStageBytes<__nv_bfloat16>), out);
     const BwdGeom bg = make_bwd_geom(q);
     out[8] = bg.tj; out[9] = bg.ring_lo; out[10] = bg.ring_hi; out[11] = bg.box_rows;
     out[12] = (int)((long long)q.n * bg.tiles_x * bg.tiles_y * bg.chunks);

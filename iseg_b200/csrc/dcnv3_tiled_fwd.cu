@@ -8,6 +8,9 @@
 //   3. taps whose 2x2 patch leaves the staged box (large learned offsets) fall back to L2/global
 //      loads -- correctness never depends on the halo, only speed does.
 // Algorithmic HBM bytes per (pixel, group): x 16 + out 16 + offset 18 + mask 9 elements.
+#include <mutex>
+#include <unordered_map>
+
 #include "dcnv3_kernels.h"
 #include "dcnv3_tiled.cuh"
 
@@ -20,14 +23,17 @@ __device__ __forceinline__ const T* global_slab(const T* x, const KParams& q, in
     return x + ((((size_t)n * q.h + y) * q.w + xx) * q.G + g) * kGC;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256, 2)
-fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict__ x,
-                 const T* __restrict__ offset, const T* __restrict__ mask, T* __restrict__ out,
-                 const KParams q, const TileGeom tg) {
+template <typename T, bool STAGED>
+__global__ void __launch_bounds__(kTiledWarps * 32, 2)
+fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap offmap,
+                 const T* __restrict__ x, const T* __restrict__ offset, const T* __restrict__ mask,
+                 T* __restrict__ out, const KParams q, const TileGeom tg) {
     using C = Chunk<T>;
+    using RS = RowStage<T>;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t sbar[kTiledWarps];
+    pdl_launch_dependents();  // the next kernel of the stream may start its prologue (it waits before reading)
 
     // ---- which tile ----
     int b = blockIdx.x;
@@ -44,9 +50,12 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict__
 
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
+#pragma unroll
+        for (int i = 0; i < kTiledWarps; ++i) mbar_init(&sbar[i], 1);
         fence_mbar_init();
     }
     __syncthreads();
+    pdl_wait();  // from here on global memory is read: everything the previous kernels wrote is visible
     if (threadIdx.x == 0) {
         mbar_expect_tx(&bar, (uint32_t)(tg.bw * tg.bh * kCellBytes));
         tma_load_4d(smem, &xmap, &bar, chunk * C::GQ * kGC, cx0 - q.pw, cy0 - q.ph, n);
@@ -58,28 +67,52 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict__
     const int g = min(chunk * C::GQ + g_l, q.G - 1);        // (phantom lanes shadow the last group, never store)
     const int rot = Slab<T>::rot_of(px_l);
     const unsigned char* sbase = smem + g_l * (kGC * (int)sizeof(T));
+    unsigned char* st = smem + (size_t)tg.bw * tg.bh * kCellBytes + warp * RS::BYTES;  // the warp's side slot
     const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
-    const int npix = th * tw;
+    const int colblocks = (tw + C::PXW - 1) / C::PXW, nit = th * colblocks;
     bool waited = false;
-    (void)th;
+    uint32_t sphase = 0;
 
-    for (int p0 = warp * C::PXW; p0 < npix; p0 += (blockDim.x >> 5) * C::PXW) {
-        const bool valid = real_g && p0 + px_l < npix;
-        const int pix = min(p0 + px_l, npix - 1);  // idle lanes shadow the last pixel (loads stay in bounds)
-        const int h = h0 + pix / tw, w = w0 + pix % tw;
+    // side inputs of one warp iteration (PXW consecutive pixels of one output row) -> the warp's slot
+    auto request = [&](int it) {
+        const int h = h0 + it / colblocks, wb = w0 + (it % colblocks) * C::PXW;
+        const size_t pix0 = ((size_t)n * q.ho + h) * q.wo + wb;
+        RS::request(st, &sbar[warp], &offmap, mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, chunk, wb, n * q.ho + h,
+                    min(C::PXW, w0 + tw - wb), lane);
+    };
+    if (STAGED && warp < nit) request(warp);
+
+    for (int it = warp; it < nit; it += kTiledWarps) {
+        const int h = h0 + it / colblocks, wb = w0 + (it % colblocks) * C::PXW;
+        const int npx = min(C::PXW, w0 + tw - wb);
+        const bool valid = real_g && px_l < npx;
+        const int w = wb + min(px_l, npx - 1);  // idle lanes shadow the last pixel (loads stay in bounds)
         const size_t pg = (((size_t)n * q.ho + h) * q.wo + w) * q.G + g;
         const T* offp = offset + pg * 18;
         const T* mskp = mask + pg * 9;
-        float mx = 0.f, inv_sum = 1.f;
-        if (logits) softmax_stats9<T>(mskp, mx, inv_sum);
         float ref0, ref1;
         ref_point(q, h, w, ref0, ref1);
+        if (STAGED) {
+            cp_async_wait_all();
+            __syncwarp();
+            mbar_wait(&sbar[warp], sphase);
+            sphase ^= 1;
+        }
+        float mx = 0.f, inv_sum = 1.f;
+        if (logits) {
+            if (STAGED) RS::softmax_stats(st, lane, mx, inv_sum);
+            else softmax_stats9<T>(mskp, mx, inv_sum);
+        }
         f2 acc[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[c] = 0ull;
-        float ox, oy, ml, ox2, oy2, ml2;
-        load_tap_inputs<T>(offp, mskp, 0, ox, oy, ml);
-        load_tap_inputs<T>(offp, mskp, 1, ox2, oy2, ml2);
+        float ox, oy, ml, ox2 = 0.f, oy2 = 0.f, ml2 = 0.f;
+        if (STAGED) {
+            RS::tap(st, lane, 0, ox, oy, ml);
+        } else {
+            load_tap_inputs<T>(offp, mskp, 0, ox, oy, ml);
+            load_tap_inputs<T>(offp, mskp, 1, ox2, oy2, ml2);
+        }
         if (!waited) {  // the box is needed from here on
             mbar_wait(&bar, 0);
             waited = true;
@@ -87,13 +120,17 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict__
 #pragma unroll 1
         for (int p = 0; p < kTaps; ++p) {
             const float cx = ox, cy = oy, cm = ml;
-            ox = ox2; oy = oy2; ml = ml2;
-            if (p + 2 < kTaps) load_tap_inputs<T>(offp, mskp, p + 2, ox2, oy2, ml2);  // prefetch two taps ahead
+            if (STAGED) {
+                if (p + 1 < kTaps) RS::tap(st, lane, p + 1, ox, oy, ml);  // shared memory: one tap ahead is enough
+            } else {
+                ox = ox2; oy = oy2; ml = ml2;
+                if (p + 2 < kTaps) load_tap_inputs<T>(offp, mskp, p + 2, ox2, oy2, ml2);  // prefetch two taps ahead
+            }
             const Tap t = make_tap(q, ref0, ref1, p, cx, cy);
             const int bx = t.x0 - cx0, by = t.y0 - cy0;
             const bool inbox = bx >= 0 && bx + 1 < tg.bw && by >= 0 && by + 1 < tg.bh;
             const float mm = t.alive ? (logits ? expf(cm - mx) * inv_sum : cm) : 0.f;
-            const float wa = t.dx1 * t.dy1 * mm, wb = t.dx1 * t.dy0 * mm;   // (y0,x0) (y1,x0)
+            const float wa = t.dx1 * t.dy1 * mm, wb_ = t.dx1 * t.dy0 * mm;  // (y0,x0) (y1,x0)
             const float wc = t.dx0 * t.dy1 * mm, wd = t.dx0 * t.dy0 * mm;   // (y0,x1) (y1,x1)
             if (__builtin_expect(t.alive && !inbox, 0)) {
                 // rare: patch outside the staged box -> straight from global memory
@@ -101,7 +138,7 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict__
                 for (int k = 0; k < 4; ++k) {
                     const T* src = global_slab(x, q, n, t.y0 + (k & 1), t.x0 + (k >> 1), g);
                     if (src == nullptr) continue;
-                    const float wk = (k & 1) ? ((k >> 1) ? wd : wb) : ((k >> 1) ? wc : wa);
+                    const float wk = (k & 1) ? ((k >> 1) ? wd : wb_) : ((k >> 1) ? wc : wa);
 #pragma unroll
                     for (int pc = 0; pc < C::NPIECE; ++pc) {
                         f2 v[C::PAIRS];
@@ -120,13 +157,18 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const T* __restrict__
                 for (int c = 0; c < 8; ++c) ffma2s(acc[c], va[c], wa);
                 Slab<T>::load(a + kCellBytes, rot, va);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) ffma2s(acc[c], vb[c], wb);
+                for (int c = 0; c < 8; ++c) ffma2s(acc[c], vb[c], wb_);
                 Slab<T>::load(a + (size_t)(tg.bw + 1) * kCellBytes, rot, vb);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) ffma2s(acc[c], va[c], wc);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) ffma2s(acc[c], vb[c], wd);
             }
+        }
+        if (STAGED) {
+            // every lane has consumed its slot values (they fed the arithmetic above): refill for the next iteration
+            __syncwarp();
+            if (it + kTiledWarps < nit) request(it + kTiledWarps);
         }
         if (valid) {
             T* dst = out + pg * kGC;
@@ -144,32 +186,99 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn == nullptr) {
+    static const EncodeTiledFn fn = [] {  // (thread-safe: initialised once)
         void* p = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
+            return (EncodeTiledFn)p;
+        return (EncodeTiledFn) nullptr;
+    }();
     return fn;
 }
 
-bool make_x_tensor_map(CUtensorMap* map, const void* x, const KParams& q, int dtype, int bw, int bh) {
+cudaError_t ensure_max_smem(const void* kernel, int bytes) {
+    static std::mutex mu;
+    static std::unordered_map<const void*, unsigned long long> done;  // kernel -> devices (bit mask) already set
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    unsigned long long& m = done[kernel];
+    if (dev < 64 && (m >> dev) & 1ull) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);  // lives in the device's context
+    if (e == cudaSuccess && dev < 64) m |= 1ull << dev;
+    return e;
+}
+
+// Encoding a tensor map costs a driver call (~1 us); layers call with the same tensors over and over, so the
+// encoded maps are kept in a small per-thread table keyed by everything that went into them.
+struct MapKey {
+    const void* base;
+    unsigned long long d0, d1, d2, d3;
+    unsigned b0, b1, b2, es;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && b0 == o.b0 && b1 == o.b1 &&
+               b2 == o.b2 && es == o.es;
+    }
+};
+struct MapSlot {
+    MapKey key;
+    CUtensorMap map;
+    bool used;
+};
+static bool encode_cached(CUtensorMap* out, const MapKey& k, int rank, CUtensorMapDataType dt, const cuuint64_t* dims,
+                          const cuuint64_t* strides, const cuuint32_t* box) {
+    constexpr int kSlots = 128;
+    static thread_local MapSlot table[kSlots];
+    size_t hsh = (size_t)k.base * 0x9E3779B97F4A7C15ull;
+    hsh ^= (k.d0 * 31 + k.d1) * 0xC2B2AE3D27D4EB4Full + k.d2 * 1315423911ull + k.d3 * 2654435761ull + k.b1 * 97 + k.b2 * 89 + k.b0;
+    MapSlot& sl = table[(hsh >> 17) % kSlots];
+    if (sl.used && sl.key == k) {
+        *out = sl.map;
+        return true;
+    }
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) return false;
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(k.base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    sl.key = k;
+    sl.map = *out;
+    sl.used = true;
+    return true;
+}
+
+bool make_x_tensor_map(CUtensorMap* map, const void* x, const KParams& q, int dtype, int bw, int bh) {
     const cuuint64_t es = dtype == DCNV3_F32 ? 4 : 2;
     const int gq = dtype == DCNV3_F32 ? 2 : 4;
     const cuuint64_t C = (cuuint64_t)q.G * q.gc;
     const cuuint64_t dims[4] = {C, (cuuint64_t)q.w, (cuuint64_t)q.h, (cuuint64_t)q.n};
     const cuuint64_t strides[3] = {C * es, (cuuint64_t)q.w * C * es, (cuuint64_t)q.h * q.w * C * es};
     const cuuint32_t box[4] = {(cuuint32_t)(gq * kGC), (cuuint32_t)bw, (cuuint32_t)bh, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = fn(map, dtype == DCNV3_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                          4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS;
+    const MapKey k = {x, dims[0], dims[1], dims[2], dims[3], box[0], box[1], box[2], (unsigned)es};
+    return encode_cached(map, k, 4, dtype == DCNV3_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                         dims, strides, box);
+}
+
+// offsets / grad_offset as [N*Ho rows][Wo][G*18]: box = the 18 values of the GQ groups of a chunk for the PXW
+// pixels of one warp iteration.  (The mask's 72-byte runs are not a legal box width; see RowStage.)
+bool side_stageable(const KParams& q, int dtype) {
+    const int gq = dtype == DCNV3_F32 ? 2 : 4;
+    return q.G % gq == 0 && (long long)q.n * q.ho < (1ll << 31);
+}
+bool make_side_tensor_map(CUtensorMap* map, const void* base, const KParams& q, int dtype, int per_group) {
+    const cuuint64_t es = dtype == DCNV3_F32 ? 4 : 2;
+    const int gq = dtype == DCNV3_F32 ? 2 : 4, pxw = 32 / gq;
+    const cuuint64_t ch = (cuuint64_t)q.G * per_group;
+    const cuuint64_t dims[3] = {ch, (cuuint64_t)q.wo, (cuuint64_t)q.n * q.ho};
+    const cuuint64_t strides[2] = {ch * es, (cuuint64_t)q.wo * ch * es};
+    const cuuint32_t box[3] = {(cuuint32_t)(gq * per_group), (cuuint32_t)pxw, 1};
+    const MapKey k = {base, dims[0], dims[1], dims[2], 0, box[0], box[1], box[2], (unsigned)es};
+    return encode_cached(map, k, 3, dtype == DCNV3_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                         dims, strides, box);
 }
 
 // Box geometry: the nominal footprint of a th x tw output tile spans (th-1)*ax columns and (tw-1)*ay
@@ -227,6 +336,9 @@ TileGeom make_geom(const KParams& q, int dtype, int th, int tw, float reach, int
     return best;
 }
 
+// forward box budget: with staged side inputs the per-warp slots share the CTA's shared memory
+static int fwd_box_bytes(const KParams& q, int dtype) { return side_stageable(q, dtype) ? kMaxBoxBytes : kFwdBoxBytes; }
+
 // Tiled kernels serve the InternImage configuration only -- and only images whose tile boxes fit shared
 // memory (everything but extreme aspect ratios at large offset_scale); the rest runs the generic kernels.
 bool tiled_applicable(const KParams& q, int dtype) {
@@ -234,31 +346,37 @@ bool tiled_applicable(const KParams& q, int dtype) {
     if (!(q.P == 9 && q.kh == 3 && q.sh == 1 && q.sw == 1 && q.dh == 1 && q.dw == 1 && q.gc == kGC && q.ho == q.h &&
           q.wo == q.w && q.ph == 1 && q.pw == 1 && q.scale > 0.f && q.scale <= 16.f && q.h <= 16384 && q.w <= 16384))
         return false;
-    const int fwd_cells = kFwdBoxBytes / kCellBytes, bwd_cells = kMaxBoxBytes / kCellBytes;
+    const int fwd_cells = fwd_box_bytes(q, dtype) / kCellBytes, bwd_cells = kMaxBoxBytes / kCellBytes;
     const TileGeom a = make_geom(q, dtype, 16, 16, 3.0f, fwd_cells), b = make_geom(q, dtype, 16, 16, 3.0f, bwd_cells);
     return a.bw * a.bh <= fwd_cells && b.bw * b.bh <= bwd_cells;
+}
+
+template <typename T, bool STAGED>
+static cudaError_t launch_fwd_variant(const CUtensorMap& map, const CUtensorMap& offmap, const void* x, const void* offset,
+                                      const void* mask, void* out, const KParams& q, const TileGeom& tg, cudaStream_t st) {
+    const size_t smem = (size_t)tg.bw * tg.bh * kCellBytes + (STAGED ? kTiledWarps * RowStage<T>::BYTES : 0);
+    cudaError_t e = ensure_max_smem((const void*)fwd_tiled_kernel<T, STAGED>,
+                                    STAGED ? kMaxBoxBytes + kTiledWarps * RowStage<T>::BYTES : kFwdBoxBytes);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((size_t)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
+    return launch_pdl(fwd_tiled_kernel<T, STAGED>, grid, kTiledWarps * 32, smem, st, map, offmap, (const T*)x,
+                      (const T*)offset, (const T*)mask, (T*)out, q, tg);
 }
 
 template <typename T>
 static cudaError_t launch_fwd_tiled_t(const void* x, const void* offset, const void* mask, void* out,
                                       const KParams& q, int dtype, cudaStream_t st) {
-    const int max_cells = kFwdBoxBytes / kCellBytes;  // two CTAs per SM
+    const int max_cells = fwd_box_bytes(q, dtype) / kCellBytes;  // two CTAs per SM
     const TileGeom tg = make_geom(q, dtype, 16, 16, 3.0f, max_cells);
     if (tg.bw * tg.bh > max_cells) return cudaErrorInvalidConfiguration;
-    CUtensorMap map;
+    CUtensorMap map, offmap;
     if (!make_x_tensor_map(&map, x, q, dtype, tg.bw, tg.bh)) return cudaErrorNotSupported;
-    const size_t smem = (size_t)tg.bw * tg.bh * kCellBytes;
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_set[dev & 63]) {  // per device: the attribute lives in the context
-        cudaError_t e = cudaFuncSetAttribute(fwd_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kFwdBoxBytes);
-        if (e != cudaSuccess) return e;
-        attr_set[dev & 63] = true;
-    }
-    const unsigned grid = (unsigned)((size_t)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
-    fwd_tiled_kernel<T><<<grid, 256, smem, st>>>(map, (const T*)x, (const T*)offset, (const T*)mask, (T*)out, q, tg);
+    const bool staged = side_stageable(q, dtype);
+    if (staged && !make_side_tensor_map(&offmap, offset, q, dtype, 18)) return cudaErrorNotSupported;
+    if (!staged) offmap = map;  // unused by the kernel variant
+    cudaError_t e = staged ? launch_fwd_variant<T, true>(map, offmap, x, offset, mask, out, q, tg, st)
+                           : launch_fwd_variant<T, false>(map, offmap, x, offset, mask, out, q, tg, st);
+    if (e != cudaSuccess) return e;
     count_launch(1);
     return cudaGetLastError();
 }
@@ -270,8 +388,9 @@ static void geom_numbers(const KParams& q, const TileGeom& tg, long long smem, i
 }
 
 void fwd_tiled_plan(const KParams& q, int dtype, int out[8]) {
-    const TileGeom tg = make_geom(q, dtype, 16, 16, 3.0f, kFwdBoxBytes / kCellBytes);
-    geom_numbers(q, tg, (long long)tg.bw * tg.bh * kCellBytes, out);
+    const TileGeom tg = make_geom(q, dtype, 16, 16, 3.0f, fwd_box_bytes(q, dtype) / kCellBytes);
+    const int slot = dtype == DCNV3_F32 ? RowStage<float>::BYTES : RowStage<__nv_bfloat16>::BYTES;
+    geom_numbers(q, tg, (long long)tg.bw * tg.bh * kCellBytes + (side_stageable(q, dtype) ? kTiledWarps * slot : 0), out);
 }
 
 void gather_tiled_plan(const KParams& q, int dtype, int stage_bytes, int out[8]) {

@@ -110,7 +110,7 @@ def test_launch_plans_fit_the_hardware_for_any_shape(cabi):
     n_tiled = 0
     for h, w in shapes:
         for scale in (0.25, 0.5, 1.0, 2.0, 4.0):
-            for dtype, g in ((cabi.F32, 4), (cabi.BF16, 5), (cabi.F32, 1)):
+            for dtype, g in ((cabi.F32, 4), (cabi.BF16, 5), (cabi.F32, 1), (cabi.BF16, 8)):
                 p = cabi.make_params((2, h, w, g * 16), (h, w), (3, 3), (1, 1), (1, 1), (1, 1), g, 16, scale, dtype)
                 plan = cabi.launch_plan(p)
                 if not plan["tiled"]:
@@ -121,22 +121,29 @@ def test_launch_plans_fit_the_hardware_for_any_shape(cabi):
                     assert 1 <= k["th"] <= 16 and 1 <= k["tw"] <= 128, (h, w, scale, k)
                     assert 2 <= k["bw"] <= min(w + 2, 256) and 2 <= k["bh"] <= min(h + 2, 256), (h, w, scale, k)
                     assert k["halo_x"] >= 1 and k["halo_y"] >= 1 and k["ctas"] >= 1
-                assert f["smem"] == f["bw"] * f["bh"] * 128 <= 100 * 1024, (h, w, scale, f)
+                # forward: box + (when the group count allows TMA / cp.async staging) eight per-warp side slots
+                slots = 8 * (3456 if dtype == cabi.F32 else 1792) if g % (2 if dtype == cabi.F32 else 4) == 0 else 0
+                assert f["bw"] * f["bh"] * 128 <= (82 if slots else 100) * 1024, (h, w, scale, f)
+                assert f["smem"] == f["bw"] * f["bh"] * 128 + slots, (h, w, scale, f)
+                assert 2 * (f["smem"] + 1024) <= 227 * 1024, (h, w, scale, f)
                 assert ga["bw"] * ga["bh"] * 128 <= 82 * 1024 and 2 * ga["smem"] <= 227 * 1024, (h, w, scale, ga)
                 pitch = sc["tj"] + 9
                 assert sc["tj"] in (16, 32) and 1 <= sc["ring_lo"] <= 4 and 2 <= sc["ring_hi"] <= 5
                 assert 1 <= sc["box_rows"] <= pitch and sc["smem"] <= 227 * 1024 and sc["ctas"] >= 1
                 assert sc["merge"] == (h > sc["tj"] or w > sc["tj"])
-    assert n_tiled > 3000
+    assert n_tiled > 4000
     # the shapes InternImage runs (square-ish, offset_scale 1 or 2): always tiled, full 16 x 16 tiles, and
     # at offset_scale 1 a forward reach of 3 offset units (halo 4)
     for h, w, g, scale in ((128, 128, 4, 1.0), (32, 32, 16, 1.0), (193, 193, 4, 1.0), (160, 160, 10, 2.0),
                            (256, 512, 4, 1.0), (25, 49, 32, 1.0)):
         p = cabi.make_params((16, h, w, g * 16), (h, w), (3, 3), (1, 1), (1, 1), (1, 1), g, 16, scale, cabi.F32)
         plan = cabi.launch_plan(p)
-        assert plan["tiled"] and plan["forward"]["th"] == 16 and plan["forward"]["tw"] == 16, (h, w, plan)
+        assert plan["tiled"], (h, w, plan)
         if scale == 1.0:
-            assert plan["forward"]["halo_x"] == 4 and plan["scatter"]["ring_lo"] == 4 and plan["scatter"]["ring_hi"] == 5
+            assert plan["forward"]["th"] == 16 and plan["forward"]["tw"] == 16, (h, w, plan)
+        if scale == 1.0:
+            assert plan["scatter"]["ring_lo"] == 4 and plan["scatter"]["ring_hi"] == 5
+            assert plan["forward"]["halo_x"] == (4 if h == w else 3)  # (a 2:1 image gives up a little reach to fit 82 KB)
     # other kernel sizes / strides / channel counts are served by the generic kernels
     p = cabi.make_params((2, 32, 32, 64), (32, 32), (5, 5), (1, 1), (2, 2), (1, 1), 4, 16, 1.0, cabi.F32)
     assert not cabi.launch_plan(p)["tiled"]
