@@ -58,6 +58,12 @@ typedef enum { DCNV3_F32 = 0, DCNV3_BF16 = 1 } dcnv3_dtype;
 #define DCNV3_FLAG_WORKSPACE_ZEROED 4u
 /* testing aid: bypass the shared-memory tiled kernels and run the generic kernels */
 #define DCNV3_FLAG_FORCE_GENERIC 2u
+/* bf16 tensors only (ignored for fp32): reproduce the arithmetic the reference performs under the
+   mixed_bfloat16 policy -- reference points, grids, sampling locations, pixel coordinates, bilinear weights
+   and the forward accumulation all rounded to bfloat16 after every primitive (op.py:62-87, utils.py:130-206).
+   Default (flag clear): coordinates and accumulation in fp32 on the bf16 inputs -- better numerics, but a
+   different result, because bf16 coordinates near 130 have a step of 1 pixel.  Runs the generic kernels. */
+#define DCNV3_FLAG_REF_DTYPE 8u
 
 typedef struct dcnv3_params {
     int32_t n, h, w;                 /* x is [n, h, w, groups*group_channels] */

@@ -32,6 +32,9 @@ static int cuda_fail(cudaError_t e, const char* what) {
     return fail(DCNV3_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
 
+// the reference-dtype emulation exists for bf16 only (for fp32 the reference dtype IS the kernels' arithmetic)
+static bool ref_dtype_mode(const dcnv3_params* p) { return p->dtype == DCNV3_BF16 && (p->flags & DCNV3_FLAG_REF_DTYPE); }
+
 static size_t elem_size(int dtype) { return dtype == DCNV3_F32 ? 4 : 2; }
 
 // The envelope the reference enforces through tf.reshape (op.py:83 with utils.py:26-27): the
@@ -104,7 +107,7 @@ static int forward_impl(const void* x, const void* offset, const void* mask, voi
         (rc = check_ptr_align(mask, "mask")) || (rc = check_ptr_align(out, "out")))
         return rc;
     const KParams q = derive(p);
-    const bool tiled = tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC);
+    const bool tiled = tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC) && !ref_dtype_mode(p);
     cudaError_t e = tiled ? launch_fwd_tiled(x, offset, mask, out, q, p->dtype, st)
                           : launch_fwd_generic(x, offset, mask, out, q, p->dtype, st);
     if (e != cudaSuccess) return cuda_fail(e, "dcnv3_forward launch");
@@ -133,7 +136,7 @@ static int backward_impl(const void* x, const void* offset, const void* mask, co
         return fail(DCNV3_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", need, ws_bytes);
     if ((rc = check_ptr_align(ws, "workspace", 256))) return rc;
     const KParams q = derive(p);
-    const bool tiled = tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC);
+    const bool tiled = tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC) && !ref_dtype_mode(p);
     cudaError_t e =
         tiled ? launch_bwd_tiled(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, p->dtype,
                                  (p->flags & DCNV3_FLAG_WORKSPACE_ZEROED) != 0, st)
@@ -297,7 +300,7 @@ int dcnv3_launch_plan(const dcnv3_params* p, int* plan25) {
     if (plan25 == nullptr) return fail(DCNV3_ERR_ARGUMENT, "NULL plan buffer");
     const KParams q = derive(p);
     for (int i = 0; i < 25; ++i) plan25[i] = 0;
-    plan25[0] = tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC);
+    plan25[0] = tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC) && !ref_dtype_mode(p);
     if (plan25[0]) {
         fwd_tiled_plan(q, p->dtype, plan25 + 1);
         bwd_tiled_plan(q, p->dtype, plan25 + 9);

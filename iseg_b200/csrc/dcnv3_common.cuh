@@ -123,6 +123,48 @@ __device__ __forceinline__ Tap make_tap(const KParams& q, float ref0, float ref1
     return t;
 }
 
+// ---- reference-dtype (bfloat16) coordinate arithmetic --------------------------------------------------
+// Under the mixed_bfloat16 policy the reference computes reference points, grids, sampling locations,
+// pixel coordinates and bilinear weights in x.dtype = bfloat16 (op.py:62,72,80-87; utils.py:130,140-172):
+// every primitive rounds its result to bf16.  DCNV3_FLAG_REF_DTYPE reproduces that operation by operation
+// (rb = round to bf16) so that the SAME cells are sampled with the SAME weights; the default bf16 path
+// keeps fp32 coordinates (better numerics, different results: coordinates near 130 have a bf16 step of 1).
+__device__ __forceinline__ float rb(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// one axis: pos = h*stride + start (utils.py:29-36, fp32 linspace value), ref_dim = the extent the
+// reference point is divided by (utils.py:49-50), disp = the tap's integer displacement (utils.py:77-87),
+// dim = the extent this coordinate is paired with (op.py:77: [W_in, H_in])
+__device__ __forceinline__ Axis axis_refdtype(float pos, float ref_dim, int disp, float dim, float off, float scale) {
+    const float sc = rb(scale);                                              // python float -> tensor of x.dtype
+    const float ref = rb(__fdiv_rn(rb(pos), rb(ref_dim)));                   // utils.py:40-50
+    const float gs = rb(rb(__fdiv_rn(rb((float)disp), rb(dim))) * sc);       // utils.py:91-95, op.py:82
+    float loc = rb(ref + gs);                                                // op.py:82
+    loc = rb(loc + rb(__fdiv_rn(rb(off * sc), rb(dim))));                    // op.py:85
+    const float g = rb(rb(2.0f * loc) - 1.0f);                               // op.py:87
+    const float coord = rb(0.5f * rb(rb(g + 1.0f) * rb(dim - 2.0f)));        // utils.py:142-143
+    Axis a;
+    const float f = floorf(coord), max_f = dim - 1.0f;
+    a.alive = (f >= 0.0f) && (f < max_f);                                    // clipped corners coincide otherwise
+    a.i0 = a.alive ? (int)f : 0;
+    const float c0 = rb(f), c1 = rb(f + 1.0f);                               // utils.py:158-161: int -> x.dtype
+    a.d0 = a.alive ? rb(coord - c0) : 0.0f;                                  // utils.py:163-166
+    a.d1 = a.alive ? rb(c1 - coord) : 0.0f;
+    return a;
+}
+__device__ __forceinline__ Tap make_tap_refdtype(const KParams& q, int h, int w, int p, float offx, float offy) {
+    const int kw = q.P / q.kh, i = p / q.kh, j = p % q.kh;                   // utils.py:77-101: p = i*kh + j
+    const int dxp = -((q.dw * (kw - 1)) / 2) + i * q.dw, dyp = -((q.dh * (q.kh - 1)) / 2) + j * q.dh;
+    // channel 0: ref_y (divided by H_in) + x displacement / W_in + offset / W_in -> x coordinate
+    const Axis ax = axis_refdtype((float)(h * q.sh) + q.y0c, q.hin_f, dxp, q.win_f, offx, q.scale);
+    const Axis ay = axis_refdtype((float)(w * q.sw) + q.x0c, q.win_f, dyp, q.hin_f, offy, q.scale);
+    Tap t;
+    t.alive = ax.alive && ay.alive;
+    t.x0 = ax.i0; t.y0 = ay.i0;
+    t.dx0 = t.alive ? ax.d0 : 0.0f; t.dx1 = t.alive ? ax.d1 : 0.0f;
+    t.dy0 = t.alive ? ay.d0 : 0.0f; t.dy1 = t.alive ? ay.d1 : 0.0f;
+    return t;
+}
+
 // ---- element access -----------------------------------------------------------------------------
 template <typename T>
 struct Elem;

@@ -55,12 +55,35 @@ fwd_generic_kernel(const T* __restrict__ x, const T* __restrict__ offset, const 
 #pragma unroll
     for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
     const int c0 = cq * VEC;
+    // bf16 only: every intermediate rounded to bf16 in the reference's op order (dcnv3_common.cuh)
+    const bool refdt = sizeof(T) == 2 && (q.flags & DCNV3_FLAG_REF_DTYPE);
     for (int p = 0; p < q.P; ++p) {
-        const Tap t = make_tap(q, ref0, ref1, p, Elem<T>::ld(off + 2 * p), Elem<T>::ld(off + 2 * p + 1));
+        const float ox = Elem<T>::ld(off + 2 * p), oy = Elem<T>::ld(off + 2 * p + 1);
+        const Tap t = refdt ? make_tap_refdtype(q, h, w, p, ox, oy) : make_tap(q, ref0, ref1, p, ox, oy);
         if (!t.alive) continue;
         float m = Elem<T>::ld(msk + p);
         if (logits) m = expf(m - mx) * inv_sum;
-        const float wgt[4] = {t.dx1 * t.dy1, t.dx1 * t.dy0, t.dx0 * t.dy1, t.dx0 * t.dy0};
+        float wgt[4] = {t.dx1 * t.dy1, t.dx1 * t.dy0, t.dx0 * t.dy1, t.dx0 * t.dy0};
+        if (refdt) {
+            // utils.py:169-206 in bf16: weights, the four products, their sum (fp32 accumulator, rounded once),
+            // the mask product and the running output are each rounded to bf16
+#pragma unroll
+            for (int k = 0; k < 4; ++k) wgt[k] = rb(wgt[k]);
+            if (logits) m = rb(m);
+            float s[VEC];
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) s[c] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const T* src = slab_ptr(x, q, n, t.y0 + (k & 1), t.x0 + (k >> 1), g);
+                if (src == nullptr) continue;
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) s[c] += rb(Elem<T>::ld(src + c0 + c) * wgt[k]);
+            }
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) acc[c] = rb(acc[c] + rb(rb(s[c]) * m));
+            continue;
+        }
         float s[VEC];
 #pragma unroll
         for (int c = 0; c < VEC; ++c) s[c] = 0.f;
@@ -145,8 +168,12 @@ bwd_generic_kernel(const T* __restrict__ x, const T* __restrict__ offset, const 
     if (logits) softmax_stats(msk, q.P, mx, inv_sum);
     float gm_dot_m = 0.f;       // sum_p m_p * dL/dm_p, for the softmax Jacobian
     float gm_local[DCNV3_MAX_TAPS];
+    // bf16 only: sampling cells and weights as the reference computes them in bf16 (dcnv3_common.cuh); the
+    // gradient arithmetic itself stays in fp32
+    const bool refdt = sizeof(T) == 2 && (q.flags & DCNV3_FLAG_REF_DTYPE);
     for (int p = 0; p < q.P; ++p) {
-        const Tap t = make_tap(q, ref0, ref1, p, Elem<T>::ld(off + 2 * p), Elem<T>::ld(off + 2 * p + 1));
+        const float ox = Elem<T>::ld(off + 2 * p), oy = Elem<T>::ld(off + 2 * p + 1);
+        const Tap t = refdt ? make_tap_refdtype(q, h, w, p, ox, oy) : make_tap(q, ref0, ref1, p, ox, oy);
         float m = Elem<T>::ld(msk + p);
         if (logits) m = expf(m - mx) * inv_sum;
         float gm = 0.f, gxq = 0.f, gyq = 0.f;

@@ -36,15 +36,19 @@ class _DCNv3Function(torch.autograd.Function):
 
 
 def dcnv3_op(x, offset, mask, kernel_size, strides, padding, dilation_rate, groups, group_channels,
-             offset_scale, mask_is_logits=False):
+             offset_scale, mask_is_logits=False, reference_dtype_math=False):
     """x [N,H,W,G*gc], offset [N,Ho,Wo,G*P*2], mask [N,Ho,Wo,G*P] -> [N,Ho,Wo,G*gc] (dtype of x).
 
     `mask_is_logits=True` (extension, not in the reference signature) fuses the softmax over the P
-    taps that the layer applies just before the call (dcn_v3.py:120-123)."""
+    taps that the layer applies just before the call (dcn_v3.py:120-123).
+    `reference_dtype_math=True` (extension; bf16 tensors only) rounds every intermediate of the coordinate,
+    weight and accumulation arithmetic to bf16 as the reference does under mixed_bfloat16 (op.py:62-87,
+    utils.py:130-206); the default keeps that arithmetic in fp32."""
     pad = _resolve_padding(kernel_size, padding)
     if offset.dtype != x.dtype or mask.dtype != x.dtype:
         raise TypeError("x, offset and mask must have the same dtype")
     cfg = (tuple(int(k) for k in kernel_size), tuple(int(s) for s in strides), pad,
            tuple(int(d) for d in dilation_rate), int(groups), int(group_channels),
-           float(offset_scale), _cabi.FLAG_MASK_LOGITS if mask_is_logits else 0)
+           float(offset_scale), (_cabi.FLAG_MASK_LOGITS if mask_is_logits else 0) |
+           (_cabi.FLAG_REF_DTYPE if reference_dtype_math else 0))
     return _DCNv3Function.apply(x, offset, mask, cfg)

@@ -256,6 +256,114 @@ def backward(x, offset, mask, grad_out, kernel_size=(3, 3), strides=(1, 1), padd
     return np.ascontiguousarray(grad_x).astype(dtype), grad_offset, grad_mask
 
 
+# --------------------------------------------------------------------------------------------------
+# the reference under mixed_bfloat16: every primitive rounds to bfloat16 (op.py:62-87, utils.py:130-206)
+# --------------------------------------------------------------------------------------------------
+def rb(a):
+    """float32 -> nearest bfloat16 (ties to even) -> float32, the rounding every bf16 TF / torch primitive
+    applies to its result."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    u = a.view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
+    out = r.view(np.float32).reshape(a.shape)
+    return np.where(np.isfinite(a), out, a)
+
+
+def _taps_bf16(offset, hin, win, kernel_size, strides, dilation_rate, groups, offset_scale):
+    """_taps with x.dtype = bfloat16: the same operations in the same order, each result rounded with rb().
+    Python scalars become tensors of x.dtype first (offset_scale -> rb(offset_scale)), ints cast to x.dtype
+    (H_in, W_in, the clipped corner indices, utils.py:158-161) are rounded too."""
+    f32 = np.float32
+    kh, kw = kernel_size
+    sh, sw = strides
+    dh, dw = dilation_rate
+    n, ho, wo, _ = offset.shape
+    p_ = kh * kw
+    s = rb(f32(offset_scale))
+    off = offset.reshape(n, ho, wo, groups, p_, 2).astype(f32)
+    hh = np.arange(ho, dtype=f32) * f32(sh) + f32((dh * (kh - 1)) // 2 + 0.5)  # fp32 linspace (utils.py:35-36)
+    ww = np.arange(wo, dtype=f32) * f32(sw) + f32((dw * (kw - 1)) // 2 + 0.5)
+    hin_b, win_b = rb(f32(hin)), rb(f32(win))
+    ref0 = rb(rb(hh) / hin_b).reshape(1, ho, 1, 1, 1)  # utils.py:40-50; ref_y -> channel 0 (:52)
+    ref1 = rb(rb(ww) / win_b).reshape(1, 1, wo, 1, 1)
+    pi, pj = np.divmod(np.arange(p_), kh)
+    g0 = rb(rb((-((dw * (kw - 1)) // 2) + pi * dw).astype(f32)) / win_b).reshape(1, 1, 1, 1, p_)
+    g1 = rb(rb((-((dh * (kh - 1)) // 2) + pj * dh).astype(f32)) / hin_b).reshape(1, 1, 1, 1, p_)
+    loc0 = rb(rb(ref0 + rb(g0 * s)) + rb(rb(off[..., 0] * s) / win_b))  # op.py:82-85
+    loc1 = rb(rb(ref1 + rb(g1 * s)) + rb(rb(off[..., 1] * s) / hin_b))
+    t = _Taps()
+    t.xq = rb(f32(0.5) * rb(rb(rb(rb(f32(2) * loc0) - f32(1)) + f32(1)) * rb(f32(win - 2))))  # op.py:87, utils.py:142
+    t.yq = rb(f32(0.5) * rb(rb(rb(rb(f32(2) * loc1) - f32(1)) + f32(1)) * rb(f32(hin - 2))))
+    fx = np.floor(t.xq).astype(np.int64)
+    fy = np.floor(t.yq).astype(np.int64)
+    t.x0, t.x1 = np.clip(fx, 0, win - 1), np.clip(fx + 1, 0, win - 1)
+    t.y0, t.y1 = np.clip(fy, 0, hin - 1), np.clip(fy + 1, 0, hin - 1)
+    t.dx0, t.dx1 = rb(t.xq - rb(t.x0.astype(f32))), rb(rb(t.x1.astype(f32)) - t.xq)  # utils.py:158-166
+    t.dy0, t.dy1 = rb(t.yq - rb(t.y0.astype(f32))), rb(rb(t.y1.astype(f32)) - t.yq)
+    return t
+
+
+def forward_bf16(x, offset, mask, kernel_size=(3, 3), strides=(1, 1), padding="SAME",
+                 dilation_rate=(1, 1), groups=4, group_channels=16, offset_scale=1.0):
+    """The forward as the reference computes it when x.dtype is bfloat16.  Inputs: float32 arrays holding
+    bf16-representable values.  Weights (utils.py:169-172), the four corner products (:201), their sum (:202,
+    one rounding: the reduction accumulates in fp32), the mask product (:204) and the running output (:206)
+    are each rounded to bf16.  Pinned against tests/golden/op_bf16_*.npz (the unmodified reference run on
+    bf16 tensors through the shim)."""
+    ph, pw = resolve_padding(kernel_size, padding)
+    hin, win, ho, wo = check_shapes(x.shape, offset.shape, mask.shape, kernel_size, strides,
+                                    (ph, pw), dilation_rate, groups, group_channels)
+    n = x.shape[0]
+    p_ = kernel_size[0] * kernel_size[1]
+    xp = np.pad(x.astype(np.float32), [(0, 0), (ph, ph), (pw, pw), (0, 0)])
+    t = _taps_bf16(offset, hin, win, kernel_size, strides, dilation_rate, groups, offset_scale)
+    ia, ib, ic, id_ = _corner_values(xp, t, groups, group_channels)
+    wa, wb = rb(t.dx1 * t.dy1)[..., None], rb(t.dx1 * t.dy0)[..., None]
+    wc, wd = rb(t.dx0 * t.dy1)[..., None], rb(t.dx0 * t.dy0)[..., None]
+    s_ = rb(((rb(ia * wa) + rb(ib * wb)) + rb(ic * wc)) + rb(id_ * wd))
+    m = mask.reshape(n, ho, wo, groups, p_, 1).astype(np.float32)
+    out = np.zeros((n, ho, wo, groups, group_channels), dtype=np.float32)
+    for p in range(p_):
+        out = rb(out + rb(s_[..., p, :] * m[..., p, :]))
+    return out.reshape(n, ho, wo, groups * group_channels)
+
+
+def backward_bf16_coords(x, offset, mask, grad_out, kernel_size=(3, 3), strides=(1, 1), padding="SAME",
+                         dilation_rate=(1, 1), groups=4, group_channels=16, offset_scale=1.0):
+    """Gradients with the sampling cells and bilinear weights of the bf16 reference (_taps_bf16) and fp32
+    gradient arithmetic -- what the kernels compute under DCNV3_FLAG_REF_DTYPE.  (What TF / XLA autodiff does
+    in bf16 -- every backward primitive rounded to bf16, bf16 scatter accumulation -- is an implementation
+    detail that is not reproduced; tests record the distance to the shim's bf16 autograd instead.)"""
+    ph, pw = resolve_padding(kernel_size, padding)
+    hin, win, ho, wo = check_shapes(x.shape, offset.shape, mask.shape, kernel_size, strides,
+                                    (ph, pw), dilation_rate, groups, group_channels)
+    f32 = np.float32
+    n = x.shape[0]
+    p_ = kernel_size[0] * kernel_size[1]
+    xp = np.pad(x.astype(f32), [(0, 0), (ph, ph), (pw, pw), (0, 0)])
+    t = _taps_bf16(offset, hin, win, kernel_size, strides, dilation_rate, groups, offset_scale)
+    ia, ib, ic, id_ = _corner_values(xp, t, groups, group_channels)
+    go = grad_out.reshape(n, ho, wo, groups, 1, group_channels).astype(f32)
+    m = mask.reshape(n, ho, wo, groups, p_).astype(f32)
+    wa, wb, wc, wd = t.dx1 * t.dy1, t.dx1 * t.dy0, t.dx0 * t.dy1, t.dx0 * t.dy0
+    da, db = (go * ia).sum(-1), (go * ib).sum(-1)
+    dc, dd = (go * ic).sum(-1), (go * id_).sum(-1)
+    grad_mask = ((wa * da + wb * db) + wc * dc) + wd * dd
+    g_xq = m * (t.dy1 * (dc - da) + t.dy0 * (dd - db))
+    g_yq = m * (t.dx1 * (db - da) + t.dx0 * (dd - dc))
+    s = f32(offset_scale)
+    fx, fy = f32(win - 2) * s / f32(win), f32(hin - 2) * s / f32(hin)
+    grad_offset = np.stack([g_xq * fx, g_yq * fy], axis=-1).reshape(offset.shape).astype(f32)
+    gxp = np.zeros((n, hin, win, groups, group_channels), dtype=np.float64)
+    nn = np.broadcast_to(np.arange(n).reshape(n, 1, 1, 1, 1), t.x0.shape)
+    gg = np.broadcast_to(np.arange(groups).reshape(1, 1, 1, groups, 1), t.x0.shape)
+    gs = go * m[..., None]
+    for (yy, xx, w_) in ((t.y0, t.x0, wa), (t.y1, t.x0, wb), (t.y0, t.x1, wc), (t.y1, t.x1, wd)):
+        np.add.at(gxp, (nn, yy, xx, gg), gs * w_[..., None])
+    grad_x = gxp[:, ph:hin - ph, pw:win - pw].reshape(x.shape)
+    return np.ascontiguousarray(grad_x).astype(f32), grad_offset, grad_mask.reshape(mask.shape).astype(f32)
+
+
 def mask_softmax(logits, groups):
     """layers/dcn_v3/dcn_v3.py:120-123 -- softmax over the P taps of each group."""
     n, h, w, gp = logits.shape

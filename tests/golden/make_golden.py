@@ -87,6 +87,45 @@ def make_op_case(name, spec):
         offset_scale=np.array(scale, dtype="f8"))
 
 
+# The reference under the mixed_bfloat16 policy: the same unmodified source run on bfloat16 tensors (every
+# primitive then rounds to bf16, op.py:62-87 / utils.py:130-206).  Stored as uint16 bf16 bit patterns
+# (tests/helpers.py load_op_case widens them to float32).
+# name: (N, H, W, G, gc, offset_scale, offset_sigma, seed)   -- 3x3, stride 1, SAME (the InternImage configuration);
+# offset scales are bf16-representable (a python scalar becomes a tensor of x.dtype in TF)
+BF16_CASES = {
+    "bf16_32x32_g4c16": (1, 32, 32, 4, 16, 1.0, 1.0, 20),
+    "bf16_136x24_g2c16": (1, 136, 24, 2, 16, 1.0, 1.0, 21),   # coordinates beyond 128: bf16 step of 1 pixel
+    "bf16_17x23_g2c16_s2": (2, 17, 23, 2, 16, 2.0, 2.0, 22),
+    "bf16_12x12_g3c8_s0.5": (1, 12, 12, 3, 8, 0.5, 4.0, 23),
+    "bf16_24x24_g8c16": (1, 24, 24, 8, 16, 1.0, 1.0, 24),
+}
+
+
+def make_bf16_case(name, spec):
+    import torch
+
+    n, h, w, g, gc, scale, sigma, seed = spec
+    rng = np.random.default_rng(seed)
+    ref = ref_runner.load()
+    bf = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).bfloat16()  # noqa: E731
+    x = bf(rng.standard_normal((n, h, w, g * gc)))
+    offset = bf(sigma * rng.standard_normal((n, h, w, g * 18)))
+    mask = bf(softmax_taps(rng.standard_normal((n, h, w, g * 9)), g))
+    grad_out = bf(rng.standard_normal((n, h, w, g * gc)))
+    tx, to, tm = (ref.tf.convert_to_tensor(t.clone()) for t in (x, offset, mask))
+    tx.requires_grad_(True), to.requires_grad_(True), tm.requires_grad_(True)
+    out = ref.dcnv3_op(tx, to, tm, [3, 3], [1, 1], "SAME", [1, 1], g, gc, scale)
+    assert out.dtype == torch.bfloat16
+    out.backward(grad_out)
+    f = lambda t: t.detach().contiguous().view(torch.int16).numpy().view(np.uint16)  # noqa: E731  (bf16 bits)
+    np.savez_compressed(
+        os.path.join(OUT, f"op_{name}.npz"), bf16_bits=np.array(1), x=f(x), offset=f(offset), mask=f(mask), grad_out=f(grad_out),
+        out=f(out), grad_x=f(tx.grad), grad_offset=f(to.grad), grad_mask=f(tm.grad),
+        kernel_size=np.array((3, 3)), strides=np.array((1, 1)), dilation_rate=np.array((1, 1)),
+        padding=np.array("SAME"), groups=np.array(g), group_channels=np.array(gc),
+        offset_scale=np.array(scale, dtype="f8"))
+
+
 def make_kats():
     """Known answers that are also derivable by hand."""
     h = w = 6
@@ -172,6 +211,9 @@ if __name__ == "__main__":
     assert ref_runner.available(), "needs /root/reference"
     for nm, sp in OP_CASES.items():
         make_op_case(nm, sp)
+        print("wrote", nm)
+    for nm, sp in BF16_CASES.items():
+        make_bf16_case(nm, sp)
         print("wrote", nm)
     make_kats()
     make_layer_case()

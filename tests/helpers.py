@@ -7,12 +7,16 @@ import numpy as np
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def golden_op_cases():
-    return sorted(os.path.basename(p)[3:-4] for p in glob.glob(os.path.join(GOLDEN, "op_*.npz")))
+def golden_op_cases(bf16=False):
+    """fp32 / fp64 fixtures by default; bf16=True: the reference run on bfloat16 tensors (op_bf16_*)."""
+    names = sorted(os.path.basename(p)[3:-4] for p in glob.glob(os.path.join(GOLDEN, "op_*.npz")))
+    return [n for n in names if n.startswith("bf16_") == bf16]
 
 
 def load_op_case(name):
     z = np.load(os.path.join(GOLDEN, f"op_{name}.npz"))
+    if "bf16_bits" in z.files:  # bfloat16 fixtures are stored as uint16 bit patterns: widen to float32
+        z = {k: ((z[k].astype(np.uint32) << 16).view(np.float32) if z[k].dtype == np.uint16 else z[k]) for k in z.files}
     kw = dict(kernel_size=tuple(int(v) for v in z["kernel_size"]),
               strides=tuple(int(v) for v in z["strides"]),
               padding=str(z["padding"]),

@@ -29,14 +29,15 @@ def cuda(*arrs, dtype=torch.float32):
     return [torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dtype) for a in arrs]
 
 
-def run_op(ops, x, off, m, go=None, dtype=torch.float32, mask_is_logits=False, **kw):
+def run_op(ops, x, off, m, go=None, dtype=torch.float32, mask_is_logits=False, reference_dtype_math=False, **kw):
     iseg, _ = ops
     tx, to, tm = cuda(x, off, m, dtype=dtype)
     if go is not None:
         tx.requires_grad_(True), to.requires_grad_(True), tm.requires_grad_(True)
     out = iseg.dcnv3_op(tx, to, tm, list(kw.get("kernel_size", (3, 3))), list(kw.get("strides", (1, 1))),
                         kw.get("padding", "SAME"), list(kw.get("dilation_rate", (1, 1))), kw["groups"],
-                        kw["group_channels"], kw.get("offset_scale", 1.0), mask_is_logits=mask_is_logits)
+                        kw["group_channels"], kw.get("offset_scale", 1.0), mask_is_logits=mask_is_logits,
+                        reference_dtype_math=reference_dtype_math)
     if go is None:
         return out.float().cpu().numpy()
     out.backward(cuda(go, dtype=dtype)[0])
@@ -51,6 +52,38 @@ def test_golden_fp32(ops, name):
     assert rel_err(gx, z["grad_x"]) <= TOL_F32
     assert rel_err(goff, z["grad_offset"]) <= TOL_F32
     assert rel_err(gm, z["grad_mask"]) <= TOL_F32
+
+
+@pytest.mark.parametrize("name", golden_op_cases(bf16=True))
+def test_golden_bf16_reference_dtype(ops, name):
+    """The reference run on bfloat16 tensors (tests/golden/op_bf16_*, made by executing its unmodified source
+    in bf16).  With reference_dtype_math=True the kernels round every intermediate as the reference does: the
+    forward matches bit for bit or to one bf16 ulp, all four results within the 1e-2 bar of north_star."""
+    z, kw = load_op_case(name)
+    out, gx, goff, gm = run_op(ops, z["x"], z["offset"], z["mask"], z["grad_out"], dtype=torch.bfloat16,
+                               reference_dtype_math=True, **kw)
+    assert rel_err(out, z["out"]) <= TOL_BF16
+    assert (out != z["out"]).mean() < 1e-3   # essentially bit-exact (exp / division free path: identical roundings)
+    assert rel_err(gx, z["grad_x"]) <= TOL_BF16
+    assert rel_err(goff, z["grad_offset"]) <= TOL_BF16
+    assert rel_err(gm, z["grad_mask"]) <= TOL_BF16
+    # the default bf16 mode keeps coordinates in fp32: a different (documented) result
+    out32 = run_op(ops, z["x"], z["offset"], z["mask"], dtype=torch.bfloat16, **kw)
+    assert rel_err(out32, c_oracle.forward(z["x"], z["offset"], z["mask"], **kw)) <= TOL_BF16
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 8, 16, 1.0, 1.0), (1, 160, 160, 10, 16, 1.0, 2.0), (1, 193, 193, 4, 16, 1.0, 1.0)])
+def test_random_bf16_reference_dtype_vs_oracle(ops, case):
+    n, h, w, g, gc, sigma, scale = case
+    x, off, m, go = make_inputs(n, h, w, g, gc, sigma=sigma, seed=3 + h)
+    rnd = lambda a: torch.from_numpy(a).bfloat16().float().numpy()  # noqa: E731
+    x, off, m, go = rnd(x), rnd(off), rnd(m), rnd(go)
+    kw = dict(groups=g, group_channels=gc, offset_scale=scale)
+    out, gx, goff, gm = run_op(ops, x, off, m, go, dtype=torch.bfloat16, reference_dtype_math=True, **kw)
+    ref = O.forward_bf16(x, off, m, **kw)
+    assert rel_err(out, ref) <= TOL_BF16 and (out != ref).mean() < 1e-3
+    rx, roff, rm = O.backward_bf16_coords(x, off, m, go, **kw)
+    assert rel_err(gx, rx) <= TOL_BF16 and rel_err(goff, roff) <= TOL_BF16 and rel_err(gm, rm) <= TOL_BF16
 
 
 def test_known_answers(ops):
@@ -319,6 +352,115 @@ def test_layer_matches_reference_layer(ops):
             with torch.no_grad():
                 y = layer(torch.from_numpy(z["x"]).cuda()).cpu().numpy()
             assert rel_err(y, z["y"]) <= 5e-5, (name, fuse)  # dense / conv / LN around the op are cuBLAS / cuDNN
+
+
+FULL_CASES = [  # dtype, (n, h, w, g, gc), offset_scale -- BASELINE.json configs at their full sizes
+    (torch.float32, (16, 128, 128, 4, 16), 1.0),   # config 2: InternImage-T at a 512 crop, batch 16, stages 1-4
+    (torch.float32, (16, 64, 64, 8, 16), 1.0),
+    (torch.float32, (16, 32, 32, 16, 16), 1.0),
+    (torch.float32, (16, 16, 16, 32, 16), 1.0),
+    (torch.bfloat16, (16, 128, 128, 4, 16), 1.0),
+    (torch.bfloat16, (16, 64, 64, 8, 16), 1.0),
+    (torch.bfloat16, (16, 32, 32, 16, 16), 1.0),
+    (torch.bfloat16, (16, 16, 16, 32, 16), 1.0),
+    (torch.bfloat16, (4, 160, 160, 10, 16), 2.0),  # config 4: InternImage-L at a 640 crop, stage 1 (4 images) ...
+    (torch.bfloat16, (16, 20, 20, 80, 16), 2.0),   # ... and stage 4 (G = 80)
+    (torch.bfloat16, (2, 193, 193, 4, 16), 1.0),   # config 5: 769x769 sliding-window tiles, stage 1
+]
+
+
+@pytest.mark.parametrize("dtype,shape,scale", FULL_CASES)
+def test_full_size_vs_c_oracle(ops, dtype, shape, scale):
+    """Full-size configurations against the oracle itself (not only through properties): the C restatement
+    does the 9.4 M sampled points of stage 1 at batch 16 in about a second."""
+    n, h, w, g, gc = shape
+    x, off, m, go = make_inputs(n, h, w, g, gc, sigma=1.0, seed=h + g)
+    tol = TOL_F32
+    if dtype == torch.bfloat16:
+        rnd = lambda a: torch.from_numpy(a).bfloat16().float().numpy()  # noqa: E731
+        x, off, m, go = rnd(x), rnd(off), rnd(m), rnd(go)
+        tol = TOL_BF16
+    kw = dict(groups=g, group_channels=gc, offset_scale=scale)
+    out, gx, goff, gm = run_op(ops, x, off, m, go, dtype=dtype, **kw)
+    assert rel_err(out, c_oracle.forward(x, off, m, **kw)) <= tol
+    rx, roff, rm = c_oracle.backward(x, off, m, go, **kw)
+    assert rel_err(gx, rx) <= tol and rel_err(goff, roff) <= tol and rel_err(gm, rm) <= tol
+
+
+@pytest.mark.parametrize("flags", ["tiled", "generic"])
+def test_grad_x_batch_invariant_and_wide_range(ops, flags):
+    """The fixed-point scale of grad_x comes from each image's own max|grad_out|: an image's gradient is
+    bit-identical whether it is alone or shares the batch with images whose grad_out is 1e6 times larger or
+    smaller, and every image keeps fp32-like accuracy relative to its own magnitude."""
+    _, cabi = ops
+    n, h, w, g, gc = 4, 40, 48, 4, 16
+    x, off, m, go = make_inputs(n, h, w, g, gc, sigma=1.5, seed=77)
+    scales = np.array([1.0, 1e6, 1e-6, 3e3], np.float32).reshape(n, 1, 1, 1)
+    go = go * scales
+    cfg = ((3, 3), (1, 1), (1, 1), (1, 1), g, gc, 1.0)
+    fl = cabi.FLAG_FORCE_GENERIC if flags == "generic" else 0
+    t = [torch.from_numpy(a).cuda() for a in (x, off, m, go)]
+    gx, goff, gm = (v.cpu().numpy() for v in cabi.backward(*t, *cfg, flags=fl))
+    rx, roff, rm = c_oracle.backward(x, off, m, go, groups=g, group_channels=gc)
+    for i in range(n):
+        assert rel_err(gx[i], rx[i]) <= TOL_F32, i      # per image: relative to the image's own maximum
+        alone = [torch.from_numpy(a[i:i + 1]).cuda() for a in (x, off, m, go)]
+        gxi = cabi.backward(*alone, *cfg, flags=fl)[0].cpu().numpy()
+        assert np.array_equal(gxi[0], gx[i]), i          # batch invariance, bit for bit
+    assert rel_err(goff, roff) <= TOL_F32 and rel_err(gm, rm) <= TOL_F32
+
+
+@pytest.mark.parametrize("flags", ["tiled", "generic"])
+@pytest.mark.parametrize("bad", [float("nan"), float("inf")])
+def test_non_finite_grad_out_is_not_swallowed(ops, flags, bad):
+    """A NaN / Inf in grad_out cannot be carried by integer accumulation; instead of disappearing (fmaxf skips
+    NaN, float -> int of NaN is 0) it turns that image's grad_x into NaN, so found-inf checks fire.  Other
+    images of the batch are untouched, and the workspace is left clean."""
+    _, cabi = ops
+    n, h, w, g, gc = 3, 36, 36, 4, 16
+    x, off, m, go = make_inputs(n, h, w, g, gc, seed=5)
+    go[1, 7, 9, 3] = bad
+    cfg = ((3, 3), (1, 1), (1, 1), (1, 1), g, gc, 1.0)
+    fl = cabi.FLAG_FORCE_GENERIC if flags == "generic" else 0
+    t = [torch.from_numpy(a).cuda() for a in (x, off, m, go)]
+    gx, goff, gm = (v.cpu().numpy() for v in cabi.backward(*t, *cfg, flags=fl))
+    assert np.isnan(gx[1]).all()
+    assert not np.isfinite(goff[1, 7, 9]).all() or not np.isfinite(gm[1, 7, 9]).all()
+    go[1, 7, 9, 3] = 0.0
+    rx, _, _ = c_oracle.backward(x, off, m, go, groups=g, group_channels=gc)
+    assert rel_err(gx[0], rx[0]) <= TOL_F32 and rel_err(gx[2], rx[2]) <= TOL_F32
+    t[3] = torch.from_numpy(go).cuda()
+    gx2 = cabi.backward(*t, *cfg, flags=fl)[0].cpu().numpy()  # same cached workspace: must have been left zeroed
+    assert rel_err(gx2, rx) <= TOL_F32
+
+
+def test_two_threads_two_streams(ops):
+    """Re-entrancy: two host threads drive the library concurrently on their own streams (the reference's
+    MirroredStrategy runs one host thread per replica); results are those of the sequential run."""
+    import threading
+    iseg, _ = ops
+    cases = [(2, 48, 40, 4, 16, 11), (3, 33, 57, 6, 16, 12)]
+    want, got, errs = {}, {}, []
+    data = {}
+    for i, (n, h, w, g, gc, seed) in enumerate(cases):
+        data[i] = (make_inputs(n, h, w, g, gc, seed=seed), dict(groups=g, group_channels=gc))
+        want[i] = run_op(ops, *data[i][0], **data[i][1])
+
+    def worker(i):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for _ in range(20):
+                    got[i] = run_op(ops, *data[i][0], **data[i][1])
+                torch.cuda.current_stream().synchronize()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in data]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for i in data:
+        assert all(np.array_equal(a, b) for a, b in zip(got[i], want[i])), i
 
 
 @pytest.mark.parametrize("dtype,shape,scale", [

@@ -34,6 +34,38 @@ def test_c_oracle_matches_golden(name):
     assert rel_err(gm, z["grad_mask"]) < 2e-6
 
 
+# what the default bf16 path (fp32 coordinates) is known to differ by from the reference's own bf16 arithmetic
+BF16_COORD_DEVIATION = {}
+
+
+@pytest.mark.parametrize("name", golden_op_cases(bf16=True))
+def test_bf16_oracle_matches_reference_run_in_bf16(name):
+    """tests/golden/op_bf16_*: the unmodified reference source executed on bfloat16 tensors.  The bf16
+    restatement (every primitive rounded to bf16 in the reference's op order) reproduces its forward BIT for
+    bit; gradients formed in fp32 from the same bf16 cells / weights stay within the 1e-2 bar of its bf16
+    autograd.  The fp32-coordinate arithmetic (the kernels' default bf16 mode) does NOT: it samples different
+    cells wherever bf16 coordinates collapse (step 1 pixel beyond 128)."""
+    z, kw = load_op_case(name)
+    x, off, m, go = z["x"], z["offset"], z["mask"], z["grad_out"]
+    assert np.array_equal(O.forward_bf16(x, off, m, **kw), z["out"])
+    gx, goff, gm = O.backward_bf16_coords(x, off, m, go, **kw)
+    assert rel_err(gx, z["grad_x"]) <= 1e-2
+    assert rel_err(goff, z["grad_offset"]) <= 1e-2
+    assert rel_err(gm, z["grad_mask"]) <= 1e-2
+    dev = rel_err(O.forward(x, off, m, **kw), z["out"])
+    BF16_COORD_DEVIATION[name] = dev
+    assert dev > 1e-2  # documented, not hidden: DESIGN.md section 2, bench.py "bf16_reference_deviation"
+
+
+def test_rb_is_round_to_nearest_even_bf16():
+    import torch
+    rng = np.random.default_rng(1)
+    a = np.concatenate([rng.standard_normal(4096).astype(np.float32) * 10.0 ** rng.integers(-20, 20, 4096),
+                        np.array([0.0, -0.0, 1.0, 1.00390625, 1.005859375, 3.0e38, -3.4e38, 1e-40], np.float32)])
+    want = torch.from_numpy(a).bfloat16().float().numpy()
+    assert np.array_equal(O.rb(a).view(np.uint32), want.view(np.uint32))
+
+
 def test_known_answers():
     z = np.load(f"{GOLDEN}/kat_ramp.npz")
     kw = dict(groups=2, group_channels=1)
