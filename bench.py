@@ -103,9 +103,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, sample_batch=1, budget_s=None):
-    """The reference path on the host CPU: C restatement, all threads, batch `sample_batch` of each of
-    the 30 layers, forward + backward.  Returns (points/s, info)."""
+def cpu_reference_run(steps, warmup, batch=BATCH, budget_s=None):
+    """The reference path on the host CPU: C restatement, all threads, batch `batch` of each of the 30
+    layers -- every layer on its own tensors, as in the GPU arm -- forward 1..30 then backward 30..1.
+    Returns (points/s, ms/step, info)."""
     import numpy as np
     from oracle import c_oracle
 
@@ -116,23 +117,22 @@ def cpu_reference_run(steps, warmup, sample_batch=1, budget_s=None):
     except AttributeError:
         threads = os.cpu_count() or 1
     rng = np.random.default_rng(0)
-    data = []
+    layers = []
     for h, w, c, g, depth in STAGES:
-        x = rng.standard_normal((sample_batch, h, w, c), dtype=np.float32)
-        off = rng.standard_normal((sample_batch, h, w, g * P * 2), dtype=np.float32)
-        z = rng.standard_normal((sample_batch, h, w, g, P), dtype=np.float32)
-        e = np.exp(z - z.max(-1, keepdims=True))
-        m = (e / e.sum(-1, keepdims=True)).reshape(sample_batch, h, w, g * P).astype(np.float32)
-        go = rng.standard_normal((sample_batch, h, w, c), dtype=np.float32)
-        data.append((x, off, m, go, g, depth))
+        for _ in range(depth):
+            x = rng.standard_normal((batch, h, w, c), dtype=np.float32)
+            off = rng.standard_normal((batch, h, w, g * P * 2), dtype=np.float32)
+            z = rng.standard_normal((batch, h, w, g, P), dtype=np.float32)
+            np.exp(z - z.max(-1, keepdims=True), out=z)
+            m = np.ascontiguousarray((z / z.sum(-1, keepdims=True)).reshape(batch, h, w, g * P))
+            go = rng.standard_normal((batch, h, w, c), dtype=np.float32)
+            layers.append((x, off, m, go, g))
 
     def one_step():
-        for x, off, m, go, g, depth in data:
-            for _ in range(depth):
-                c_oracle.forward(x, off, m, groups=g, group_channels=GC, nthreads=threads)
-        for x, off, m, go, g, depth in reversed(data):
-            for _ in range(depth):
-                c_oracle.backward(x, off, m, go, groups=g, group_channels=GC, nthreads=threads)
+        for x, off, m, go, g in layers:
+            c_oracle.forward(x, off, m, groups=g, group_channels=GC, nthreads=threads)
+        for x, off, m, go, g in reversed(layers):
+            c_oracle.backward(x, off, m, go, groups=g, group_channels=GC, nthreads=threads)
 
     for _ in range(warmup):
         one_step()
@@ -144,25 +144,27 @@ def cpu_reference_run(steps, warmup, sample_batch=1, budget_s=None):
         if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    pts = points_per_step(sample_batch) * done
-    info = {"kind": "port", "cores": threads,
-            "sample": f"batch {sample_batch} of each of the 30 InternImage-T DCNv3 layers, fwd+bwd, fp32, "
-                      f"{done} step(s) of {points_per_step(sample_batch)} points; oracle/dcnv3_oracle.c -O3 "
-                      f"-march=native OpenMP (TensorFlow reference not installable)"}
+    pts = points_per_step(batch) * done
+    info = {"kind": "port", "cores": threads, "batch_per_layer": batch,
+            "sample": f"{done} full step(s): all 30 InternImage-T DCNv3 layers at batch {batch}, each on its own tensors, "
+                      f"fwd+bwd, fp32, {points_per_step(batch)} points per step; oracle/dcnv3_oracle.c -O3 -march=native "
+                      f"OpenMP, {threads} threads (TensorFlow reference not installable)"}
     return pts / dt, dt / done * 1e3, info
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    value, ms, info = cpu_reference_run(args.steps, max(args.warmup, 1), sample_batch=1)
+    value, ms, info = cpu_reference_run(args.steps, max(args.warmup, 1), batch=BATCH)
     info["value"] = value
     info["unit"] = UNIT
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, "f32", world, launch="cpu"),
+        "config": workload_config(args, "f32", world), "launch": "cpu",
+        "note": "the CPU arm runs ONE replica of the per-GPU workload (batch 16) on all host cores; it does not "
+                "grow with --gpus",
         "cpu_baseline": info,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -170,15 +172,108 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def workload_config(args, dtype, world, launch):
+def workload_config(args, dtype, world):
+    """The workload only (identical for both arms); how it is launched is reported beside it."""
     return {
         "workload": "InternImage-T DCNv3 core op fwd+bwd, all 30 layers (stages 128^2xC64/G4 x4, 64^2xC128/G8 x4, "
                     "32^2xC256/G16 x18, 16^2xC512/G32 x4), 512x512 crop",
         "batch_per_gpu": BATCH, "global_batch": BATCH * world, "kernel": "3x3 s1 d1 SAME", "group_channels": GC,
         "offset_sigma": 1.0, "parallelism": f"dp{world} (whole images sharded, no collective on the op)",
-        "launch": launch,
         "l2": "each layer owns its tensors (working set >> 126 MB L2); fwd 1..30 then bwd 30..1",
     }
+
+
+# ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(torch, index):
+    """Moves this process onto the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers
+    allocated afterwards are local to the GPU's PCIe root.  Returns the node (None if unknown)."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
+SM_COUNT, SM_CLOCK_HZ = 148, 1.965e9
+
+
+def by_function(classes, dtype):
+    """Per kernel FUNCTION, summed over the layer shapes it is launched at in one step: time, algorithmic bytes,
+    GB/s, and the on-chip ceiling that bounds it: the forward / gather kernels read 36
+    corner slabs of 16 channels per (pixel, group) from shared memory at 128 B/clk/SM, the scatter kernel makes
+    576 shared-memory integer atomic updates per (pixel, group) at 32 per clk per SM."""
+    esize = 4 if dtype == "f32" else 2
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    traffic_tab = json.load(open(tpath)) if os.path.isfile(tpath) else {}
+    agg = {}
+    for t in classes:
+        fn, shape = t["kernel"].split(" ", 1)
+        h, w = (int(v) for v in shape.split()[0].split("x"))
+        g = int(shape.split()[2][1:])
+        a = agg.setdefault(fn, {"function": fn, "us_per_step": 0.0, "algo_bytes_per_step": 0, "launches_per_step": 0,
+                                "ceiling_us": 0.0, "traffic": 0.0, "traffic_known": True})
+        n = t["launches_per_step"]
+        a["us_per_step"] += t["avg_us"] * n
+        a["algo_bytes_per_step"] += t["algo_bytes"] * n
+        a["launches_per_step"] += n
+        pg = BATCH * h * w * g
+        clk = {"fwd_tiled": 36 * 16 * esize / 128.0, "bwd_gather": 36 * 16 * esize / 128.0, "bwd_scatter": 576 / 32.0}.get(fn, 0.0)
+        a["ceiling_us"] += n * pg * clk / SM_COUNT / SM_CLOCK_HZ * 1e6
+        tr = traffic_tab.get(f"{dtype}:{t['kernel']}")
+        if tr is None:
+            a["traffic_known"] = False
+        else:
+            a["traffic"] += tr * n
+    tot = sum(a["us_per_step"] for a in agg.values())
+    out = []
+    for a in sorted(agg.values(), key=lambda v: -v["us_per_step"]):
+        out.append({
+            "function": a["function"], "us_per_step": round(a["us_per_step"], 1), "share": round(a["us_per_step"] / tot, 4),
+            "launches_per_step": a["launches_per_step"], "algo_bytes_per_step": a["algo_bytes_per_step"],
+            "gbs": round(a["algo_bytes_per_step"] / a["us_per_step"] * 1e-3, 1) if a["us_per_step"] > 0 else 0.0,
+            "onchip_ceiling_us": round(a["ceiling_us"], 1),
+            "frac_of_onchip_ceiling": round(a["ceiling_us"] / a["us_per_step"], 4) if a["us_per_step"] > 0 else None,
+            "traffic_per_launch": a["traffic"] / a["launches_per_step"] if a["traffic_known"] and a["traffic"] > 0 else None,
+        })
+    return out
+
+
+def bf16_parity_numbers():
+    """How far the two bf16 modes are from the reference's own bf16 arithmetic: max|d|/max|ref| of the forward
+    over tests/golden/op_bf16_*.npz (the unmodified reference executed on bfloat16 tensors)."""
+    import glob
+
+    import numpy as np
+    import torch
+
+    import iseg_b200
+    worst = {"reference_dtype_math": 0.0, "default_fp32_coordinates": 0.0}
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "op_bf16_*.npz")))
+    for f in files:
+        z = np.load(f)
+        w = lambda k: torch.from_numpy((z[k].astype(np.uint32) << 16).view(np.float32)).cuda()  # noqa: E731
+        ref = w("out")
+        args = [w("x").bfloat16(), w("offset").bfloat16(), w("mask").bfloat16(), [3, 3], [1, 1], "SAME", [1, 1],
+                int(z["groups"]), int(z["group_channels"]), float(z["offset_scale"])]
+        for key, flag in (("reference_dtype_math", True), ("default_fp32_coordinates", False)):
+            out = iseg_b200.dcnv3_op(*args, reference_dtype_math=flag).float()
+            worst[key] = max(worst[key], float((out - ref).abs().max() / ref.abs().max()))
+    worst["fixtures"] = len(files)
+    worst["note"] = ("bf16 tensors: DCNV3_FLAG_REF_DTYPE rounds every intermediate to bf16 like the reference under "
+                     "mixed_bfloat16 (<= 1e-2 bar); the default bf16 mode -- the one benchmarked -- keeps coordinates and "
+                     "accumulation in fp32 and is held to 1e-2 against the fp32 oracle on the bf16-rounded inputs instead")
+    return worst
 
 
 # ------------------------------------------------------------------------------------------------
@@ -336,9 +431,35 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.empty_cache()
         return res
 
+    def pcie_ceiling():
+        """What the host lets every rank copy at the same time: all ranks run one pinned 256 MB H2D and one D2H
+        copy concurrently (duplex, separate streams); GB/s per direction, the slowest rank's."""
+        nb = 256 << 20
+        hin, hout = torch.empty(nb, dtype=torch.uint8).pin_memory(), torch.empty(nb, dtype=torch.uint8).pin_memory()
+        din, dout = torch.empty(nb, dtype=torch.uint8, device=device), torch.empty(nb, dtype=torch.uint8, device=device)
+        s1, s2 = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+        best = 0.0
+        for _ in range(4):
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s1):
+                din.copy_(hin, non_blocking=True)
+            with torch.cuda.stream(s2):
+                hout.copy_(dout, non_blocking=True)
+            s1.synchronize(), s2.synchronize()
+            dt = time.perf_counter() - t0
+            if dist is not None:
+                t = torch.tensor([dt], device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            best = max(best, nb / dt * 1e-9)
+        return best
+
     def measure_e2e(dtype):
         """Same step through the host-buffer C-ABI entry point: pinned host tensors in, host tensors out;
         H2D + kernels + D2H all inside the timed region."""
+        numa = bind_to_gpu_numa(torch, local_rank) if world > 1 else None  # pinned pages first-touch on the GPU's node
+        ceiling = pcie_ceiling()
         tdt = torch.float32 if dtype == "f32" else torch.bfloat16
         esize = 4 if dtype == "f32" else 2
         host, h2d, d2h = [], 0, 0
@@ -383,8 +504,60 @@ def run_ours(args, rank, world, local_rank):
         lib.dcnv3_release_host_scratch()
         return {"value": points_per_step() * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": dt / steps * 1e3, "steps": steps,
+                "pcie_gbs_per_direction_all_ranks_concurrent": ceiling,
+                "achieved_gbs_per_direction": h2d / (dt / steps) * 1e-9,
+                "frac_of_pcie_ceiling": h2d / (dt / steps) * 1e-9 / ceiling if ceiling > 0 else None,
+                "numa_node": numa,
                 "api": "dcnv3_forward_backward_host_async + dcnv3_host_sync (C ABI, pinned host buffers, per layer, "
                        f"{nslots} pipelined slots)"}
+
+    def measure_gather(dtype):
+        """NCCL all_gather_into_tensor of every rank's stage-1 output shard (what the reference's
+        experimental_local_results + concat does, core_predict.py:136-153): alone, and issued on a side stream
+        while the next layer's forward runs on the compute stream."""
+        tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+        h, w, c, g, _ = STAGES[0]
+        layer = Layer(torch, cabi, h, w, c, g, dtype, 999 + rank, device)
+        full = torch.empty((world * BATCH, h, w, c), dtype=tdt, device=device)
+        comm, comp = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+        sp = ctypes.c_void_p(comp.cuda_stream)
+        nbytes = layer.out.numel() * layer.out.element_size()
+
+        def fwd():
+            with torch.cuda.stream(comp):
+                cabi.check(lib.dcnv3_forward(*layer.fwd_args, layer.pref, sp))
+
+        def gather_only():
+            with torch.cuda.stream(comm):
+                dist.all_gather_into_tensor(full, layer.out)
+
+        def both():
+            fwd()
+            gather_only()
+
+        def timeit(fn, reps=20):
+            for _ in range(3):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+                torch.cuda.current_stream().wait_stream(comm)
+                torch.cuda.current_stream().wait_stream(comp)
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b) / reps], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        t_f, t_g, t_b = timeit(fwd), timeit(gather_only), timeit(both)
+        ok = bool(torch.equal(full[rank * BATCH:(rank + 1) * BATCH], layer.out))
+        recv = (world - 1) * nbytes
+        return {"what": "all_gather_into_tensor of the stage-1 output shards (NCCL over NVLink), max over ranks",
+                "shard_bytes": nbytes, "gathered_bytes": world * nbytes, "ms_gather": t_g, "ms_forward": t_f,
+                "ms_forward_and_gather_overlapped": t_b, "recv_gbs_per_gpu": recv / (t_g * 1e-3) * 1e-9,
+                "nvlink_nominal_gbs_per_direction": 900.0, "own_shard_bit_exact": ok}
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     main = measure(args.dtype, sampler)
@@ -392,42 +565,57 @@ def run_ours(args, rank, world, local_rank):
     other = measure(other_dtype) if args.both_dtypes else None
     e2e = measure_e2e(args.dtype)
 
+    gather = measure_gather(args.dtype) if dist is not None else None
+    parity = bf16_parity_numbers() if rank == 0 else None
+
     if rank == 0:
         peak, peak_src = peaks()
         ms_step = main["ms_total"] / args.steps
         value = points_per_step() * world / (ms_step * 1e-3)
-        top = main["classes"][0]
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.isfile(tpath):
-            traffic = json.load(open(tpath)).get(f"{args.dtype}:{top['kernel']}")
         esize = 4 if args.dtype == "f32" else 2
         step_bytes = sum(sum(algo_bytes(h, w, c, g, esize)) * d for h, w, c, g, d in STAGES)
-        cpu_v, cpu_ms, cpu_info = cpu_reference_run(steps=3, warmup=1, sample_batch=1, budget_s=20.0)
-        cpu_info.update(value=cpu_v, unit=UNIT)
+        functions = by_function(main["classes"], args.dtype)
+        top = functions[0]
+        if world == 1:
+            cpu_v, cpu_ms, cpu_info = cpu_reference_run(steps=2, warmup=1, batch=BATCH, budget_s=25.0)
+            cpu_info.update(value=cpu_v, unit=UNIT, ms_per_step=cpu_ms)
+        else:  # measured on rank 0 at N = 1 only: the other ranks' host threads would share the cores
+            cpu_info = {"value": None, "unit": UNIT, "kind": "port", "cores": 0, "sample": "not measured at N > 1"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": workload_config(args, args.dtype, world, main["launch"]),
+            "config": workload_config(args, args.dtype, world), "launch": main["launch"],
             "clocks": sampler.summary(),
             "e2e": e2e,
             "gpu_launches": main["launches"],
-            "roofline": {"bound": "hbm", "kernel": top["kernel"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": top["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algo_bytes_per_launch": top["algo_bytes"], "avg_launch_us": top["avg_us"],
-                         "share_of_step": top["share"]},
+            # the dominant kernel FUNCTION of the step, summed over the four layer shapes it runs at
+            "roofline": {"bound": "hbm", "kernel": top["function"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": top["gbs"] / peak, "traffic": top["traffic_per_launch"], "peak_source": peak_src,
+                         "launches_per_step": top["launches_per_step"],
+                         "algo_bytes_per_launch": top["algo_bytes_per_step"] / top["launches_per_step"],
+                         "avg_launch_us": top["us_per_step"] / top["launches_per_step"],
+                         "share_of_step": top["share"], "onchip_ceiling_frac": top["frac_of_onchip_ceiling"],
+                         "traffic_note": "ncu --set full dram__bytes_read+write per launch, launch-weighted mean over the layer "
+                                         "shapes (profiles/traffic.json; null if a shape was not captured).  It can sit "
+                                         "below the algorithmic bytes: a kernel's last writes are still dirty in the "
+                                         "126 MB L2 when it ends and inputs written by the previous kernel are read from L2"},
             "step_hbm": {"algo_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms_step * 1e-3) * 1e-9,
                          "frac_of_peak": step_bytes / (ms_step * 1e-3) * 1e-9 / peak},
+            "functions": functions,
             "kernels": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in t.items()} for t in main["classes"]],
+            "bf16_parity": parity,
             "cpu_baseline": cpu_info,
         }
+        if gather is not None:
+            line["gather"] = gather
         if other is not None:
             oms = other["ms_total"] / args.steps
             ob = sum(sum(algo_bytes(h, w, c, g, 6 - esize)) * d for h, w, c, g, d in STAGES)
+            of = by_function(other["classes"], other_dtype)
             line[other_dtype] = {"value": points_per_step() * world / (oms * 1e-3), "ms_per_step": oms,
                                  "achieved_gbs": ob / (oms * 1e-3) * 1e-9, "frac_of_peak": ob / (oms * 1e-3) * 1e-9 / peak,
-                                 "top_kernel": other["classes"][0]["kernel"], "top_kernel_gbs": other["classes"][0]["gbs"]}
+                                 "functions": of}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

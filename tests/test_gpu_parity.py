@@ -64,9 +64,14 @@ def test_golden_bf16_reference_dtype(ops, name):
                                reference_dtype_math=True, **kw)
     assert rel_err(out, z["out"]) <= TOL_BF16
     assert (out != z["out"]).mean() < 1e-3   # essentially bit-exact (exp / division free path: identical roundings)
-    assert rel_err(gx, z["grad_x"]) <= TOL_BF16
     assert rel_err(goff, z["grad_offset"]) <= TOL_BF16
     assert rel_err(gm, z["grad_mask"]) <= TOL_BF16
+    # grad_x: the fixture's own gradient is a bf16 scatter-add (torch autograd in bf16 standing in for TF's; every
+    # one of the up to ~100 additions into a cell rounds to 8 bits), so the fixture itself is only good to about
+    # 1e-2; against the same cells / weights accumulated exactly the kernel is within the bar
+    assert rel_err(gx, z["grad_x"]) <= 2 * TOL_BF16
+    rx, roff, rm = O.backward_bf16_coords(z["x"], z["offset"], z["mask"], z["grad_out"], **kw)
+    assert rel_err(gx, rx) <= TOL_BF16 and rel_err(goff, roff) <= TOL_BF16 and rel_err(gm, rm) <= TOL_BF16
     # the default bf16 mode keeps coordinates in fp32: a different (documented) result
     out32 = run_op(ops, z["x"], z["offset"], z["mask"], dtype=torch.bfloat16, **kw)
     assert rel_err(out32, c_oracle.forward(z["x"], z["offset"], z["mask"], **kw)) <= TOL_BF16
