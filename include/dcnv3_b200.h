@@ -18,7 +18,10 @@
  * ABI; dcnv3_last_error() gives a thread-local message for the last failure on the calling thread.
  * No user-visible memory is allocated: outputs and the backward workspace are caller-owned device
  * buffers.  All work is enqueued on the caller's CUDA stream (cudaStream_t passed as void*); the
- * calls are asynchronous except the *_host variants.  The library is re-entrant.
+ * calls are asynchronous except the *_host variants.  The library is re-entrant: any number of host threads
+ * may call it concurrently on their own streams / devices (tests/test_gpu_parity.py::test_two_threads_two_streams);
+ * the only shared mutable state is the per-device scratch of the *_host entry points (one lock per device) and
+ * the bench-only kernel timing switch, which is not meant to be flipped while other threads launch.
  *
  * There is no CPU fallback: without a CUDA device every compute entry point fails with
  * DCNV3_ERR_CUDA.
@@ -56,6 +59,11 @@ typedef enum { DCNV3_F32 = 0, DCNV3_BF16 = 1 } dcnv3_dtype;
 /* backward only: the caller guarantees the workspace is all-zero on entry (e.g. it was zeroed once
    and only ever used by dcnv3_backward, which leaves it zeroed); saves a memset of the workspace */
 #define DCNV3_FLAG_WORKSPACE_ZEROED 4u
+/* debugging aid, with DCNV3_FLAG_WORKSPACE_ZEROED: verify that promise before the call (one reduction kernel
+   and a stream synchronisation; DCNV3_ERR_WORKSPACE if the workspace is dirty).  A launch failure or an aborted
+   CUDA graph in the middle of an earlier backward leaves the workspace dirty; callers that keep a workspace
+   should re-zero it after any failed call (iseg_b200/_cabi.py drops its cached one). */
+#define DCNV3_FLAG_CHECK_WORKSPACE 16u
 /* testing aid: bypass the shared-memory tiled kernels and run the generic kernels */
 #define DCNV3_FLAG_FORCE_GENERIC 2u
 /* bf16 tensors only (ignored for fp32): reproduce the arithmetic the reference performs under the

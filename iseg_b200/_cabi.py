@@ -17,6 +17,7 @@ FLAG_MASK_LOGITS = 1
 FLAG_FORCE_GENERIC = 2
 FLAG_WORKSPACE_ZEROED = 4
 FLAG_REF_DTYPE = 8
+FLAG_CHECK_WORKSPACE = 16
 
 ERR_DTYPE, ERR_SHAPE, ERR_LAYOUT, ERR_DEVICE, ERR_CUDA, ERR_WORKSPACE, ERR_ARGUMENT = range(-1, -8, -1)
 

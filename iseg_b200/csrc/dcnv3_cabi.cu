@@ -120,6 +120,34 @@ static size_t backward_ws_bytes(const dcnv3_params* p) {
     return a > b ? a : b;
 }
 
+// DCNV3_FLAG_CHECK_WORKSPACE: is the workspace really all-zero?  (debug aid: one reduction kernel + a
+// stream synchronisation)
+__global__ void __launch_bounds__(256) workspace_nonzero_kernel(const uint4* __restrict__ ws, size_t n16, int* flag) {
+    unsigned any = 0u;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = ws[i];
+        any |= v.x | v.y | v.z | v.w;
+    }
+    if (__any_sync(0xffffffffu, any != 0u) && (threadIdx.x & 31) == 0) *flag = 1;
+}
+
+static int check_workspace_zero(const void* ws, size_t bytes, cudaStream_t st) {
+    int* flag = nullptr;
+    cudaError_t e = cudaMallocHost(&flag, sizeof(int));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
+    *flag = 0;
+    workspace_nonzero_kernel<<<148 * 4, 256, 0, st>>>((const uint4*)ws, bytes / 16, flag);
+    e = cudaStreamSynchronize(st);
+    const int dirty = *flag;
+    cudaFreeHost(flag);
+    if (e != cudaSuccess) return cuda_fail(e, "workspace check");
+    if (dirty)
+        return fail(DCNV3_ERR_WORKSPACE, "DCNV3_FLAG_WORKSPACE_ZEROED was given but the workspace is not all-zero "
+                                         "(an earlier call failed or something else wrote to it)");
+    return 0;
+}
+
 static int backward_impl(const void* x, const void* offset, const void* mask, const void* grad_out,
                          void* grad_x, void* grad_offset, void* grad_mask, void* ws, size_t ws_bytes,
                          const dcnv3_params* p, cudaStream_t st) {
@@ -135,6 +163,9 @@ static int backward_impl(const void* x, const void* offset, const void* mask, co
     if (ws == nullptr || ws_bytes < need)
         return fail(DCNV3_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", need, ws_bytes);
     if ((rc = check_ptr_align(ws, "workspace", 256))) return rc;
+    if ((p->flags & DCNV3_FLAG_CHECK_WORKSPACE) && (p->flags & DCNV3_FLAG_WORKSPACE_ZEROED) &&
+        (rc = check_workspace_zero(ws, need, st)))
+        return rc;
     const KParams q = derive(p);
     const bool tiled = tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC) && !ref_dtype_mode(p);
     cudaError_t e =
@@ -226,7 +257,9 @@ struct HostScratch {
 struct DevicePipes {
     cudaStream_t in = nullptr, out = nullptr;
 };
-static std::mutex g_scratch_mu;
+// one lock per device: host threads driving different GPUs (one thread per replica, as under the reference's
+// MirroredStrategy) never wait for each other; calls on the same device are enqueued one after the other
+static std::mutex g_scratch_mu[64];
 static HostScratch g_scratch[64][kHostSlots];
 static DevicePipes g_pipes[64];
 
@@ -416,7 +449,8 @@ static int host_run(const void* x, const void* offset, const void* mask, const v
     const size_t b_ws = with_backward ? align_up(backward_ws_bytes(p), 256) : 0;
     size_t total = b_x + b_off + b_m + b_o;
     if (with_backward) total += b_o + b_x + b_off + b_m;
-    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    if (device < 0 || device >= 64) return fail(DCNV3_ERR_DEVICE, "device %d out of range", device);
+    std::lock_guard<std::mutex> lock(g_scratch_mu[device]);
     HostScratch* s;
     if ((rc = scratch_reserve(device, slot, total, b_ws, &s))) return rc;
     char* base = (char*)s->buf;
@@ -490,7 +524,7 @@ int dcnv3_forward_backward_host_async(const void* x, const void* offset, const v
 
 int dcnv3_host_sync(int device) {
     if (device < 0 || device >= 64) return fail(DCNV3_ERR_DEVICE, "device %d out of range", device);
-    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    std::lock_guard<std::mutex> lock(g_scratch_mu[device]);
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     if (g_pipes[device].in && (e = cudaStreamSynchronize(g_pipes[device].in)) != cudaSuccess)
@@ -506,8 +540,8 @@ int dcnv3_host_sync(int device) {
 int dcnv3_host_slots(void) { return kHostSlots; }
 
 int dcnv3_release_host_scratch(void) {
-    std::lock_guard<std::mutex> lock(g_scratch_mu);
     for (int d = 0; d < 64; ++d) {
+        std::lock_guard<std::mutex> lock(g_scratch_mu[d]);
         DevicePipes& dp = g_pipes[d];
         if (dp.in) {
             cudaSetDevice(d);

@@ -229,7 +229,8 @@ struct Elem<__nv_bfloat16> {
 // seen (and the image's grad_x becomes NaN) instead of being swallowed by fmaxf / float -> int conversion.
 struct WsHeader {
     unsigned done;      // tiled path: CTAs of the last kernel that have finished (reset by the last one)
-    unsigned pad[63];
+    unsigned any_redo;  // tiled path: some scatter CTA found overflow-suspect cells (reset by the last kernel)
+    unsigned pad[62];
 };
 struct ImgMax {
     unsigned go_bits;   // max |grad_out| of the image, float bits

@@ -142,7 +142,10 @@ __device__ __forceinline__ void finalize_workspace(const FarWs& ws, int n_images
     if (!s_last) return;
     unsigned* m = reinterpret_cast<unsigned*>(ws.img_max);
     for (int i = threadIdx.x; i < 2 * n_images; i += blockDim.x) m[i] = 0u;
-    if (threadIdx.x == 0) ws.hd->done = 0u;
+    if (threadIdx.x == 0) {
+        ws.hd->any_redo = 0u;
+        ws.hd->done = 0u;
+    }
 }
 
 // grad_out of one (pixel, group) in fixed point: G[c] = round(go[c] * 2^eg)
@@ -426,9 +429,9 @@ __device__ __forceinline__ bool cell_is_hot(const int* wsum, int cy, int cx, int
 __device__ __forceinline__ int qmul(int g, int wq) {
     return (int)(((long long)g * wq + 0x80000000ll) >> 32);
 }
-__device__ __forceinline__ int weight_fixed(float wf) {
-    return __float2int_rn(fminf(fmaxf(wf, -3.9f), 3.9f) * (float)(1 << kWShift));
-}
+// (|wf| < 3.9 whenever the tap's cells are not hot -- weight_units() -- so the conversion cannot saturate there;
+//  for hot cells it may, deterministically, and those accumulators are discarded and recomputed)
+__device__ __forceinline__ int weight_fixed(float wf) { return __float2int_rn(wf * (float)(1 << kWShift)); }
 
 // one landing into the 64-bit side buffer: the same integers q as the shared-memory path; |Wk| >= 3.9
 // (raw masks only) is pre-shifted so that the product still fits
@@ -611,29 +614,31 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
     __syncthreads();
 
     // ---- flush: the cells of J are written exactly once; ring cells go to the side buffer ----
+    // work item = 32 consecutive 4-channel pieces of one box row (4 cells x 2 groups), dealt round-robin to the warps
     const float inv_s = ldexpf(1.0f, -(eg + kWShift - 32));  // q = value * 2^(eg + kWShift - 32)
     constexpr int QPC = kSCell / 4;  // 4-channel pieces per cell
-    const size_t img_pixels = (size_t)q.h * q.w;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int segs = (box.bw * QPC + 31) >> 5;
+    const int piece = lane & (QPC - 1), gl = piece >> 2;  // (QPC = 8 divides 32: a lane keeps its piece)
+    const int g = chunk * kSG + gl;
+    const float qnan = __int_as_float(0x7fc00000);
     bool any_hot = false;
-    for (int i = threadIdx.x; i < box.bh * (PITCH * QPC); i += blockDim.x) {
-        const int cy = i / (PITCH * QPC), r = i - cy * (PITCH * QPC);
-        const int cx = r / QPC, piece = r % QPC;
+    for (int item = warp; item < box.bh * segs; item += nwarps) {
+        const int cy = item / segs, cx = ((item - cy * segs) << 2) + (lane >> 3);
         const int ax = box.bx0 + cx, ay = box.by0 + cy;
-        // beyond the box row; zero ring: gradient dropped (Pad-grad)
-        if (cx >= box.bw || ax < 0 || ax >= q.w || ay < 0 || ay >= q.h) continue;
-        const int gl = (piece * 4) / kGC;
-        const int g = chunk * kSG + gl;
-        if (g >= q.G) continue;  // phantom group
+        // beyond the box row; zero ring: gradient dropped (Pad-grad); phantom group
+        if (cx >= box.bw || ax < 0 || ax >= q.w || ay < 0 || ay >= q.h || g >= q.G) continue;
         // a hot (cell, group) may have wrapped: it is skipped here and recomputed by redo_hot_kernel
         const bool hot = cell_is_hot<WP>(wsum, cy, cx, gl);
         any_hot |= hot;
         const int4 v = *reinterpret_cast<const int4*>(acc + (cy * PITCH + cx) * kSCell + piece * 4);
-        const size_t gpix = (size_t)n * img_pixels + (size_t)(ay * q.w + ax);
+        const size_t gpix = ((size_t)n * q.h + ay) * q.w + ax;
         if ((unsigned)(ax - box.ux0) < (unsigned)box.tjw && (unsigned)(ay - box.uy0) < (unsigned)box.tjh) {
             const size_t gidx = gpix * ((size_t)q.G * kGC) + (size_t)(chunk * kSCell + piece * 4);
-            const float qnan = __int_as_float(0x7fc00000);
-            const float f0 = nonfinite ? qnan : hot ? 0.f : (float)v.x * inv_s, f1 = nonfinite ? qnan : hot ? 0.f : (float)v.y * inv_s;
-            const float f2_ = nonfinite ? qnan : hot ? 0.f : (float)v.z * inv_s, f3 = nonfinite ? qnan : hot ? 0.f : (float)v.w * inv_s;
+            const bool drop = hot || nonfinite;
+            const float fill = nonfinite ? qnan : 0.f;
+            const float f0 = drop ? fill : (float)v.x * inv_s, f1 = drop ? fill : (float)v.y * inv_s;
+            const float f2_ = drop ? fill : (float)v.z * inv_s, f3 = drop ? fill : (float)v.w * inv_s;
             if (sizeof(T) == 4) {
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(grad_x) + gidx) = make_float4(f0, f1, f2_, f3);
             } else {
@@ -652,58 +657,68 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
             ws.dirty[cellg] = 1;
         }
     }
-    if (any_hot) ws.redo[blockIdx.x] = 1;
+    if (any_hot) {
+        ws.redo[blockIdx.x] = 1;
+        ws.hd->any_redo = 1u;  // (benign race: every writer stores the same value)
+    }
 }
 
 // Exact recomputation of the hot cells of one box (see header): pass 1 rebuilds the weight counters,
 // pass 2 adds the landings on hot cells to the 64-bit side buffer.  Exits at once unless the scatter
 // kernel flagged the CTA -- which only adversarial inputs make it do.
+// Launched with a handful of CTAs: unless some scatter CTA raised any_redo they only read that word and leave;
+// otherwise they share the flagged tiles among themselves.
 template <typename T, int TJ>
 __global__ void __launch_bounds__(256)
 redo_hot_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
-                T* __restrict__ grad_x, const FarWs ws, const KParams q, const BwdGeom bg, const int is_last) {
+                T* __restrict__ grad_x, const FarWs ws, const KParams q, const BwdGeom bg, const int n_tiles,
+                const int is_last) {
     constexpr int WP = ScatterShape<TJ>::WPITCH;
     extern __shared__ __align__(16) int wsum[];  // [box_rows + 1][WP][kSG]
     __shared__ Range s_home_h, s_home_w;
     pdl_launch_dependents();
     pdl_wait();
-    if (ws.redo[blockIdx.x] != 0) {  // (uniform per CTA)
-        int b = blockIdx.x;
-        const int jx = b % bg.tiles_x; b /= bg.tiles_x;
-        const int jy = b % bg.tiles_y; b /= bg.tiles_y;
-        const int chunk = b % bg.chunks;
-        const int n = b / bg.chunks;
-        const TileBox box = make_box(q, bg, jx, jy);
-        if (threadIdx.x < 2) tile_ranges(q, bg, jx, jy, s_home_h, s_home_w);
-        for (int i = threadIdx.x; i < (bg.box_rows + 1) * WP * kSG; i += blockDim.x) wsum[i] = 0;
-        __syncthreads();
-        const int eg = 30 - fixed_exponent_raw(ws.img_max[n].go_bits);
-        scatter_walk<T, 1, TJ>(nullptr, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
-        __syncthreads();
-        scatter_walk<T, 2, TJ>(nullptr, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
-        __syncthreads();
-        if (threadIdx.x == 0) ws.redo[blockIdx.x] = 0;
-        if (bg.tiles_x * bg.tiles_y == 1) {  // (otherwise merge_far_kernel folds the side buffer into grad_x)
-            // The tile is the whole image: nobody else contributes to its cells (no ring, no far landings), so
-            // there is no merge launch and this CTA converts its hot cells itself.
-            __threadfence();
+    if (ws.hd->any_redo != 0u) {  // (uniform over the grid)
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            if (ws.redo[tile] == 0) continue;  // (uniform per CTA)
+            int b = tile;
+            const int jx = b % bg.tiles_x; b /= bg.tiles_x;
+            const int jy = b % bg.tiles_y; b /= bg.tiles_y;
+            const int chunk = b % bg.chunks;
+            const int n = b / bg.chunks;
+            const TileBox box = make_box(q, bg, jx, jy);
+            __syncthreads();  // the previous tile's counters and ranges are no longer read
+            if (threadIdx.x < 2) tile_ranges(q, bg, jx, jy, s_home_h, s_home_w);
+            for (int i = threadIdx.x; i < (bg.box_rows + 1) * WP * kSG; i += blockDim.x) wsum[i] = 0;
             __syncthreads();
-            constexpr int PITCH = ScatterShape<TJ>::PITCH;
-            const size_t img_pixels = (size_t)q.h * q.w;
-            const double inv_d = ldexp(1.0, -(eg + kWShift - 32));
-            for (int i = threadIdx.x; i < box.bh * (PITCH * kSCell); i += blockDim.x) {
-                const int cy = i / (PITCH * kSCell), r = i - cy * (PITCH * kSCell);
-                const int cx = r / kSCell, ch = r % kSCell, gl = ch / kGC;
-                const int ax = box.bx0 + cx, ay = box.by0 + cy, g = chunk * kSG + gl;
-                if (cx >= box.bw || ax < 0 || ax >= q.w || ay < 0 || ay >= q.h || g >= q.G) continue;
-                if (!cell_is_hot<WP>(wsum, cy, cx, gl)) continue;
-                const size_t cellg = ((size_t)n * img_pixels + (size_t)(ay * q.w + ax)) * q.G + g;
-                const size_t idx = cellg * kGC + ch % kGC;
-                const long long v = (long long)__ldcg(ws.acc64 + idx);
-                // |v| can exceed 2^24: go through double so that the exact total is rounded once
-                Elem<T>::st(grad_x + idx, (float)((double)v * inv_d));
-                ws.acc64[idx] = 0ull;
-                ws.dirty[cellg] = 0;
+            const int eg = 30 - fixed_exponent_raw(ws.img_max[n].go_bits);
+            scatter_walk<T, 1, TJ>(nullptr, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+            __syncthreads();
+            scatter_walk<T, 2, TJ>(nullptr, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+            __syncthreads();
+            if (threadIdx.x == 0) ws.redo[tile] = 0;
+            if (bg.tiles_x * bg.tiles_y == 1) {  // (otherwise merge_far_kernel folds the side buffer into grad_x)
+                // The tile is the whole image: nobody else contributes to its cells (no ring, no far landings), so
+                // there is no merge launch and this CTA converts its hot cells itself.
+                __threadfence();
+                __syncthreads();
+                constexpr int PITCH = ScatterShape<TJ>::PITCH;
+                const size_t img_pixels = (size_t)q.h * q.w;
+                const double inv_d = ldexp(1.0, -(eg + kWShift - 32));
+                for (int i = threadIdx.x; i < box.bh * (PITCH * kSCell); i += blockDim.x) {
+                    const int cy = i / (PITCH * kSCell), r = i - cy * (PITCH * kSCell);
+                    const int cx = r / kSCell, ch = r % kSCell, gl = ch / kGC;
+                    const int ax = box.bx0 + cx, ay = box.by0 + cy, g = chunk * kSG + gl;
+                    if (cx >= box.bw || ax < 0 || ax >= q.w || ay < 0 || ay >= q.h || g >= q.G) continue;
+                    if (!cell_is_hot<WP>(wsum, cy, cx, gl)) continue;
+                    const size_t cellg = ((size_t)n * img_pixels + (size_t)(ay * q.w + ax)) * q.G + g;
+                    const size_t idx = cellg * kGC + ch % kGC;
+                    const long long v = (long long)__ldcg(ws.acc64 + idx);
+                    // |v| can exceed 2^24: go through double so that the exact total is rounded once
+                    Elem<T>::st(grad_x + idx, (float)((double)v * inv_d));
+                    ws.acc64[idx] = 0ull;
+                    ws.dirty[cellg] = 0;
+                }
             }
         }
     }
@@ -810,8 +825,9 @@ static cudaError_t launch_scatter(const T* offset, const T* mask, const T* grad_
     e = launch_pdl(bwd_scatter_kernel<T, TJ>, grid, S::THREADS, smem, st, offset, mask, grad_out, grad_x, ws, q, bg);
     if (e != cudaSuccess) return e;
     if (kt.enabled) cudaEventRecord(kt.ev[2], st);
-    return launch_pdl(redo_hot_kernel<T, TJ>, grid, 256, (size_t)(bg.box_rows + 1) * S::WPITCH * kSG * sizeof(int), st,
-                      offset, mask, grad_out, grad_x, ws, q, bg, (int)redo_is_last);
+    const unsigned redo_grid = grid < 32u ? grid : 32u;  // normally they only read one word and leave
+    return launch_pdl(redo_hot_kernel<T, TJ>, redo_grid, 256, (size_t)(bg.box_rows + 1) * S::WPITCH * kSG * sizeof(int), st,
+                      offset, mask, grad_out, grad_x, ws, q, bg, (int)grid, (int)redo_is_last);
 }
 
 template <typename T, bool STAGED>

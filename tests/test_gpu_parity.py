@@ -339,6 +339,29 @@ def test_raw_pointer_and_host_entry_points(ops):
     assert rc == cabi.ERR_WORKSPACE
 
 
+def test_dirty_workspace_is_detected_on_request(ops):
+    """DCNV3_FLAG_WORKSPACE_ZEROED is a promise; DCNV3_FLAG_CHECK_WORKSPACE verifies it (debug aid)."""
+    _, cabi = ops
+    n, h, w, g, gc = 1, 20, 20, 4, 16
+    x, off, m, go = make_inputs(n, h, w, g, gc, seed=4)
+    tx, to, tm, tgo = cuda(x, off, m, go)
+    gx, goff, gm = torch.empty_like(tx), torch.empty_like(to), torch.empty_like(tm)
+    p = cabi.make_params(x.shape, (h, w), (3, 3), (1, 1), (1, 1), (1, 1), g, gc, 1.0, cabi.F32,
+                         cabi.FLAG_WORKSPACE_ZEROED | cabi.FLAG_CHECK_WORKSPACE)
+    nb = int(cabi.lib.dcnv3_backward_workspace_bytes(ctypes.byref(p)))
+    ws = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    args = [t.data_ptr() for t in (tx, to, tm, tgo, gx, goff, gm, ws)]
+    assert cabi.lib.dcnv3_backward(*args, nb, ctypes.byref(p), st) == 0
+    torch.cuda.synchronize()
+    assert int(ws.count_nonzero()) == 0
+    rx, _, _ = c_oracle.backward(x, off, m, go, groups=g, group_channels=gc)
+    assert rel_err(gx.cpu().numpy(), rx) <= TOL_F32
+    ws[nb // 2] = 1  # something scribbled on it
+    assert cabi.lib.dcnv3_backward(*args, nb, ctypes.byref(p), st) == cabi.ERR_WORKSPACE
+    assert b"not all-zero" in cabi.lib.dcnv3_last_error()
+
+
 def test_layer_matches_reference_layer(ops):
     iseg, _ = ops
     for name in ("c64_g4_cfs", "c32_g2_dw5"):
