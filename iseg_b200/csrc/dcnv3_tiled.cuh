@@ -21,7 +21,17 @@ constexpr int kGC = 16;
 constexpr int kCellBytes = 128;
 constexpr int kMaxBoxBytes = 82 * 1024;  // staged input box of the forward / gather kernels; with the per-warp side slots two CTAs fit one SM
 constexpr int kFwdBoxBytes = 100 * 1024; // forward box when the side inputs are not staged (no slots): two CTAs per SM
-constexpr int kTiledWarps = 8;           // warps per forward / gather CTA
+// Forward / gather launch shape.  Persistent: one 16-warp CTA per SM walks over tiles t = blockIdx.x, + gridDim.x, ...
+// with TWO input boxes, so that the TMA load of the next tile's box runs under the current tile's arithmetic.
+// (DCNV3_ONE_TILE_PER_CTA selects the round-1 shape for A/B runs: 8-warp CTAs, one tile each, two per SM.)
+#ifdef DCNV3_ONE_TILE_PER_CTA
+constexpr int kTiledWarps = 8;
+constexpr int kBoxBuffers = 1;
+#else
+constexpr int kTiledWarps = 16;
+constexpr int kBoxBuffers = 2;
+#endif
+constexpr int kTiledCtasPerSm = kBoxBuffers == 2 ? 1 : 2;
 
 template <typename T>
 struct Chunk {
@@ -41,12 +51,20 @@ struct TileGeom {
     int chunks;            // G / GQ
 };
 
+// One tile of the forward / gather kernels, decoded from its linear index (x fastest, then y, chunk, image).
+struct TileCtx {
+    int n, chunk, h0, w0, th, tw;  // image, group chunk, output tile origin and clipped extent
+    int cx0, cy0;                  // origin of the staged input box (padded coordinates)
+    int colblocks, nit;            // row segments per tile row / per tile (one warp iteration each)
+};
+
 // host helpers implemented in dcnv3_tiled_fwd.cu
 TileGeom make_geom(const KParams& q, int dtype, int th, int tw, float reach, int max_cells);
 bool make_x_tensor_map(CUtensorMap* map, const void* x, const KParams& q, int dtype, int bw, int bh);
 // [N*Ho][Wo][G*per_group] view of offset / mask (and their gradients), box = one warp iteration of one chunk
 bool side_stageable(const KParams& q, int dtype);
 bool make_side_tensor_map(CUtensorMap* map, const void* base, const KParams& q, int dtype, int per_group);
+unsigned tiled_grid(int n_tiles);
 // raises a kernel's dynamic shared-memory limit once per (kernel, device); safe to call from any thread
 cudaError_t ensure_max_smem(const void* kernel, int bytes);
 
@@ -77,6 +95,26 @@ __device__ __forceinline__ float nominal_x(const KParams& q, int h) {
 }
 __device__ __forceinline__ float nominal_y(const KParams& q, int w) {
     return ((float)w + q.x0c) / q.win_f * q.hm2_f;
+}
+
+template <int PXW>
+__device__ __forceinline__ TileCtx decode_tile(const KParams& q, const TileGeom& tg, int t) {
+    TileCtx c;
+    const int tx = t % tg.tiles_w; t /= tg.tiles_w;
+    const int ty = t % tg.tiles_h; t /= tg.tiles_h;
+    c.chunk = t % tg.chunks;
+    c.n = t / tg.chunks;
+    c.h0 = ty * tg.th;
+    c.w0 = tx * tg.tw;
+    c.th = min(tg.th, q.ho - c.h0);
+    c.tw = min(tg.tw, q.wo - c.w0);
+    // box origin in padded coordinates (output rows h walk along x, columns w along y); kept inside the padded
+    // image: cells beyond it can only belong to dead taps
+    c.cx0 = max(0, min((int)floorf(nominal_x(q, c.h0)) - tg.halo_x, q.win - tg.bw));
+    c.cy0 = max(0, min((int)floorf(nominal_y(q, c.w0)) - tg.halo_y, q.hin - tg.bh));
+    c.colblocks = (c.tw + PXW - 1) / PXW;
+    c.nit = c.th * c.colblocks;
+    return c;
 }
 
 // ---- mbarrier / TMA (sm_90+ PTX; SASS: SYNCS / UTMALDG) -------------------------------------------
@@ -147,6 +185,43 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 //      this one drains; it must not touch global memory before pdl_wait() ------------------------------
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Shared skeleton of the forward and gather kernels: the CTA's tiles are t = blockIdx.x + k * gridDim.x.  Tile k's
+// input box lives in buffer k % kBoxBuffers; when the last warp has finished with a buffer, that warp's lane 0 asks the
+// TMA unit for the box of tile k + kBoxBuffers.  Every warp always has exactly one side-slot request in flight: its
+// next row segment, in this tile or in the next one that has a segment for it.
+struct TileWalk {
+    int k, it;  // position of the warp: its it-th row segment of the CTA's k-th tile
+};
+template <int PXW>
+__device__ __forceinline__ bool next_segment(const KParams& q, const TileGeom& tg, int n_tiles, int warp, TileWalk& w,
+                                             TileCtx& ctx) {
+    w.it += kTiledWarps;
+    for (;;) {
+        if (w.it < ctx.nit) return true;
+        ++w.k;
+        const int t = blockIdx.x + w.k * gridDim.x;
+        if (t >= n_tiles) return false;
+        ctx = decode_tile<PXW>(q, tg, t);
+        w.it = warp;
+    }
+}
+
+// a warp is done with box buffer `buf` (tile k): the last of the CTA's warps to say so refills it with tile k + 2
+__device__ __forceinline__ void release_box(unsigned* cnt, uint64_t* full, unsigned char* box, const CUtensorMap* xmap,
+                                            const KParams& q, const TileGeom& tg, int n_tiles, int k, int lane, int gq) {
+    __syncwarp();
+    if (lane != 0) return;
+    __threadfence_block();  // this warp's reads of the box precede the refill
+    if (atomicAdd(cnt, 1u) != kTiledWarps - 1) return;
+    *cnt = 0u;
+    const int t = blockIdx.x + (k + kBoxBuffers) * gridDim.x;
+    if (t >= n_tiles) return;
+    __threadfence_block();
+    const TileCtx c = decode_tile<1>(q, tg, t);
+    mbar_expect_tx(full, (uint32_t)(tg.bw * tg.bh * kCellBytes));
+    tma_load_4d(box, xmap, full, c.chunk * gq * kGC, c.cx0 - q.pw, c.cy0 - q.ph, c.n);
+}
 
 // ---- packed fp32 pairs: Blackwell issues two fp32 FMAs per instruction (PTX fma.rn.f32x2, SASS FFMA2) ----
 typedef unsigned long long f2;  // {lo, hi} = two consecutive channels

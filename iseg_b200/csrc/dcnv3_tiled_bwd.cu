@@ -188,31 +188,27 @@ __device__ __forceinline__ void load_fixed_point_go(const T* go, float sg, int r
 // grad_offset / grad_mask
 // =====================================================================================================
 template <typename T, bool STAGED>
-__global__ void __launch_bounds__(kTiledWarps * 32, 2)
+__global__ void __launch_bounds__(kTiledWarps * 32, kTiledCtasPerSm)
 bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap offmap,
                   const __grid_constant__ CUtensorMap goffmap, const T* __restrict__ x,
                   const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
                   T* __restrict__ grad_offset, T* __restrict__ grad_mask, ImgMax* __restrict__ img_max, const KParams q,
-                  const TileGeom tg) {
+                  const TileGeom tg, const int n_tiles) {
     using C = Chunk<T>;
     using RS = RowStage<T>;
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t full[kBoxBuffers];
     __shared__ __align__(8) uint64_t sbar[kTiledWarps];
+    __shared__ unsigned released[kBoxBuffers];
     pdl_launch_dependents();
 
-    int b = blockIdx.x;
-    const int tx = b % tg.tiles_w; b /= tg.tiles_w;
-    const int ty = b % tg.tiles_h; b /= tg.tiles_h;
-    const int chunk = b % tg.chunks;
-    const int n = b / tg.chunks;
-    const int h0 = ty * tg.th, w0 = tx * tg.tw;
-    const int th = min(tg.th, q.ho - h0), tw = min(tg.tw, q.wo - w0);
-    const int cx0 = max(0, min((int)floorf(nominal_x(q, h0)) - tg.halo_x, q.win - tg.bw));
-    const int cy0 = max(0, min((int)floorf(nominal_y(q, w0)) - tg.halo_y, q.hin - tg.bh));
-
+    const int box_bytes = tg.bw * tg.bh * kCellBytes;
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+#pragma unroll
+        for (int i = 0; i < kBoxBuffers; ++i) {
+            mbar_init(&full[i], 1);
+            released[i] = 0u;
+        }
 #pragma unroll
         for (int i = 0; i < kTiledWarps; ++i) mbar_init(&sbar[i], 1);
         fence_mbar_init();
@@ -220,168 +216,191 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
     __syncthreads();
     pdl_wait();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(&bar, (uint32_t)(tg.bw * tg.bh * kCellBytes));
-        tma_load_4d(smem, &xmap, &bar, chunk * C::GQ * kGC, cx0 - q.pw, cy0 - q.ph, n);
+#pragma unroll
+        for (int i = 0; i < kBoxBuffers; ++i) {
+            const int t = blockIdx.x + i * gridDim.x;
+            if (t < n_tiles) {
+                const TileCtx c = decode_tile<1>(q, tg, t);
+                mbar_expect_tx(&full[i], (uint32_t)box_bytes);
+                tma_load_4d(smem + (size_t)i * box_bytes, &xmap, &full[i], c.chunk * C::GQ * kGC, c.cx0 - q.pw, c.cy0 - q.ph,
+                            c.n);
+            }
+        }
     }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g_l = lane % C::GQ, px_l = lane / C::GQ;
-    const int g = min(chunk * C::GQ + g_l, q.G - 1);  // phantom groups of a trailing chunk shadow the last one
-    const int ng = min(C::GQ, q.G - chunk * C::GQ);   // real groups in this chunk
     const int rot = Slab<T>::rot_of(px_l);
-    const unsigned char* sbase = smem + g_l * (kGC * (int)sizeof(T));
     // The warp's slot: side inputs in (STAGED), results out -- every result overwrites the input value of the
     // same tap (identical layout), and the slot is stored once per row segment.  For the fused soft-max path an
     // fp32 park holds dL/dm_p (it aliases the mask part when T is fp32).
-    unsigned char* st = smem + (size_t)tg.bw * tg.bh * kCellBytes + warp * kGatherStageBytes<T>;
+    unsigned char* st = smem + (size_t)kBoxBuffers * box_bytes + warp * kGatherStageBytes<T>;
     float* park = sizeof(T) == 4 ? reinterpret_cast<float*>(st + RS::OFF_BYTES)
                                  : reinterpret_cast<float*>(st + RS::BYTES);
     const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
-    const int colblocks = (tw + C::PXW - 1) / C::PXW, nit = th * colblocks;
-    bool waited = false;
     uint32_t sphase = 0;
-    unsigned amax = 0u;  // max |grad_out| bits seen by this thread: the fixed-point scale of the scatter kernel
 
-    auto request = [&](int it) {
-        const int h = h0 + it / colblocks, wb = w0 + (it % colblocks) * C::PXW;
-        const size_t pix0 = ((size_t)n * q.ho + h) * q.wo + wb;
-        RS::request(st, &sbar[warp], &offmap, mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, chunk, wb, n * q.ho + h,
-                    min(C::PXW, w0 + tw - wb), lane);
+    auto request = [&](const TileCtx& c, int it) {
+        const int h = c.h0 + it / c.colblocks, wb = c.w0 + (it % c.colblocks) * C::PXW;
+        const size_t pix0 = ((size_t)c.n * q.ho + h) * q.wo + wb;
+        RS::request(st, &sbar[warp], &offmap, mask + (pix0 * q.G + c.chunk * C::GQ) * 9, q.G, c.chunk, wb, c.n * q.ho + h,
+                    min(C::PXW, c.w0 + c.tw - wb), lane);
     };
-    if (STAGED && warp < nit) request(warp);
+    if (STAGED) {  // the warp's first row segment
+        TileWalk nw = {0, warp - kTiledWarps};
+        TileCtx nc = decode_tile<C::PXW>(q, tg, blockIdx.x);
+        if (next_segment<C::PXW>(q, tg, n_tiles, warp, nw, nc)) request(nc, nw.it);
+    }
 
-    // one warp iteration = PXW consecutive pixels of one output row
-    for (int it = warp; it < nit; it += kTiledWarps) {
-        const int h = h0 + it / colblocks, wb = w0 + (it % colblocks) * C::PXW;
-        const int npx = min(C::PXW, w0 + tw - wb);
-        const int w = wb + min(px_l, npx - 1);  // idle lanes shadow the last pixel (their slots are never stored)
-        const size_t pix0 = ((size_t)n * q.ho + h) * q.wo + wb;
-        const size_t pg = (pix0 + min(px_l, npx - 1)) * q.G + g;
-        const T* offp = offset + pg * 18;
-        const T* mskp = mask + pg * 9;
-        f2 go[8];
+    int k = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+        const TileCtx ctx = decode_tile<C::PXW>(q, tg, tile);
+        const int buf = k % kBoxBuffers;
+        const unsigned char* sbase = smem + (size_t)buf * box_bytes + g_l * (kGC * (int)sizeof(T));
+        const int n = ctx.n, chunk = ctx.chunk, cx0 = ctx.cx0, cy0 = ctx.cy0;
+        const int g = min(chunk * C::GQ + g_l, q.G - 1);  // phantom groups of a trailing chunk shadow the last one
+        const int ng = min(C::GQ, q.G - chunk * C::GQ);   // real groups in this chunk
+        bool waited = false;
+        unsigned amax = 0u;  // max |grad_out| bits seen by this thread in this tile: the image's fixed-point scale
+
+        // one warp iteration = PXW consecutive pixels of one output row
+        for (int it = warp; it < ctx.nit; it += kTiledWarps) {
+            const int h = ctx.h0 + it / ctx.colblocks, wb = ctx.w0 + (it % ctx.colblocks) * C::PXW;
+            const int npx = min(C::PXW, ctx.w0 + ctx.tw - wb);
+            const int w = wb + min(px_l, npx - 1);  // idle lanes shadow the last pixel (their slots are never stored)
+            const size_t pix0 = ((size_t)n * q.ho + h) * q.wo + wb;
+            const size_t pg = (pix0 + min(px_l, npx - 1)) * q.G + g;
+            const T* offp = offset + pg * 18;
+            const T* mskp = mask + pg * 9;
+            f2 go[8];
 #pragma unroll
-        for (int pc = 0; pc < C::NPIECE; ++pc)
-            load_piece<T>(grad_out + pg * kGC + Slab<T>::chan_of(pc, rot), go + pc * C::PAIRS);
-        float ref0, ref1;
-        ref_point(q, h, w, ref0, ref1);
-        if (STAGED) {
-            cp_async_wait_all();
-            __syncwarp();
-            mbar_wait(&sbar[warp], sphase);
-            sphase ^= 1;
-        }
-        float mx = 0.f, inv_sum = 1.f;
-        if (logits) {
-            if (STAGED) RS::softmax_stats(st, lane, mx, inv_sum);
-            else softmax_stats9<T>(mskp, mx, inv_sum);
-        }
-        float ox, oy, ml, ox2 = 0.f, oy2 = 0.f, ml2 = 0.f;
-        if (STAGED) {
-            RS::tap(st, lane, 0, ox, oy, ml);
-        } else {
-            load_tap_inputs<T>(offp, mskp, 0, ox, oy, ml);
-            load_tap_inputs<T>(offp, mskp, 1, ox2, oy2, ml2);
-        }
-        if (!waited) {
-            mbar_wait(&bar, 0);
-            waited = true;
-        }
-        float gm_dot_m = 0.f;
-#pragma unroll 1
-        for (int p = 0; p < kTaps; ++p) {
-            const float cx = ox, cy = oy, cm = ml;
+            for (int pc = 0; pc < C::NPIECE; ++pc)
+                load_piece<T>(grad_out + pg * kGC + Slab<T>::chan_of(pc, rot), go + pc * C::PAIRS);
+            float ref0, ref1;
+            ref_point(q, h, w, ref0, ref1);
             if (STAGED) {
-                if (p + 1 < kTaps) RS::tap(st, lane, p + 1, ox, oy, ml);  // (read before tap p's results land)
-            } else {
-                ox = ox2; oy = oy2; ml = ml2;
-                if (p + 2 < kTaps) load_tap_inputs<T>(offp, mskp, p + 2, ox2, oy2, ml2);  // two taps ahead
+                cp_async_wait_all();
+                __syncwarp();
+                mbar_wait(&sbar[warp], sphase);
+                sphase ^= 1;
             }
-            const Tap t = make_tap(q, ref0, ref1, p, cx, cy);
-            const int bx = t.x0 - cx0, by = t.y0 - cy0;
-            const bool inbox = bx >= 0 && bx + 1 < tg.bw && by >= 0 && by + 1 < tg.bh;
-            const float mm = logits ? expf(cm - mx) * inv_sum : cm;
-            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;  // <go, I_k>: a=(y0,x0) b=(y1,x0) c=(y0,x1) d=(y1,x1)
-            if (__builtin_expect(t.alive && !inbox, 0)) {
-#pragma unroll 1
-                for (int k = 0; k < 4; ++k) {
-                    const T* src = global_slab_b(x, q, n, t.y0 + (k & 1), t.x0 + (k >> 1), g);
-                    if (src == nullptr) continue;
-                    f2 dk2 = 0ull;
-#pragma unroll
-                    for (int pc = 0; pc < C::NPIECE; ++pc) {
-                        f2 v[C::PAIRS];
-                        load_piece<T>(src + Slab<T>::chan_of(pc, rot), v);
-#pragma unroll
-                        for (int j = 0; j < C::PAIRS; ++j) ffma2v(dk2, v[j], go[pc * C::PAIRS + j]);
-                    }
-                    const float dk = lo_of(dk2) + hi_of(dk2);
-                    if (k == 0) d0 = dk; else if (k == 1) d1 = dk; else if (k == 2) d2 = dk; else d3 = dk;
-                }
-            } else {
-                const unsigned char* a = sbase + (size_t)(t.alive ? by * tg.bw + bx : 0) * kCellBytes;
-                f2 va[8], vb[8], e0 = 0ull, e1 = 0ull, e2 = 0ull, e3 = 0ull;
-                Slab<T>::load(a, rot, va);
-                Slab<T>::load(a + (size_t)tg.bw * kCellBytes, rot, vb);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) ffma2v(e0, va[c], go[c]);
-                Slab<T>::load(a + kCellBytes, rot, va);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) ffma2v(e1, vb[c], go[c]);
-                Slab<T>::load(a + (size_t)(tg.bw + 1) * kCellBytes, rot, vb);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) ffma2v(e2, va[c], go[c]);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) ffma2v(e3, vb[c], go[c]);
-                d0 = lo_of(e0) + hi_of(e0);
-                d1 = lo_of(e1) + hi_of(e1);
-                d2 = lo_of(e2) + hi_of(e2);
-                d3 = lo_of(e3) + hi_of(e3);
+            float mx = 0.f, inv_sum = 1.f;
+            if (logits) {
+                if (STAGED) RS::softmax_stats(st, lane, mx, inv_sum);
+                else softmax_stats9<T>(mskp, mx, inv_sum);
             }
-            // dead taps have all four deltas zero => zero gradients
-            const float g_m = t.dx1 * t.dy1 * d0 + t.dx1 * t.dy0 * d1 + t.dx0 * t.dy1 * d2 + t.dx0 * t.dy0 * d3;
-            const float gxq = mm * (t.dy1 * (d2 - d0) + t.dy0 * (d3 - d1));
-            const float gyq = mm * (t.dx1 * (d1 - d0) + t.dx0 * (d3 - d2));
-            gm_dot_m += g_m * mm;
-            // results go to the lane's slot positions (lane stride 72 / 36 bytes: conflict free)
-            if (sizeof(T) == 4) {
-                *reinterpret_cast<float2*>(st + lane * RS::LANE_OFF + p * 8) = make_float2(gxq * q.fx, gyq * q.fy);
+            float ox, oy, ml, ox2 = 0.f, oy2 = 0.f, ml2 = 0.f;
+            if (STAGED) {
+                RS::tap(st, lane, 0, ox, oy, ml);
             } else {
-                *reinterpret_cast<unsigned*>(st + lane * RS::LANE_OFF + p * 4) = pack_bf16x2(gxq * q.fx, gyq * q.fy);
+                load_tap_inputs<T>(offp, mskp, 0, ox, oy, ml);
+                load_tap_inputs<T>(offp, mskp, 1, ox2, oy2, ml2);
             }
-            if (logits || sizeof(T) == 4) park[lane * kTaps + p] = g_m;
-            else *reinterpret_cast<__nv_bfloat16*>(st + RS::OFF_BYTES + lane * RS::LANE_MSK + p * 2) = __float2bfloat16_rn(g_m);
-        }
-        // (max |grad_out| is taken here, after the taps: the first use of the freshly loaded grad_out is then
-        //  the first tap's dot products, behind its coordinate arithmetic and shared-memory loads)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) amax = max(amax, max(abs_bits(lo_of(go[c])), abs_bits(hi_of(go[c]))));
-        if (logits) {
-            // softmax Jacobian needs sum_p m_p*dL/dm_p: second sweep over this lane's own 9 values.  The logits
-            // are still in the slot when T is bf16 (the park is a separate area); for fp32 the park has
-            // overwritten them and they are read again from global memory (L1 / L2 hits)
+            if (!waited) {
+                mbar_wait(&full[buf], (k / kBoxBuffers) & 1);
+                waited = true;
+            }
+            float gm_dot_m = 0.f;
 #pragma unroll 1
             for (int p = 0; p < kTaps; ++p) {
-                const float lg = (STAGED && sizeof(T) == 2) ? RS::mask_at(st, lane, p) : Elem<T>::ld(mskp + p);
-                const float mm = expf(lg - mx) * inv_sum;
-                const float v = mm * (park[lane * kTaps + p] - gm_dot_m);
-                if (sizeof(T) == 4) park[lane * kTaps + p] = v;
-                else *reinterpret_cast<__nv_bfloat16*>(st + RS::OFF_BYTES + lane * RS::LANE_MSK + p * 2) = __float2bfloat16_rn(v);
+                const float cx = ox, cy = oy, cm = ml;
+                if (STAGED) {
+                    if (p + 1 < kTaps) RS::tap(st, lane, p + 1, ox, oy, ml);  // (read before tap p's results land)
+                } else {
+                    ox = ox2; oy = oy2; ml = ml2;
+                    if (p + 2 < kTaps) load_tap_inputs<T>(offp, mskp, p + 2, ox2, oy2, ml2);  // two taps ahead
+                }
+                const Tap t = make_tap(q, ref0, ref1, p, cx, cy);
+                const int bx = t.x0 - cx0, by = t.y0 - cy0;
+                const bool inbox = bx >= 0 && bx + 1 < tg.bw && by >= 0 && by + 1 < tg.bh;
+                const float mm = logits ? expf(cm - mx) * inv_sum : cm;
+                float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;  // <go, I_k>: a=(y0,x0) b=(y1,x0) c=(y0,x1) d=(y1,x1)
+                if (__builtin_expect(t.alive && !inbox, 0)) {
+#pragma unroll 1
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const T* src = global_slab_b(x, q, n, t.y0 + (kk & 1), t.x0 + (kk >> 1), g);
+                        if (src == nullptr) continue;
+                        f2 dk2 = 0ull;
+#pragma unroll
+                        for (int pc = 0; pc < C::NPIECE; ++pc) {
+                            f2 v[C::PAIRS];
+                            load_piece<T>(src + Slab<T>::chan_of(pc, rot), v);
+#pragma unroll
+                            for (int j = 0; j < C::PAIRS; ++j) ffma2v(dk2, v[j], go[pc * C::PAIRS + j]);
+                        }
+                        const float dk = lo_of(dk2) + hi_of(dk2);
+                        if (kk == 0) d0 = dk; else if (kk == 1) d1 = dk; else if (kk == 2) d2 = dk; else d3 = dk;
+                    }
+                } else {
+                    const unsigned char* a = sbase + (size_t)(t.alive ? by * tg.bw + bx : 0) * kCellBytes;
+                    f2 va[8], vb[8], e0 = 0ull, e1 = 0ull, e2 = 0ull, e3 = 0ull;
+                    Slab<T>::load(a, rot, va);
+                    Slab<T>::load(a + (size_t)tg.bw * kCellBytes, rot, vb);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) ffma2v(e0, va[c], go[c]);
+                    Slab<T>::load(a + kCellBytes, rot, va);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) ffma2v(e1, vb[c], go[c]);
+                    Slab<T>::load(a + (size_t)(tg.bw + 1) * kCellBytes, rot, vb);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) ffma2v(e2, va[c], go[c]);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) ffma2v(e3, vb[c], go[c]);
+                    d0 = lo_of(e0) + hi_of(e0);
+                    d1 = lo_of(e1) + hi_of(e1);
+                    d2 = lo_of(e2) + hi_of(e2);
+                    d3 = lo_of(e3) + hi_of(e3);
+                }
+                // dead taps have all four deltas zero => zero gradients
+                const float g_m = t.dx1 * t.dy1 * d0 + t.dx1 * t.dy0 * d1 + t.dx0 * t.dy1 * d2 + t.dx0 * t.dy0 * d3;
+                const float gxq = mm * (t.dy1 * (d2 - d0) + t.dy0 * (d3 - d1));
+                const float gyq = mm * (t.dx1 * (d1 - d0) + t.dx0 * (d3 - d2));
+                gm_dot_m += g_m * mm;
+                // results go to the lane's slot positions (lane stride 72 / 36 bytes: conflict free)
+                if (sizeof(T) == 4) {
+                    *reinterpret_cast<float2*>(st + lane * RS::LANE_OFF + p * 8) = make_float2(gxq * q.fx, gyq * q.fy);
+                } else {
+                    *reinterpret_cast<unsigned*>(st + lane * RS::LANE_OFF + p * 4) = pack_bf16x2(gxq * q.fx, gyq * q.fy);
+                }
+                if (logits || sizeof(T) == 4) park[lane * kTaps + p] = g_m;
+                else *reinterpret_cast<__nv_bfloat16*>(st + RS::OFF_BYTES + lane * RS::LANE_MSK + p * 2) = __float2bfloat16_rn(g_m);
+            }
+            // (max |grad_out| is taken here, after the taps: the first use of the freshly loaded grad_out is then
+            //  the first tap's dot products, behind its coordinate arithmetic and shared-memory loads)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) amax = max(amax, max(abs_bits(lo_of(go[c])), abs_bits(hi_of(go[c]))));
+            if (logits) {
+                // softmax Jacobian needs sum_p m_p*dL/dm_p: second sweep over this lane's own 9 values.  The logits
+                // are still in the slot when T is bf16 (the park is a separate area); for fp32 the park has
+                // overwritten them and they are read again from global memory (L1 / L2 hits)
+#pragma unroll 1
+                for (int p = 0; p < kTaps; ++p) {
+                    const float lg = (STAGED && sizeof(T) == 2) ? RS::mask_at(st, lane, p) : Elem<T>::ld(mskp + p);
+                    const float mm = expf(lg - mx) * inv_sum;
+                    const float v = mm * (park[lane * kTaps + p] - gm_dot_m);
+                    if (sizeof(T) == 4) park[lane * kTaps + p] = v;
+                    else *reinterpret_cast<__nv_bfloat16*>(st + RS::OFF_BYTES + lane * RS::LANE_MSK + p * 2) = __float2bfloat16_rn(v);
+                }
+            }
+            if (STAGED) {
+                RS::store_results(st, &goffmap, grad_mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, chunk, wb, n * q.ho + h,
+                                  npx, lane);
+                TileWalk nw = {k, it};  // the slot is free again: the warp's next row segment, here or in a later tile
+                TileCtx nc = ctx;
+                if (next_segment<C::PXW>(q, tg, n_tiles, warp, nw, nc)) request(nc, nw.it);
+            } else {
+                RS::store_off_msk(st, grad_offset + (pix0 * q.G + chunk * C::GQ) * 18,
+                                  grad_mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, npx, ng, lane);
             }
         }
-        if (STAGED) {
-            RS::store_results(st, &goffmap, grad_mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, chunk, wb, n * q.ho + h,
-                              npx, lane);
-            if (it + kTiledWarps < nit) request(it + kTiledWarps);  // the slot is free again
-        } else {
-            RS::store_off_msk(st, grad_offset + (pix0 * q.G + chunk * C::GQ) * 18,
-                              grad_mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, npx, ng, lane);
-        }
-    }
-    if (!waited) mbar_wait(&bar, 0);
+        if (kBoxBuffers > 1)
+            release_box(&released[buf], &full[buf], smem + (size_t)buf * box_bytes, &xmap, q, tg, n_tiles, k, lane, C::GQ);
+        else if (!waited)
+            mbar_wait(&full[buf], 0);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    if (lane == 0) atomicMax(&img_max[n].go_bits, amax);
+        for (int o = 16; o > 0; o >>= 1) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if (lane == 0 && amax != 0u) atomicMax(&img_max[n].go_bits, amax);
+    }
 }
 
 // =====================================================================================================
@@ -417,7 +436,11 @@ __device__ __forceinline__ void red_shared_add(uint32_t addr, int v) {
 // most the sum of the four counters anchored at (y, x), (y-1, x), (y, x-1), (y-1, x-1).  A raw mask beyond
 // the fixed-point range (|m| >= 3.9) makes the four cells hot by itself.
 __device__ __forceinline__ int weight_units(float mm) {
+#ifdef DCNV3_EXP_MAGICUNITS
+    const int wb = fabsf(mm) < 4.0f ? __float_as_int(__fmaf_rn(fabsf(mm), 1025.f, 12582913.0f)) - 0x4B400000 : kBudget + 1;
+#else
     const int wb = __float2int_ru(fabsf(mm) * 1025.f);
+#endif
     return wb < 3994 ? wb : kBudget + 1;
 }
 template <int WP>
@@ -431,7 +454,13 @@ __device__ __forceinline__ int qmul(int g, int wq) {
 }
 // (|wf| < 3.9 whenever the tap's cells are not hot -- weight_units() -- so the conversion cannot saturate there;
 //  for hot cells it may, deterministically, and those accumulators are discarded and recomputed)
+#ifdef DCNV3_EXP_MAGICWEIGHT
+__device__ __forceinline__ int weight_fixed(float wf) {
+    return (__float_as_int(__fmaf_rn(wf, 1048576.0f, 12582912.0f)) - 0x4B400000) << (kWShift - 20);
+}
+#else
 __device__ __forceinline__ int weight_fixed(float wf) { return __float2int_rn(wf * (float)(1 << kWShift)); }
+#endif
 
 // one landing into the 64-bit side buffer: the same integers q as the shared-memory path; |Wk| >= 3.9
 // (raw masks only) is pre-shifted so that the product still fits
@@ -836,14 +865,14 @@ static cudaError_t launch_gather_variant(const CUtensorMap& map, const CUtensorM
                                          void* grad_offset, void* grad_mask, ImgMax* img_max, const KParams& q,
                                          const TileGeom& tg, cudaStream_t st) {
     cudaError_t e = ensure_max_smem((const void*)bwd_gather_kernel<T, STAGED>,
-                                    kMaxBoxBytes + kTiledWarps * kGatherStageBytes<T>);
+                                    kBoxBuffers * kMaxBoxBytes + kTiledWarps * kGatherStageBytes<T>);
     if (e != cudaSuccess) return e;
-    const unsigned grid = (unsigned)((size_t)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
+    const int n_tiles = (int)((size_t)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
     // (also leaves the per-image max |grad_out| in the workspace: the fixed-point scale of the scatter kernel)
-    return launch_pdl(bwd_gather_kernel<T, STAGED>, grid, kTiledWarps * 32,
-                      (size_t)tg.bw * tg.bh * kCellBytes + kTiledWarps * kGatherStageBytes<T>, st, map, offmap, goffmap,
-                      (const T*)x, (const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_offset, (T*)grad_mask,
-                      img_max, q, tg);
+    return launch_pdl(bwd_gather_kernel<T, STAGED>, tiled_grid(n_tiles), kTiledWarps * 32,
+                      (size_t)kBoxBuffers * tg.bw * tg.bh * kCellBytes + kTiledWarps * kGatherStageBytes<T>, st, map, offmap,
+                      goffmap, (const T*)x, (const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_offset,
+                      (T*)grad_mask, img_max, q, tg, n_tiles);
 }
 
 template <typename T>

@@ -24,32 +24,25 @@ __device__ __forceinline__ const T* global_slab(const T* x, const KParams& q, in
 }
 
 template <typename T, bool STAGED>
-__global__ void __launch_bounds__(kTiledWarps * 32, 2)
+__global__ void __launch_bounds__(kTiledWarps * 32, kTiledCtasPerSm)
 fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap offmap,
                  const T* __restrict__ x, const T* __restrict__ offset, const T* __restrict__ mask,
-                 T* __restrict__ out, const KParams q, const TileGeom tg) {
+                 T* __restrict__ out, const KParams q, const TileGeom tg, const int n_tiles) {
     using C = Chunk<T>;
     using RS = RowStage<T>;
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t full[kBoxBuffers];
     __shared__ __align__(8) uint64_t sbar[kTiledWarps];
+    __shared__ unsigned released[kBoxBuffers];
     pdl_launch_dependents();  // the next kernel of the stream may start its prologue (it waits before reading)
 
-    // ---- which tile ----
-    int b = blockIdx.x;
-    const int tx = b % tg.tiles_w; b /= tg.tiles_w;
-    const int ty = b % tg.tiles_h; b /= tg.tiles_h;
-    const int chunk = b % tg.chunks;
-    const int n = b / tg.chunks;
-    const int h0 = ty * tg.th, w0 = tx * tg.tw;
-    const int th = min(tg.th, q.ho - h0), tw = min(tg.tw, q.wo - w0);
-    // box origin in padded coordinates (output rows h walk along x, columns w along y)
-    // (kept inside the padded image: cells beyond it can only belong to dead taps)
-    const int cx0 = max(0, min((int)floorf(nominal_x(q, h0)) - tg.halo_x, q.win - tg.bw));
-    const int cy0 = max(0, min((int)floorf(nominal_y(q, w0)) - tg.halo_y, q.hin - tg.bh));
-
+    const int box_bytes = tg.bw * tg.bh * kCellBytes;
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+#pragma unroll
+        for (int i = 0; i < kBoxBuffers; ++i) {
+            mbar_init(&full[i], 1);
+            released[i] = 0u;
+        }
 #pragma unroll
         for (int i = 0; i < kTiledWarps; ++i) mbar_init(&sbar[i], 1);
         fence_mbar_init();
@@ -57,127 +50,153 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     __syncthreads();
     pdl_wait();  // from here on global memory is read: everything the previous kernels wrote is visible
     if (threadIdx.x == 0) {
-        mbar_expect_tx(&bar, (uint32_t)(tg.bw * tg.bh * kCellBytes));
-        tma_load_4d(smem, &xmap, &bar, chunk * C::GQ * kGC, cx0 - q.pw, cy0 - q.ph, n);
+#pragma unroll
+        for (int i = 0; i < kBoxBuffers; ++i) {
+            const int t = blockIdx.x + i * gridDim.x;
+            if (t < n_tiles) {
+                const TileCtx c = decode_tile<1>(q, tg, t);
+                mbar_expect_tx(&full[i], (uint32_t)box_bytes);
+                tma_load_4d(smem + (size_t)i * box_bytes, &xmap, &full[i], c.chunk * C::GQ * kGC, c.cx0 - q.pw, c.cy0 - q.ph,
+                            c.n);
+            }
+        }
     }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g_l = lane % C::GQ, px_l = lane / C::GQ;
-    const bool real_g = chunk * C::GQ + g_l < q.G;          // false for the phantom groups of a trailing chunk
-    const int g = min(chunk * C::GQ + g_l, q.G - 1);        // (phantom lanes shadow the last group, never store)
     const int rot = Slab<T>::rot_of(px_l);
-    const unsigned char* sbase = smem + g_l * (kGC * (int)sizeof(T));
-    unsigned char* st = smem + (size_t)tg.bw * tg.bh * kCellBytes + warp * RS::BYTES;  // the warp's side slot
+    unsigned char* st = smem + (size_t)kBoxBuffers * box_bytes + warp * RS::BYTES;  // the warp's side slot
     const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
-    const int colblocks = (tw + C::PXW - 1) / C::PXW, nit = th * colblocks;
-    bool waited = false;
     uint32_t sphase = 0;
 
     // side inputs of one warp iteration (PXW consecutive pixels of one output row) -> the warp's slot
-    auto request = [&](int it) {
-        const int h = h0 + it / colblocks, wb = w0 + (it % colblocks) * C::PXW;
-        const size_t pix0 = ((size_t)n * q.ho + h) * q.wo + wb;
-        RS::request(st, &sbar[warp], &offmap, mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, chunk, wb, n * q.ho + h,
-                    min(C::PXW, w0 + tw - wb), lane);
+    auto request = [&](const TileCtx& c, int it) {
+        const int h = c.h0 + it / c.colblocks, wb = c.w0 + (it % c.colblocks) * C::PXW;
+        const size_t pix0 = ((size_t)c.n * q.ho + h) * q.wo + wb;
+        RS::request(st, &sbar[warp], &offmap, mask + (pix0 * q.G + c.chunk * C::GQ) * 9, q.G, c.chunk, wb, c.n * q.ho + h,
+                    min(C::PXW, c.w0 + c.tw - wb), lane);
     };
-    if (STAGED && warp < nit) request(warp);
-
-    for (int it = warp; it < nit; it += kTiledWarps) {
-        const int h = h0 + it / colblocks, wb = w0 + (it % colblocks) * C::PXW;
-        const int npx = min(C::PXW, w0 + tw - wb);
-        const bool valid = real_g && px_l < npx;
-        const int w = wb + min(px_l, npx - 1);  // idle lanes shadow the last pixel (loads stay in bounds)
-        const size_t pg = (((size_t)n * q.ho + h) * q.wo + w) * q.G + g;
-        const T* offp = offset + pg * 18;
-        const T* mskp = mask + pg * 9;
-        float ref0, ref1;
-        ref_point(q, h, w, ref0, ref1);
-        if (STAGED) {
-            cp_async_wait_all();
-            __syncwarp();
-            mbar_wait(&sbar[warp], sphase);
-            sphase ^= 1;
-        }
-        float mx = 0.f, inv_sum = 1.f;
-        if (logits) {
-            if (STAGED) RS::softmax_stats(st, lane, mx, inv_sum);
-            else softmax_stats9<T>(mskp, mx, inv_sum);
-        }
-        f2 acc[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = 0ull;
-        float ox, oy, ml, ox2 = 0.f, oy2 = 0.f, ml2 = 0.f;
-        if (STAGED) {
-            RS::tap(st, lane, 0, ox, oy, ml);
-        } else {
-            load_tap_inputs<T>(offp, mskp, 0, ox, oy, ml);
-            load_tap_inputs<T>(offp, mskp, 1, ox2, oy2, ml2);
-        }
-        if (!waited) {  // the box is needed from here on
-            mbar_wait(&bar, 0);
-            waited = true;
-        }
-#pragma unroll 1
-        for (int p = 0; p < kTaps; ++p) {
-            const float cx = ox, cy = oy, cm = ml;
-            if (STAGED) {
-                if (p + 1 < kTaps) RS::tap(st, lane, p + 1, ox, oy, ml);  // shared memory: one tap ahead is enough
-            } else {
-                ox = ox2; oy = oy2; ml = ml2;
-                if (p + 2 < kTaps) load_tap_inputs<T>(offp, mskp, p + 2, ox2, oy2, ml2);  // prefetch two taps ahead
-            }
-            const Tap t = make_tap(q, ref0, ref1, p, cx, cy);
-            const int bx = t.x0 - cx0, by = t.y0 - cy0;
-            const bool inbox = bx >= 0 && bx + 1 < tg.bw && by >= 0 && by + 1 < tg.bh;
-            const float mm = t.alive ? (logits ? expf(cm - mx) * inv_sum : cm) : 0.f;
-            const float wa = t.dx1 * t.dy1 * mm, wb_ = t.dx1 * t.dy0 * mm;  // (y0,x0) (y1,x0)
-            const float wc = t.dx0 * t.dy1 * mm, wd = t.dx0 * t.dy0 * mm;   // (y0,x1) (y1,x1)
-            if (__builtin_expect(t.alive && !inbox, 0)) {
-                // rare: patch outside the staged box -> straight from global memory
-#pragma unroll 1
-                for (int k = 0; k < 4; ++k) {
-                    const T* src = global_slab(x, q, n, t.y0 + (k & 1), t.x0 + (k >> 1), g);
-                    if (src == nullptr) continue;
-                    const float wk = (k & 1) ? ((k >> 1) ? wd : wb_) : ((k >> 1) ? wc : wa);
-#pragma unroll
-                    for (int pc = 0; pc < C::NPIECE; ++pc) {
-                        f2 v[C::PAIRS];
-                        load_piece<T>(src + Slab<T>::chan_of(pc, rot), v);
-#pragma unroll
-                        for (int j = 0; j < C::PAIRS; ++j) ffma2s(acc[pc * C::PAIRS + j], v[j], wk);
-                    }
-                }
-            } else {
-                // dead taps carry zero weights and read cell 0
-                const unsigned char* a = sbase + (size_t)(t.alive ? by * tg.bw + bx : 0) * kCellBytes;
-                f2 va[8], vb[8];
-                Slab<T>::load(a, rot, va);
-                Slab<T>::load(a + (size_t)tg.bw * kCellBytes, rot, vb);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) ffma2s(acc[c], va[c], wa);
-                Slab<T>::load(a + kCellBytes, rot, va);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) ffma2s(acc[c], vb[c], wb_);
-                Slab<T>::load(a + (size_t)(tg.bw + 1) * kCellBytes, rot, vb);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) ffma2s(acc[c], va[c], wc);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) ffma2s(acc[c], vb[c], wd);
-            }
-        }
-        if (STAGED) {
-            // every lane has consumed its slot values (they fed the arithmetic above): refill for the next iteration
-            __syncwarp();
-            if (it + kTiledWarps < nit) request(it + kTiledWarps);
-        }
-        if (valid) {
-            T* dst = out + pg * kGC;
-#pragma unroll
-            for (int pc = 0; pc < C::NPIECE; ++pc)
-                store_piece<T>(dst + Slab<T>::chan_of(pc, rot), acc + pc * C::PAIRS);
-        }
+    if (STAGED) {  // the warp's first row segment
+        TileWalk nw = {0, warp - kTiledWarps};
+        TileCtx nc = decode_tile<C::PXW>(q, tg, blockIdx.x);
+        if (next_segment<C::PXW>(q, tg, n_tiles, warp, nw, nc)) request(nc, nw.it);
     }
-    if (!waited) mbar_wait(&bar, 0);  // never leave with a TMA in flight
+
+    int k = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+        const TileCtx ctx = decode_tile<C::PXW>(q, tg, tile);
+        const int buf = k % kBoxBuffers;
+        const unsigned char* box = smem + (size_t)buf * box_bytes;
+        const unsigned char* sbase = box + g_l * (kGC * (int)sizeof(T));
+        const int n = ctx.n, chunk = ctx.chunk, cx0 = ctx.cx0, cy0 = ctx.cy0;
+        const bool real_g = chunk * C::GQ + g_l < q.G;    // false for the phantom groups of a trailing chunk
+        const int g = min(chunk * C::GQ + g_l, q.G - 1);  // (phantom lanes shadow the last group, never store)
+        bool waited = false;
+        for (int it = warp; it < ctx.nit; it += kTiledWarps) {
+            const int h = ctx.h0 + it / ctx.colblocks, wb = ctx.w0 + (it % ctx.colblocks) * C::PXW;
+            const int npx = min(C::PXW, ctx.w0 + ctx.tw - wb);
+            const bool valid = real_g && px_l < npx;
+            const int w = wb + min(px_l, npx - 1);  // idle lanes shadow the last pixel (loads stay in bounds)
+            const size_t pg = (((size_t)n * q.ho + h) * q.wo + w) * q.G + g;
+            const T* offp = offset + pg * 18;
+            const T* mskp = mask + pg * 9;
+            float ref0, ref1;
+            ref_point(q, h, w, ref0, ref1);
+            if (STAGED) {
+                cp_async_wait_all();
+                __syncwarp();
+                mbar_wait(&sbar[warp], sphase);
+                sphase ^= 1;
+            }
+            float mx = 0.f, inv_sum = 1.f;
+            if (logits) {
+                if (STAGED) RS::softmax_stats(st, lane, mx, inv_sum);
+                else softmax_stats9<T>(mskp, mx, inv_sum);
+            }
+            f2 acc[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = 0ull;
+            float ox, oy, ml, ox2 = 0.f, oy2 = 0.f, ml2 = 0.f;
+            if (STAGED) {
+                RS::tap(st, lane, 0, ox, oy, ml);
+            } else {
+                load_tap_inputs<T>(offp, mskp, 0, ox, oy, ml);
+                load_tap_inputs<T>(offp, mskp, 1, ox2, oy2, ml2);
+            }
+            if (!waited) {  // the box is needed from here on
+                mbar_wait(&full[buf], (k / kBoxBuffers) & 1);
+                waited = true;
+            }
+#pragma unroll 1
+            for (int p = 0; p < kTaps; ++p) {
+                const float cx = ox, cy = oy, cm = ml;
+                if (STAGED) {
+                    if (p + 1 < kTaps) RS::tap(st, lane, p + 1, ox, oy, ml);  // shared memory: one tap ahead is enough
+                } else {
+                    ox = ox2; oy = oy2; ml = ml2;
+                    if (p + 2 < kTaps) load_tap_inputs<T>(offp, mskp, p + 2, ox2, oy2, ml2);  // prefetch two taps ahead
+                }
+                const Tap t = make_tap(q, ref0, ref1, p, cx, cy);
+                const int bx = t.x0 - cx0, by = t.y0 - cy0;
+                const bool inbox = bx >= 0 && bx + 1 < tg.bw && by >= 0 && by + 1 < tg.bh;
+                const float mm = t.alive ? (logits ? expf(cm - mx) * inv_sum : cm) : 0.f;
+                const float wa = t.dx1 * t.dy1 * mm, wb_ = t.dx1 * t.dy0 * mm;  // (y0,x0) (y1,x0)
+                const float wc = t.dx0 * t.dy1 * mm, wd = t.dx0 * t.dy0 * mm;   // (y0,x1) (y1,x1)
+                if (__builtin_expect(t.alive && !inbox, 0)) {
+                    // rare: patch outside the staged box -> straight from global memory
+#pragma unroll 1
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const T* src = global_slab(x, q, n, t.y0 + (kk & 1), t.x0 + (kk >> 1), g);
+                        if (src == nullptr) continue;
+                        const float wk = (kk & 1) ? ((kk >> 1) ? wd : wb_) : ((kk >> 1) ? wc : wa);
+#pragma unroll
+                        for (int pc = 0; pc < C::NPIECE; ++pc) {
+                            f2 v[C::PAIRS];
+                            load_piece<T>(src + Slab<T>::chan_of(pc, rot), v);
+#pragma unroll
+                            for (int j = 0; j < C::PAIRS; ++j) ffma2s(acc[pc * C::PAIRS + j], v[j], wk);
+                        }
+                    }
+                } else {
+                    // dead taps carry zero weights and read cell 0
+                    const unsigned char* a = sbase + (size_t)(t.alive ? by * tg.bw + bx : 0) * kCellBytes;
+                    f2 va[8], vb[8];
+                    Slab<T>::load(a, rot, va);
+                    Slab<T>::load(a + (size_t)tg.bw * kCellBytes, rot, vb);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) ffma2s(acc[c], va[c], wa);
+                    Slab<T>::load(a + kCellBytes, rot, va);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) ffma2s(acc[c], vb[c], wb_);
+                    Slab<T>::load(a + (size_t)(tg.bw + 1) * kCellBytes, rot, vb);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) ffma2s(acc[c], va[c], wc);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) ffma2s(acc[c], vb[c], wd);
+                }
+            }
+            if (STAGED) {
+                // every lane has consumed its slot values (they fed the arithmetic above): refill with the warp's
+                // next row segment, here or in a later tile
+                __syncwarp();
+                TileWalk nw = {k, it};
+                TileCtx nc = ctx;
+                if (next_segment<C::PXW>(q, tg, n_tiles, warp, nw, nc)) request(nc, nw.it);
+            }
+            if (valid) {
+                T* dst = out + pg * kGC;
+#pragma unroll
+                for (int pc = 0; pc < C::NPIECE; ++pc)
+                    store_piece<T>(dst + Slab<T>::chan_of(pc, rot), acc + pc * C::PAIRS);
+            }
+        }
+        if (kBoxBuffers > 1)
+            release_box(&released[buf], &full[buf], smem + (size_t)buf * box_bytes, &xmap, q, tg, n_tiles, k, lane, C::GQ);
+        else if (!waited)
+            mbar_wait(&full[buf], 0);  // never leave with a TMA in flight
+    }
+    // (every box that was requested belongs to a tile of this CTA, and warp 0 at least has waited for it: no TMA
+    //  is in flight when the CTA's last warp leaves)
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -195,6 +214,18 @@ static EncodeTiledFn encode_fn() {
         return (EncodeTiledFn) nullptr;
     }();
     return fn;
+}
+
+// CTAs of a forward / gather launch: every tile its own CTA, or (persistent) one CTA per SM walking over the tiles
+unsigned tiled_grid(int n_tiles) {
+    if (kBoxBuffers == 1) return (unsigned)n_tiles;
+    static thread_local int sms[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& n = sms[dev & 63];
+    if (n == 0 && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+    const int slots = n * kTiledCtasPerSm;
+    return (unsigned)(n_tiles < slots ? n_tiles : slots);
 }
 
 cudaError_t ensure_max_smem(const void* kernel, int bytes) {
@@ -354,13 +385,14 @@ bool tiled_applicable(const KParams& q, int dtype) {
 template <typename T, bool STAGED>
 static cudaError_t launch_fwd_variant(const CUtensorMap& map, const CUtensorMap& offmap, const void* x, const void* offset,
                                       const void* mask, void* out, const KParams& q, const TileGeom& tg, cudaStream_t st) {
-    const size_t smem = (size_t)tg.bw * tg.bh * kCellBytes + (STAGED ? kTiledWarps * RowStage<T>::BYTES : 0);
+    const size_t smem = (size_t)kBoxBuffers * tg.bw * tg.bh * kCellBytes + (STAGED ? kTiledWarps * RowStage<T>::BYTES : 0);
     cudaError_t e = ensure_max_smem((const void*)fwd_tiled_kernel<T, STAGED>,
-                                    STAGED ? kMaxBoxBytes + kTiledWarps * RowStage<T>::BYTES : kFwdBoxBytes);
+                                    kBoxBuffers * (STAGED ? kMaxBoxBytes : kFwdBoxBytes) +
+                                        (STAGED ? kTiledWarps * RowStage<T>::BYTES : 0));
     if (e != cudaSuccess) return e;
-    const unsigned grid = (unsigned)((size_t)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
-    return launch_pdl(fwd_tiled_kernel<T, STAGED>, grid, kTiledWarps * 32, smem, st, map, offmap, (const T*)x,
-                      (const T*)offset, (const T*)mask, (T*)out, q, tg);
+    const int n_tiles = (int)((size_t)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
+    return launch_pdl(fwd_tiled_kernel<T, STAGED>, tiled_grid(n_tiles), kTiledWarps * 32, smem, st, map, offmap,
+                      (const T*)x, (const T*)offset, (const T*)mask, (T*)out, q, tg, n_tiles);
 }
 
 template <typename T>
@@ -390,12 +422,12 @@ static void geom_numbers(const KParams& q, const TileGeom& tg, long long smem, i
 void fwd_tiled_plan(const KParams& q, int dtype, int out[8]) {
     const TileGeom tg = make_geom(q, dtype, 16, 16, 3.0f, fwd_box_bytes(q, dtype) / kCellBytes);
     const int slot = dtype == DCNV3_F32 ? RowStage<float>::BYTES : RowStage<__nv_bfloat16>::BYTES;
-    geom_numbers(q, tg, (long long)tg.bw * tg.bh * kCellBytes + (side_stageable(q, dtype) ? kTiledWarps * slot : 0), out);
+    geom_numbers(q, tg, (long long)kBoxBuffers * tg.bw * tg.bh * kCellBytes + (side_stageable(q, dtype) ? kTiledWarps * slot : 0), out);
 }
 
 void gather_tiled_plan(const KParams& q, int dtype, int stage_bytes, int out[8]) {
     const TileGeom tg = make_geom(q, dtype, 16, 16, 3.0f, kMaxBoxBytes / kCellBytes);
-    geom_numbers(q, tg, (long long)tg.bw * tg.bh * kCellBytes + stage_bytes, out);
+    geom_numbers(q, tg, (long long)kBoxBuffers * tg.bw * tg.bh * kCellBytes + stage_bytes, out);
 }
 
 cudaError_t launch_fwd_tiled(const void* x, const void* offset, const void* mask, void* out,
