@@ -89,18 +89,9 @@ __device__ __forceinline__ Axis make_axis(float coord, float max_f /* dim-1 */) 
 // (0 <= f and f + 1 <= dim-1), so the deltas are formed from f directly -- bit-identical to make_axis.
 __device__ __forceinline__ Axis make_axis_live(float coord, float max_f /* dim-1 */) {
     Axis a;
-#ifdef DCNV3_EXP_MAGICFLOOR
-    // floor without the conversion unit: adding 1.5 * 2^23 with round-down leaves floor(coord) in the low mantissa
-    // bits (exact for |coord| < 2^22; anything larger fails the range test below and the tap is dead)
-    const float t = __fadd_rd(coord, 12582912.0f);
-    const float f = t - 12582912.0f;
-    a.alive = (f >= 0.0f) && (f < max_f);
-    a.i0 = __float_as_int(t) - 0x4B400000;
-#else
     const float f = floorf(coord);
     a.alive = (f >= 0.0f) && (f < max_f);
     a.i0 = (int)f;
-#endif
     a.d0 = __fsub_rn(coord, f);
     a.d1 = __fsub_rn(f + 1.0f, coord);
     return a;

@@ -21,17 +21,11 @@ constexpr int kGC = 16;
 constexpr int kCellBytes = 128;
 constexpr int kMaxBoxBytes = 82 * 1024;  // staged input box of the forward / gather kernels; with the per-warp side slots two CTAs fit one SM
 constexpr int kFwdBoxBytes = 100 * 1024; // forward box when the side inputs are not staged (no slots): two CTAs per SM
-// Forward / gather launch shape.  Persistent: one 16-warp CTA per SM walks over tiles t = blockIdx.x, + gridDim.x, ...
-// with TWO input boxes, so that the TMA load of the next tile's box runs under the current tile's arithmetic.
-// (DCNV3_ONE_TILE_PER_CTA selects the round-1 shape for A/B runs: 8-warp CTAs, one tile each, two per SM.)
-#ifdef DCNV3_ONE_TILE_PER_CTA
+// Forward / gather launch shape: 8-warp CTAs, one tile each, two CTAs per SM (one CTA's box load runs under the
+// other's arithmetic).  A persistent variant -- one 16-warp CTA per SM walking over tiles with two input boxes, the
+// next tile's TMA load under the current tile's arithmetic -- was measured and lost by 3-8 % on every InternImage-T
+// shape but 64x64 (profiles/r02_ab.md), so it is not kept.
 constexpr int kTiledWarps = 8;
-constexpr int kBoxBuffers = 1;
-#else
-constexpr int kTiledWarps = 16;
-constexpr int kBoxBuffers = 2;
-#endif
-constexpr int kTiledCtasPerSm = kBoxBuffers == 2 ? 1 : 2;
 
 template <typename T>
 struct Chunk {
@@ -64,7 +58,6 @@ bool make_x_tensor_map(CUtensorMap* map, const void* x, const KParams& q, int dt
 // [N*Ho][Wo][G*per_group] view of offset / mask (and their gradients), box = one warp iteration of one chunk
 bool side_stageable(const KParams& q, int dtype);
 bool make_side_tensor_map(CUtensorMap* map, const void* base, const KParams& q, int dtype, int per_group);
-unsigned tiled_grid(int n_tiles);
 // raises a kernel's dynamic shared-memory limit once per (kernel, device); safe to call from any thread
 cudaError_t ensure_max_smem(const void* kernel, int bytes);
 
@@ -185,43 +178,6 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 //      this one drains; it must not touch global memory before pdl_wait() ------------------------------
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
-// Shared skeleton of the forward and gather kernels: the CTA's tiles are t = blockIdx.x + k * gridDim.x.  Tile k's
-// input box lives in buffer k % kBoxBuffers; when the last warp has finished with a buffer, that warp's lane 0 asks the
-// TMA unit for the box of tile k + kBoxBuffers.  Every warp always has exactly one side-slot request in flight: its
-// next row segment, in this tile or in the next one that has a segment for it.
-struct TileWalk {
-    int k, it;  // position of the warp: its it-th row segment of the CTA's k-th tile
-};
-template <int PXW>
-__device__ __forceinline__ bool next_segment(const KParams& q, const TileGeom& tg, int n_tiles, int warp, TileWalk& w,
-                                             TileCtx& ctx) {
-    w.it += kTiledWarps;
-    for (;;) {
-        if (w.it < ctx.nit) return true;
-        ++w.k;
-        const int t = blockIdx.x + w.k * gridDim.x;
-        if (t >= n_tiles) return false;
-        ctx = decode_tile<PXW>(q, tg, t);
-        w.it = warp;
-    }
-}
-
-// a warp is done with box buffer `buf` (tile k): the last of the CTA's warps to say so refills it with tile k + 2
-__device__ __forceinline__ void release_box(unsigned* cnt, uint64_t* full, unsigned char* box, const CUtensorMap* xmap,
-                                            const KParams& q, const TileGeom& tg, int n_tiles, int k, int lane, int gq) {
-    __syncwarp();
-    if (lane != 0) return;
-    __threadfence_block();  // this warp's reads of the box precede the refill
-    if (atomicAdd(cnt, 1u) != kTiledWarps - 1) return;
-    *cnt = 0u;
-    const int t = blockIdx.x + (k + kBoxBuffers) * gridDim.x;
-    if (t >= n_tiles) return;
-    __threadfence_block();
-    const TileCtx c = decode_tile<1>(q, tg, t);
-    mbar_expect_tx(full, (uint32_t)(tg.bw * tg.bh * kCellBytes));
-    tma_load_4d(box, xmap, full, c.chunk * gq * kGC, c.cx0 - q.pw, c.cy0 - q.ph, c.n);
-}
 
 // ---- packed fp32 pairs: Blackwell issues two fp32 FMAs per instruction (PTX fma.rn.f32x2, SASS FFMA2) ----
 typedef unsigned long long f2;  // {lo, hi} = two consecutive channels

@@ -188,44 +188,32 @@ __device__ __forceinline__ void load_fixed_point_go(const T* go, float sg, int r
 // grad_offset / grad_mask
 // =====================================================================================================
 template <typename T, bool STAGED>
-__global__ void __launch_bounds__(kTiledWarps * 32, kTiledCtasPerSm)
+__global__ void __launch_bounds__(kTiledWarps * 32, 2)
 bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap offmap,
                   const __grid_constant__ CUtensorMap goffmap, const T* __restrict__ x,
                   const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
                   T* __restrict__ grad_offset, T* __restrict__ grad_mask, ImgMax* __restrict__ img_max, const KParams q,
-                  const TileGeom tg, const int n_tiles) {
+                  const TileGeom tg) {
     using C = Chunk<T>;
     using RS = RowStage<T>;
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t full[kBoxBuffers];
+    __shared__ __align__(8) uint64_t bar;
     __shared__ __align__(8) uint64_t sbar[kTiledWarps];
-    __shared__ unsigned released[kBoxBuffers];
     pdl_launch_dependents();
 
     const int box_bytes = tg.bw * tg.bh * kCellBytes;
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < kBoxBuffers; ++i) {
-            mbar_init(&full[i], 1);
-            released[i] = 0u;
-        }
+        mbar_init(&bar, 1);
 #pragma unroll
         for (int i = 0; i < kTiledWarps; ++i) mbar_init(&sbar[i], 1);
         fence_mbar_init();
     }
     __syncthreads();
     pdl_wait();
+    const TileCtx ctx = decode_tile<C::PXW>(q, tg, blockIdx.x);
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < kBoxBuffers; ++i) {
-            const int t = blockIdx.x + i * gridDim.x;
-            if (t < n_tiles) {
-                const TileCtx c = decode_tile<1>(q, tg, t);
-                mbar_expect_tx(&full[i], (uint32_t)box_bytes);
-                tma_load_4d(smem + (size_t)i * box_bytes, &xmap, &full[i], c.chunk * C::GQ * kGC, c.cx0 - q.pw, c.cy0 - q.ph,
-                            c.n);
-            }
-        }
+        mbar_expect_tx(&bar, (uint32_t)box_bytes);
+        tma_load_4d(smem, &xmap, &bar, ctx.chunk * C::GQ * kGC, ctx.cx0 - q.pw, ctx.cy0 - q.ph, ctx.n);
     }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -234,7 +222,7 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
     // The warp's slot: side inputs in (STAGED), results out -- every result overwrites the input value of the
     // same tap (identical layout), and the slot is stored once per row segment.  For the fused soft-max path an
     // fp32 park holds dL/dm_p (it aliases the mask part when T is fp32).
-    unsigned char* st = smem + (size_t)kBoxBuffers * box_bytes + warp * kGatherStageBytes<T>;
+    unsigned char* st = smem + (size_t)box_bytes + warp * kGatherStageBytes<T>;
     float* park = sizeof(T) == 4 ? reinterpret_cast<float*>(st + RS::OFF_BYTES)
                                  : reinterpret_cast<float*>(st + RS::BYTES);
     const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
@@ -246,17 +234,10 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
         RS::request(st, &sbar[warp], &offmap, mask + (pix0 * q.G + c.chunk * C::GQ) * 9, q.G, c.chunk, wb, c.n * q.ho + h,
                     min(C::PXW, c.w0 + c.tw - wb), lane);
     };
-    if (STAGED) {  // the warp's first row segment
-        TileWalk nw = {0, warp - kTiledWarps};
-        TileCtx nc = decode_tile<C::PXW>(q, tg, blockIdx.x);
-        if (next_segment<C::PXW>(q, tg, n_tiles, warp, nw, nc)) request(nc, nw.it);
-    }
+    if (STAGED && warp < ctx.nit) request(ctx, warp);  // the warp's first row segment
 
-    int k = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
-        const TileCtx ctx = decode_tile<C::PXW>(q, tg, tile);
-        const int buf = k % kBoxBuffers;
-        const unsigned char* sbase = smem + (size_t)buf * box_bytes + g_l * (kGC * (int)sizeof(T));
+    {
+        const unsigned char* sbase = smem + g_l * (kGC * (int)sizeof(T));
         const int n = ctx.n, chunk = ctx.chunk, cx0 = ctx.cx0, cy0 = ctx.cy0;
         const int g = min(chunk * C::GQ + g_l, q.G - 1);  // phantom groups of a trailing chunk shadow the last one
         const int ng = min(C::GQ, q.G - chunk * C::GQ);   // real groups in this chunk
@@ -297,7 +278,7 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
                 load_tap_inputs<T>(offp, mskp, 1, ox2, oy2, ml2);
             }
             if (!waited) {
-                mbar_wait(&full[buf], (k / kBoxBuffers) & 1);
+                mbar_wait(&bar, 0);
                 waited = true;
             }
             float gm_dot_m = 0.f;
@@ -385,18 +366,13 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
             if (STAGED) {
                 RS::store_results(st, &goffmap, grad_mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, chunk, wb, n * q.ho + h,
                                   npx, lane);
-                TileWalk nw = {k, it};  // the slot is free again: the warp's next row segment, here or in a later tile
-                TileCtx nc = ctx;
-                if (next_segment<C::PXW>(q, tg, n_tiles, warp, nw, nc)) request(nc, nw.it);
+                if (it + kTiledWarps < ctx.nit) request(ctx, it + kTiledWarps);  // the slot is free again
             } else {
                 RS::store_off_msk(st, grad_offset + (pix0 * q.G + chunk * C::GQ) * 18,
                                   grad_mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, npx, ng, lane);
             }
         }
-        if (kBoxBuffers > 1)
-            release_box(&released[buf], &full[buf], smem + (size_t)buf * box_bytes, &xmap, q, tg, n_tiles, k, lane, C::GQ);
-        else if (!waited)
-            mbar_wait(&full[buf], 0);
+        if (!waited) mbar_wait(&bar, 0);  // never leave with a TMA in flight
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
         if (lane == 0 && amax != 0u) atomicMax(&img_max[n].go_bits, amax);
@@ -436,11 +412,7 @@ __device__ __forceinline__ void red_shared_add(uint32_t addr, int v) {
 // most the sum of the four counters anchored at (y, x), (y-1, x), (y, x-1), (y-1, x-1).  A raw mask beyond
 // the fixed-point range (|m| >= 3.9) makes the four cells hot by itself.
 __device__ __forceinline__ int weight_units(float mm) {
-#ifdef DCNV3_EXP_MAGICUNITS
-    const int wb = fabsf(mm) < 4.0f ? __float_as_int(__fmaf_rn(fabsf(mm), 1025.f, 12582913.0f)) - 0x4B400000 : kBudget + 1;
-#else
     const int wb = __float2int_ru(fabsf(mm) * 1025.f);
-#endif
     return wb < 3994 ? wb : kBudget + 1;
 }
 template <int WP>
@@ -454,13 +426,7 @@ __device__ __forceinline__ int qmul(int g, int wq) {
 }
 // (|wf| < 3.9 whenever the tap's cells are not hot -- weight_units() -- so the conversion cannot saturate there;
 //  for hot cells it may, deterministically, and those accumulators are discarded and recomputed)
-#ifdef DCNV3_EXP_MAGICWEIGHT
-__device__ __forceinline__ int weight_fixed(float wf) {
-    return (__float_as_int(__fmaf_rn(wf, 1048576.0f, 12582912.0f)) - 0x4B400000) << (kWShift - 20);
-}
-#else
 __device__ __forceinline__ int weight_fixed(float wf) { return __float2int_rn(wf * (float)(1 << kWShift)); }
-#endif
 
 // one landing into the 64-bit side buffer: the same integers q as the shared-memory path; |Wk| >= 3.9
 // (raw masks only) is pre-shifted so that the product still fits
@@ -865,14 +831,14 @@ static cudaError_t launch_gather_variant(const CUtensorMap& map, const CUtensorM
                                          void* grad_offset, void* grad_mask, ImgMax* img_max, const KParams& q,
                                          const TileGeom& tg, cudaStream_t st) {
     cudaError_t e = ensure_max_smem((const void*)bwd_gather_kernel<T, STAGED>,
-                                    kBoxBuffers * kMaxBoxBytes + kTiledWarps * kGatherStageBytes<T>);
+                                    kMaxBoxBytes + kTiledWarps * kGatherStageBytes<T>);
     if (e != cudaSuccess) return e;
-    const int n_tiles = (int)((size_t)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
+    const unsigned grid = (unsigned)((size_t)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
     // (also leaves the per-image max |grad_out| in the workspace: the fixed-point scale of the scatter kernel)
-    return launch_pdl(bwd_gather_kernel<T, STAGED>, tiled_grid(n_tiles), kTiledWarps * 32,
-                      (size_t)kBoxBuffers * tg.bw * tg.bh * kCellBytes + kTiledWarps * kGatherStageBytes<T>, st, map, offmap,
-                      goffmap, (const T*)x, (const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_offset,
-                      (T*)grad_mask, img_max, q, tg, n_tiles);
+    return launch_pdl(bwd_gather_kernel<T, STAGED>, grid, kTiledWarps * 32,
+                      (size_t)tg.bw * tg.bh * kCellBytes + kTiledWarps * kGatherStageBytes<T>, st, map, offmap, goffmap,
+                      (const T*)x, (const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_offset, (T*)grad_mask,
+                      img_max, q, tg);
 }
 
 template <typename T>

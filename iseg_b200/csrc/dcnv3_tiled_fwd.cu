@@ -24,48 +24,36 @@ __device__ __forceinline__ const T* global_slab(const T* x, const KParams& q, in
 }
 
 template <typename T, bool STAGED>
-__global__ void __launch_bounds__(kTiledWarps * 32, kTiledCtasPerSm)
+__global__ void __launch_bounds__(kTiledWarps * 32, 2)
 fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap offmap,
                  const T* __restrict__ x, const T* __restrict__ offset, const T* __restrict__ mask,
-                 T* __restrict__ out, const KParams q, const TileGeom tg, const int n_tiles) {
+                 T* __restrict__ out, const KParams q, const TileGeom tg) {
     using C = Chunk<T>;
     using RS = RowStage<T>;
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t full[kBoxBuffers];
+    __shared__ __align__(8) uint64_t bar;
     __shared__ __align__(8) uint64_t sbar[kTiledWarps];
-    __shared__ unsigned released[kBoxBuffers];
     pdl_launch_dependents();  // the next kernel of the stream may start its prologue (it waits before reading)
 
     const int box_bytes = tg.bw * tg.bh * kCellBytes;
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < kBoxBuffers; ++i) {
-            mbar_init(&full[i], 1);
-            released[i] = 0u;
-        }
+        mbar_init(&bar, 1);
 #pragma unroll
         for (int i = 0; i < kTiledWarps; ++i) mbar_init(&sbar[i], 1);
         fence_mbar_init();
     }
     __syncthreads();
     pdl_wait();  // from here on global memory is read: everything the previous kernels wrote is visible
+    const TileCtx ctx = decode_tile<C::PXW>(q, tg, blockIdx.x);
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < kBoxBuffers; ++i) {
-            const int t = blockIdx.x + i * gridDim.x;
-            if (t < n_tiles) {
-                const TileCtx c = decode_tile<1>(q, tg, t);
-                mbar_expect_tx(&full[i], (uint32_t)box_bytes);
-                tma_load_4d(smem + (size_t)i * box_bytes, &xmap, &full[i], c.chunk * C::GQ * kGC, c.cx0 - q.pw, c.cy0 - q.ph,
-                            c.n);
-            }
-        }
+        mbar_expect_tx(&bar, (uint32_t)box_bytes);
+        tma_load_4d(smem, &xmap, &bar, ctx.chunk * C::GQ * kGC, ctx.cx0 - q.pw, ctx.cy0 - q.ph, ctx.n);
     }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g_l = lane % C::GQ, px_l = lane / C::GQ;
     const int rot = Slab<T>::rot_of(px_l);
-    unsigned char* st = smem + (size_t)kBoxBuffers * box_bytes + warp * RS::BYTES;  // the warp's side slot
+    unsigned char* st = smem + (size_t)box_bytes + warp * RS::BYTES;  // the warp's side slot
     const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
     uint32_t sphase = 0;
 
@@ -76,18 +64,10 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         RS::request(st, &sbar[warp], &offmap, mask + (pix0 * q.G + c.chunk * C::GQ) * 9, q.G, c.chunk, wb, c.n * q.ho + h,
                     min(C::PXW, c.w0 + c.tw - wb), lane);
     };
-    if (STAGED) {  // the warp's first row segment
-        TileWalk nw = {0, warp - kTiledWarps};
-        TileCtx nc = decode_tile<C::PXW>(q, tg, blockIdx.x);
-        if (next_segment<C::PXW>(q, tg, n_tiles, warp, nw, nc)) request(nc, nw.it);
-    }
+    if (STAGED && warp < ctx.nit) request(ctx, warp);  // the warp's first row segment
 
-    int k = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
-        const TileCtx ctx = decode_tile<C::PXW>(q, tg, tile);
-        const int buf = k % kBoxBuffers;
-        const unsigned char* box = smem + (size_t)buf * box_bytes;
-        const unsigned char* sbase = box + g_l * (kGC * (int)sizeof(T));
+    {
+        const unsigned char* sbase = smem + g_l * (kGC * (int)sizeof(T));
         const int n = ctx.n, chunk = ctx.chunk, cx0 = ctx.cx0, cy0 = ctx.cy0;
         const bool real_g = chunk * C::GQ + g_l < q.G;    // false for the phantom groups of a trailing chunk
         const int g = min(chunk * C::GQ + g_l, q.G - 1);  // (phantom lanes shadow the last group, never store)
@@ -124,7 +104,7 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 load_tap_inputs<T>(offp, mskp, 1, ox2, oy2, ml2);
             }
             if (!waited) {  // the box is needed from here on
-                mbar_wait(&full[buf], (k / kBoxBuffers) & 1);
+                mbar_wait(&bar, 0);
                 waited = true;
             }
 #pragma unroll 1
@@ -176,12 +156,9 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 }
             }
             if (STAGED) {
-                // every lane has consumed its slot values (they fed the arithmetic above): refill with the warp's
-                // next row segment, here or in a later tile
+                // every lane has consumed its slot values (they fed the arithmetic above): refill for the next iteration
                 __syncwarp();
-                TileWalk nw = {k, it};
-                TileCtx nc = ctx;
-                if (next_segment<C::PXW>(q, tg, n_tiles, warp, nw, nc)) request(nc, nw.it);
+                if (it + kTiledWarps < ctx.nit) request(ctx, it + kTiledWarps);
             }
             if (valid) {
                 T* dst = out + pg * kGC;
@@ -190,13 +167,8 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                     store_piece<T>(dst + Slab<T>::chan_of(pc, rot), acc + pc * C::PAIRS);
             }
         }
-        if (kBoxBuffers > 1)
-            release_box(&released[buf], &full[buf], smem + (size_t)buf * box_bytes, &xmap, q, tg, n_tiles, k, lane, C::GQ);
-        else if (!waited)
-            mbar_wait(&full[buf], 0);  // never leave with a TMA in flight
+        if (!waited) mbar_wait(&bar, 0);  // never leave with a TMA in flight
     }
-    // (every box that was requested belongs to a tile of this CTA, and warp 0 at least has waited for it: no TMA
-    //  is in flight when the CTA's last warp leaves)
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -214,18 +186,6 @@ static EncodeTiledFn encode_fn() {
         return (EncodeTiledFn) nullptr;
     }();
     return fn;
-}
-
-// CTAs of a forward / gather launch: every tile its own CTA, or (persistent) one CTA per SM walking over the tiles
-unsigned tiled_grid(int n_tiles) {
-    if (kBoxBuffers == 1) return (unsigned)n_tiles;
-    static thread_local int sms[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    int& n = sms[dev & 63];
-    if (n == 0 && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
-    const int slots = n * kTiledCtasPerSm;
-    return (unsigned)(n_tiles < slots ? n_tiles : slots);
 }
 
 cudaError_t ensure_max_smem(const void* kernel, int bytes) {
@@ -385,14 +345,13 @@ bool tiled_applicable(const KParams& q, int dtype) {
 template <typename T, bool STAGED>
 static cudaError_t launch_fwd_variant(const CUtensorMap& map, const CUtensorMap& offmap, const void* x, const void* offset,
                                       const void* mask, void* out, const KParams& q, const TileGeom& tg, cudaStream_t st) {
-    const size_t smem = (size_t)kBoxBuffers * tg.bw * tg.bh * kCellBytes + (STAGED ? kTiledWarps * RowStage<T>::BYTES : 0);
+    const size_t smem = (size_t)tg.bw * tg.bh * kCellBytes + (STAGED ? kTiledWarps * RowStage<T>::BYTES : 0);
     cudaError_t e = ensure_max_smem((const void*)fwd_tiled_kernel<T, STAGED>,
-                                    kBoxBuffers * (STAGED ? kMaxBoxBytes : kFwdBoxBytes) +
-                                        (STAGED ? kTiledWarps * RowStage<T>::BYTES : 0));
+                                    STAGED ? kMaxBoxBytes + kTiledWarps * RowStage<T>::BYTES : kFwdBoxBytes);
     if (e != cudaSuccess) return e;
-    const int n_tiles = (int)((size_t)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
-    return launch_pdl(fwd_tiled_kernel<T, STAGED>, tiled_grid(n_tiles), kTiledWarps * 32, smem, st, map, offmap,
-                      (const T*)x, (const T*)offset, (const T*)mask, (T*)out, q, tg, n_tiles);
+    const unsigned grid = (unsigned)((size_t)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
+    return launch_pdl(fwd_tiled_kernel<T, STAGED>, grid, kTiledWarps * 32, smem, st, map, offmap, (const T*)x,
+                      (const T*)offset, (const T*)mask, (T*)out, q, tg);
 }
 
 template <typename T>
@@ -422,12 +381,12 @@ static void geom_numbers(const KParams& q, const TileGeom& tg, long long smem, i
 void fwd_tiled_plan(const KParams& q, int dtype, int out[8]) {
     const TileGeom tg = make_geom(q, dtype, 16, 16, 3.0f, fwd_box_bytes(q, dtype) / kCellBytes);
     const int slot = dtype == DCNV3_F32 ? RowStage<float>::BYTES : RowStage<__nv_bfloat16>::BYTES;
-    geom_numbers(q, tg, (long long)kBoxBuffers * tg.bw * tg.bh * kCellBytes + (side_stageable(q, dtype) ? kTiledWarps * slot : 0), out);
+    geom_numbers(q, tg, (long long)tg.bw * tg.bh * kCellBytes + (side_stageable(q, dtype) ? kTiledWarps * slot : 0), out);
 }
 
 void gather_tiled_plan(const KParams& q, int dtype, int stage_bytes, int out[8]) {
     const TileGeom tg = make_geom(q, dtype, 16, 16, 3.0f, kMaxBoxBytes / kCellBytes);
-    geom_numbers(q, tg, (long long)kBoxBuffers * tg.bw * tg.bh * kCellBytes + stage_bytes, out);
+    geom_numbers(q, tg, (long long)tg.bw * tg.bh * kCellBytes + stage_bytes, out);
 }
 
 cudaError_t launch_fwd_tiled(const void* x, const void* offset, const void* mask, void* out,
