@@ -42,8 +42,9 @@ class DeformableConvolutionV3(nn.Module):
         cin = int(input_shape[-1])
         k = self.depthwise_kernel_size
         gp = self.groups * self.kernel_size * self.kernel_size
-        self.dw_conv = nn.Conv2d(cin, cin, k, stride=1, groups=cin, bias=True,
-                                 padding=k // 2 if self.padding.lower() == "same" else 0)
+        # Keras DepthwiseConv2D 'same' at stride 1 pads (k-1)//2 before and k//2 after: asymmetric for an even k
+        self.dw_conv = nn.Conv2d(cin, cin, k, stride=1, groups=cin, bias=True, padding=0)
+        self._dw_pad = ((k - 1) // 2, k // 2) if self.padding.lower() == "same" else (0, 0)
         self.dw_conv_norm = nn.LayerNorm(cin, eps=LAYER_NORM_EPSILON)
         self.offset = nn.Linear(cin, 2 * gp)
         self.mask = nn.Linear(cin, gp)
@@ -83,7 +84,8 @@ class DeformableConvolutionV3(nn.Module):
             self.to(device=inputs.device, dtype=inputs.dtype)
         n, h, w, c = inputs.shape
         x_proj = self.input_proj(inputs)  # dcn_v3.py:113
-        x1 = self.dw_conv(inputs.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)  # :115
+        lo, hi = self._dw_pad
+        x1 = self.dw_conv(F.pad(inputs.permute(0, 3, 1, 2), (lo, hi, lo, hi))).permute(0, 2, 3, 1)  # :115
         x1 = self.activation(self.dw_conv_norm(x1))  # :116-117
         offset = self.offset(x1)  # :118
         mask = self.mask(x1)  # :120

@@ -207,6 +207,30 @@ def make_layer_case():
             offset_scale=np.array(scale), **{f"w.{k_}": v.numpy() for k_, v in w.items()})
 
 
+def make_sliding_indices():
+    """Window starts of the reference's sliding-window inference: its own `_get_sliding_start_indexs_py`
+    (utils/sliding_window_inference_utils.py:16-32, plain Python) evaluated over a grid of (length, crop) pairs."""
+    import importlib.util
+    import json
+    import sys
+    import types
+
+    ref_runner.load()  # installs the tensorflow stand-in and the `iseg` package skeleton
+    common = types.ModuleType("iseg.utils.common")
+    common.isinstance_all = lambda xs, t: all(isinstance(v, t) for v in xs)
+    sys.modules["iseg.utils.common"] = common
+    path = os.path.join(ref_runner.REFERENCE_ROOT, "utils", "sliding_window_inference_utils.py")
+    spec = importlib.util.spec_from_file_location("iseg.utils.sliding_window_inference_utils", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cases = {}
+    for crop in (24, 193, 257, 512, 513, 769, 1024):
+        for length in sorted({crop, crop + 1, crop + 7, int(1.5 * crop), 2 * crop - 1, 2 * crop, 1024, 2048, 2049, 3000}):
+            if length >= crop:
+                cases[f"{length},{crop}"] = [int(v) for v in mod._get_sliding_start_indexs_py(length, crop, 2.0 / 3.0)]
+    json.dump(cases, open(os.path.join(OUT, "sliding_indices.json"), "w"), indent=0, sort_keys=True)
+
+
 if __name__ == "__main__":
     assert ref_runner.available(), "needs /root/reference"
     for nm, sp in OP_CASES.items():
@@ -217,4 +241,5 @@ if __name__ == "__main__":
         print("wrote", nm)
     make_kats()
     make_layer_case()
+    make_sliding_indices()
     print("done")

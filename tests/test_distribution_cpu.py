@@ -30,6 +30,17 @@ def test_sliding_window_indices_match_reference_rule():
     assert [len(shard_tiles(tiles, 4, r)) for r in range(4)] == [2, 2, 2, 2]
 
 
+def test_sliding_window_indices_match_reference_function():
+    """tests/golden/sliding_indices.json: the reference's own `_get_sliding_start_indexs_py` over 67 (length, crop)
+    pairs (tests/golden/make_golden.py::make_sliding_indices)."""
+    import json
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sliding_indices.json")))
+    assert len(cases) > 60
+    for key, want in cases.items():
+        length, crop = (int(v) for v in key.split(","))
+        assert get_sliding_start_indexs(length, crop) == want, key
+
+
 def test_sliding_window_inference_single_rank_matches_sequential_rule():
     from iseg_b200.distribution import inference_with_sliding_window
     torch.manual_seed(0)

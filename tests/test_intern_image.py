@@ -19,6 +19,42 @@ def test_presets_match_reference_hyperparameters():
     assert rates[0] == 0.0 and abs(rates[-1] - 0.2) < 1e-9 and rates == sorted(rates)
 
 
+def test_weights_load_by_reference_name_roundtrip(tmp_path):
+    """checkpoints of the reference are restored by layer name (saver/h5_saver.py:38-49)."""
+    import numpy as np
+    from iseg_b200.backbones.intern_image.weights import export_reference_weights, load_reference_weights, reference_names
+    torch.manual_seed(0)
+    src = intern_image_tiny()
+    for p in src.parameters():
+        torch.nn.init.normal_(p, std=0.1)
+    w = export_reference_weights(src)
+    # names and Keras layouts as the reference declares them
+    assert w["block/2/layer/17/dcn/offset/kernel"].shape == (256, 2 * 16 * 9)          # Dense [in, out]
+    assert w["block/0/layer/0/dcn/dw_conv/depthwise_kernel"].shape == (3, 3, 64, 1)   # DepthwiseConv2D
+    assert w["patch_embed/conv1/kernel"].shape == (3, 3, 3, 32) and "block/3/downsample/conv/kernel" not in w
+    assert w["block/1/downsample/conv/kernel"].shape == (3, 3, 128, 256) and "block/1/downsample/conv/bias" not in w
+    assert "block/0/layer/3/gamma1" in w and "block/0/norm/gamma" in w
+    assert len(w) == len(list(src.parameters())) == len(reference_names(src))
+    # Keras-3 style keys ("." separators, ":0" suffix, model-name prefix) through an .npz on disk
+    path = str(tmp_path / "ckpt.npz")
+    np.savez(path, **{"intern_image_tiny." + k.replace("/", ".") + ":0": v for k, v in w.items()})
+    dst = intern_image_tiny()
+    loaded, missing, unexpected = load_reference_weights(dst, path)
+    assert not missing and not unexpected and len(loaded) == len(w)
+    for a, b in zip(src.parameters(), dst.parameters()):
+        assert torch.equal(a, b)
+    w.pop("block/0/norm/beta")
+    with pytest.raises(KeyError):
+        load_reference_weights(intern_image_tiny(), w)
+    assert load_reference_weights(intern_image_tiny(), w, strict=False)[1] == ["block/0/norm/beta"]
+    huge_like = export_reference_weights(
+        __import__("iseg_b200.backbones.intern_image.intern_image", fromlist=["InternImage"]).InternImage(
+            32, [1, 1, 2, 1], [2, 4, 8, 16], layer_scale=None, use_res_post_norm=True, use_level2_post_norm=True,
+            level2_post_norm_block_ids=[1], use_center_feature_scale=True, depthwise_kernel_size=5))
+    assert "block/2/post_norms/0/gamma" in huge_like and "block/0/layer/0/res_post_norm1/beta" in huge_like
+    assert huge_like["block/0/layer/0/dcn/center_feature_scale_proj/kernel"].shape == (32, 2)
+
+
 def test_tf_same_padding_stride2_shapes():
     conv = torch.nn.Conv2d(3, 4, 3, stride=2)
     for h, w in ((512, 512), (769, 769), (15, 18)):
@@ -53,3 +89,46 @@ def test_base_variant_odd_groups_bf16():
     with torch.no_grad():
         y = m(torch.randn(1, 64, 64, 3, device="cuda", dtype=torch.bfloat16))
     assert y.shape == (1, 2, 2, 896) and torch.isfinite(y.float()).all()
+
+
+@pytest.mark.gpu
+def test_sliding_window_with_intern_image_tiles_matches_reference_rule():
+    """BASELINE config 5 in small: sliding-window inference with InternImage-T tiles of odd size (193 -> stage
+    shapes 49 / 25 / 13 / 7, like the 769 -> 193 / 97 / 49 / 25 of the real configuration).  The tiled driver must
+    give what the reference's sequential rule gives (core_inference.py:230-304: every tile's logits zero-padded to
+    the full image, summed in tile order, divided by the count map), with the window starts of the reference's own
+    function (tests/golden/sliding_indices.json)."""
+    import json
+    import os
+
+    from iseg_b200.distribution import inference_with_sliding_window, sliding_window_tiles
+    torch.manual_seed(1)
+    m = intern_image_tiny(return_endpoints=True).cuda().eval()
+    for blk in m.blocks:
+        for layer in blk.blocks:
+            torch.nn.init.normal_(layer.dcn.offset.weight, std=0.05)
+            torch.nn.init.normal_(layer.dcn.mask.weight, std=0.05)
+    head = torch.nn.Linear(64, 5).cuda()
+
+    def model_fn(tile):  # [N, h, w, 3] -> [N, h, w, 5]: stage-1 endpoint (stride 4), linear head, nearest upsampling
+        with torch.no_grad():
+            f = head(m(tile)[1])
+        up = f.repeat_interleave(4, dim=1).repeat_interleave(4, dim=2)
+        return up[:, :tile.shape[1], :tile.shape[2]]
+
+    height, width, crop = 300, 420, 193
+    image = torch.randn(1, height, width, 3, device="cuda")
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sliding_indices.json")))
+    tiles = sliding_window_tiles(height, width, crop, crop)
+    ys, xs = sorted({t[0] for t in tiles}), sorted({t[1] for t in tiles})
+    assert ys == cases.get(f"{height},{crop}", ys) and len(tiles) == len(ys) * len(xs) and len(tiles) >= 4
+    out = inference_with_sliding_window(model_fn, image, crop_h=crop, crop_w=crop)
+    # the reference's rule, literally: pad to full size, add in order, divide by the count map
+    acc = torch.zeros(1, height, width, 5, device="cuda")
+    cnt = torch.zeros(1, height, width, 1, device="cuda")
+    for (y, x, h, w) in tiles:
+        lg = model_fn(image[:, y:y + h, x:x + w])
+        acc += torch.nn.functional.pad(lg, (0, 0, x, width - x - w, y, height - y - h))
+        cnt += torch.nn.functional.pad(torch.ones(1, h, w, 1, device="cuda"), (0, 0, x, width - x - w, y, height - y - h))
+    ref = acc / cnt
+    assert torch.isfinite(out).all() and (out - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
