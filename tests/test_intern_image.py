@@ -132,3 +132,33 @@ def test_sliding_window_with_intern_image_tiles_matches_reference_rule():
         cnt += torch.nn.functional.pad(torch.ones(1, h, w, 1, device="cuda"), (0, 0, x, width - x - w, y, height - y - h))
     ref = acc / cnt
     assert torch.isfinite(out).all() and (out - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
+@pytest.mark.gpu
+def test_graphed_inference_matches_eager():
+    """Product-level CUDA graph of a whole backbone forward (and of one stage): same numbers as eager, one
+    graph launch per call, re-captured per input shape."""
+    from iseg_b200 import _cabi
+    from iseg_b200.backbones.intern_image import GraphedInference
+    torch.manual_seed(2)
+    m = intern_image_tiny(return_endpoints=True).cuda().eval()
+    for blk in m.blocks:
+        for layer in blk.blocks:
+            torch.nn.init.normal_(layer.dcn.offset.weight, std=0.05)
+            torch.nn.init.normal_(layer.dcn.mask.weight, std=0.05)
+    gm = GraphedInference(m)
+    for shape in ((2, 96, 128, 3), (1, 193, 193, 3)):
+        x = torch.randn(*shape, device="cuda")
+        with torch.no_grad():
+            want = m(x)
+            got = gm(x)
+            n0 = _cabi.launch_count()
+            got2 = gm(torch.randn(*shape, device="cuda"))
+            assert _cabi.launch_count() == n0  # replay: no launches through the C ABI, the graph holds them
+        assert all(torch.equal(a, b) for a, b in zip(want, got))
+        assert not torch.equal(got2[-1], got[-1])
+    stage = GraphedInference(m.blocks[2])  # one stage: 18 layers of 32x32-sized work at a 512 crop
+    f = torch.randn(2, 24, 32, 256, device="cuda")
+    with torch.no_grad():
+        a, b = m.blocks[2](f), stage(f)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
