@@ -339,6 +339,33 @@ def test_raw_pointer_and_host_entry_points(ops):
     assert rc == cabi.ERR_WORKSPACE
 
 
+def test_host_numpy_binding(ops):
+    """iseg_b200/bindings/host_numpy.py -- the tested part of the reference-side binding of INTEGRATION.md (the
+    TF lines around it are `tf.numpy_function` + `tf.custom_gradient`)."""
+    from iseg_b200.bindings.host_numpy import dcnv3_op_numpy, dcnv3_op_with_grads_numpy
+    n, h, w, g, gc = 2, 26, 35, 6, 16
+    x, off, m, go = make_inputs(n, h, w, g, gc, sigma=1.5, seed=31)
+    args = ([3, 3], [1, 1], "same", [1, 1], g, gc, 1.0)
+    kw = dict(groups=g, group_channels=gc)
+    keep = [a.copy() for a in (x, off, m, go)]
+    out = dcnv3_op_numpy(x, off, m, *args)
+    assert rel_err(out, c_oracle.forward(x, off, m, **kw)) <= TOL_F32
+    out2, gx, goff, gm = dcnv3_op_with_grads_numpy(x, off, m, go, *args)
+    rx, roff, rm = c_oracle.backward(x, off, m, go, **kw)
+    assert np.array_equal(out, out2)
+    assert rel_err(gx, rx) <= TOL_F32 and rel_err(goff, roff) <= TOL_F32 and rel_err(gm, rm) <= TOL_F32
+    assert all(np.array_equal(a, b) for a, b in zip(keep, (x, off, m, go)))  # inputs are never written
+    logits = np.random.default_rng(0).standard_normal(m.shape).astype(np.float32)
+    out3 = dcnv3_op_numpy(x, off, logits, *args, mask_is_logits=True)
+    assert rel_err(out3, c_oracle.forward(x, off, O.mask_softmax(logits, g), **kw)) <= TOL_F32
+    with pytest.raises(TypeError):
+        dcnv3_op_numpy(x, off, m, [3, 3], [1, 1], 1, [1, 1], g, gc, 1.0)        # op.py:29-30
+    with pytest.raises(ValueError):
+        dcnv3_op_numpy(x, off, m, [3, 3], [1, 1], "full", [1, 1], g, gc, 1.0)   # op.py:32-39
+    with pytest.raises(ValueError):
+        dcnv3_op_numpy(x, off[:, :5], m[:, :5], *args)                          # op.py:83 reshape
+
+
 def test_dirty_workspace_is_detected_on_request(ops):
     """DCNV3_FLAG_WORKSPACE_ZEROED is a promise; DCNV3_FLAG_CHECK_WORKSPACE verifies it (debug aid)."""
     _, cabi = ops
