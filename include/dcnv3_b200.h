@@ -56,8 +56,11 @@ typedef enum { DCNV3_F32 = 0, DCNV3_BF16 = 1 } dcnv3_dtype;
 /* mask argument holds pre-softmax logits; softmax over P is fused (dcn_v3.py:120-123) and
    grad_mask is the gradient w.r.t. the logits */
 #define DCNV3_FLAG_MASK_LOGITS 1u
-/* backward only: the caller guarantees the workspace is all-zero on entry (e.g. it was zeroed once
-   and only ever used by dcnv3_backward, which leaves it zeroed); saves a memset of the workspace */
+/* backward only: the caller guarantees that the zero part of the workspace -- its first
+   dcnv3_backward_workspace_zero_bytes() bytes -- is all-zero on entry (e.g. it was zeroed once and only ever
+   used by dcnv3_backward, which leaves that part zeroed); saves a memset.  The rest of the workspace is
+   scratch: never read before it is written, contents undefined afterwards.  A workspace that is reused for a
+   call with a LARGER zero part must have the difference re-zeroed first (the scratch of the earlier call lay there). */
 #define DCNV3_FLAG_WORKSPACE_ZEROED 4u
 /* debugging aid, with DCNV3_FLAG_WORKSPACE_ZEROED: verify that promise before the call (one reduction kernel
    and a stream synchronisation; DCNV3_ERR_WORKSPACE if the workspace is dirty).  A launch failure or an aborted
@@ -107,7 +110,10 @@ int dcnv3_launch_plan(const dcnv3_params* p, int* plan25);
 int dcnv3_forward(const void* x, const void* offset, const void* mask, void* out,
                   const dcnv3_params* p, void* cuda_stream);
 
+/* bytes of caller-owned device workspace dcnv3_backward needs (256-byte aligned pointer), and how many of them,
+   from the start, form the zero part (see DCNV3_FLAG_WORKSPACE_ZEROED); 0 for invalid parameters */
 size_t dcnv3_backward_workspace_bytes(const dcnv3_params* p);
+size_t dcnv3_backward_workspace_zero_bytes(const dcnv3_params* p);
 
 /* grad_x / grad_offset / grad_mask are fully overwritten.  Bitwise reproducible run to run. */
 int dcnv3_backward(const void* x, const void* offset, const void* mask, const void* grad_out,

@@ -52,6 +52,8 @@ def _load():
     lib.dcnv3_forward.argtypes = [vp] * 4 + [pp, vp]
     lib.dcnv3_backward_workspace_bytes.argtypes = [pp]
     lib.dcnv3_backward_workspace_bytes.restype = ctypes.c_size_t
+    lib.dcnv3_backward_workspace_zero_bytes.argtypes = [pp]
+    lib.dcnv3_backward_workspace_zero_bytes.restype = ctypes.c_size_t
     lib.dcnv3_backward.argtypes = [vp] * 8 + [ctypes.c_size_t, pp, vp]
     scal = [ci] * 10 + [cf, cu, vp]
     lib.dcnv3_forward_dlpack.argtypes = [vp] * 4 + scal
@@ -124,19 +126,28 @@ def _ws_key(device, nbytes):
     return (device.index, torch.cuda.current_stream(device).cuda_stream, int(nbytes))
 
 
-def _workspace(device, nbytes):
-    """Backward workspace, zeroed once and kept per (device, stream, size): dcnv3_backward leaves it
-    zeroed, so later calls on the same stream skip the memset (DCNV3_FLAG_WORKSPACE_ZEROED).
+def _workspace(device, nbytes, zero_bytes=None):
+    """Backward workspace, zeroed once and kept per (device, stream, size): dcnv3_backward leaves its zero
+    part (the first `zero_bytes`) zeroed, so later calls on the same stream skip the memset
+    (DCNV3_FLAG_WORKSPACE_ZEROED); what lies behind the zero part is scratch.  Two shapes can share a cache
+    entry (same total size): the entry remembers how long its known-zero prefix is and a call that needs a
+    longer one re-zeroes the difference.
     A workspace first needed during CUDA-graph capture lives in the graph's private pool: it is handed
     out zeroed but never cached.  A failed backward drops its cache entry (see backward())."""
+    zero_bytes = int(nbytes) if zero_bytes is None else int(zero_bytes)
     key = _ws_key(device, nbytes)
-    ws = _ws_cache.get(key)
-    if ws is None:
+    ent = _ws_cache.get(key)
+    if ent is None:
         ws = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         if not torch.cuda.is_current_stream_capturing():
             if len(_ws_cache) >= 64:
                 _ws_cache.clear()
-            _ws_cache[key] = ws
+            _ws_cache[key] = [ws, zero_bytes]
+        return ws
+    ws, clean = ent
+    if zero_bytes > clean:
+        ws[clean:zero_bytes].zero_()
+    ent[1] = zero_bytes
     return ws
 
 
@@ -165,7 +176,7 @@ def backward(x, offset, mask, grad_out, kernel_size, strides, pad, dilation_rate
     p = make_params(x.shape, offset.shape[1:3], kernel_size, strides, pad, dilation_rate, groups,
                     group_channels, offset_scale, dt, flags)
     ws_bytes = int(lib.dcnv3_backward_workspace_bytes(ctypes.byref(p)))
-    ws = _workspace(x.device, ws_bytes)
+    ws = _workspace(x.device, ws_bytes, int(lib.dcnv3_backward_workspace_zero_bytes(ctypes.byref(p))))
     rc = None
     try:
         caps = [_dl(t) for t in (x, offset, mask, grad_out, gx, goff, gm, ws)]

@@ -114,10 +114,17 @@ static int forward_impl(const void* x, const void* offset, const void* mask, voi
     return DCNV3_OK;
 }
 
-static size_t backward_ws_bytes(const dcnv3_params* p) {
+// Backward workspace = [zero part][scratch].  The zero part (fixed-point side buffer, dirty map, flags, per-image
+// maxima) must be all-zero on entry and is left all-zero on exit; the scratch tail (the tiled path's transposed
+// copy of offset / mask) carries no contract in either direction.
+static size_t backward_ws_zero_bytes(const dcnv3_params* p) {
     const KParams q = derive(p);
     const size_t a = bwd_generic_workspace_bytes(q), b = bwd_tiled_workspace_bytes(q);
-    return a > b ? a : b;
+    return ((a > b ? a : b) + 255) / 256 * 256;
+}
+static size_t backward_ws_bytes(const dcnv3_params* p) {
+    const KParams q = derive(p);
+    return backward_ws_zero_bytes(p) + (tiled_applicable(q, p->dtype) ? bwd_tiled_scratch_bytes(q, p->dtype) : 0);
 }
 
 // DCNV3_FLAG_CHECK_WORKSPACE: is the workspace really all-zero?  (debug aid: one reduction kernel + a
@@ -163,16 +170,19 @@ static int backward_impl(const void* x, const void* offset, const void* mask, co
     if (ws == nullptr || ws_bytes < need)
         return fail(DCNV3_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", need, ws_bytes);
     if ((rc = check_ptr_align(ws, "workspace", 256))) return rc;
+    const size_t zero_bytes = backward_ws_zero_bytes(p);
     if ((p->flags & DCNV3_FLAG_CHECK_WORKSPACE) && (p->flags & DCNV3_FLAG_WORKSPACE_ZEROED) &&
-        (rc = check_workspace_zero(ws, need, st)))
+        (rc = check_workspace_zero(ws, zero_bytes, st)))
         return rc;
     const KParams q = derive(p);
     const bool tiled = tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC) && !ref_dtype_mode(p);
-    cudaError_t e =
-        tiled ? launch_bwd_tiled(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, p->dtype,
-                                 (p->flags & DCNV3_FLAG_WORKSPACE_ZEROED) != 0, st)
-              : launch_bwd_generic(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, p->dtype,
-                                   (p->flags & DCNV3_FLAG_WORKSPACE_ZEROED) != 0, st);
+    cudaError_t e;
+    // the whole zero part, whichever path runs: both leave it zero, so the caller's next call may be either
+    if (!(p->flags & DCNV3_FLAG_WORKSPACE_ZEROED) && (e = cudaMemsetAsync(ws, 0, zero_bytes, st)) != cudaSuccess)
+        return cuda_fail(e, "memset(workspace)");
+    e = tiled ? launch_bwd_tiled(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, (char*)ws + zero_bytes, q,
+                                 p->dtype, true, st)
+              : launch_bwd_generic(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, p->dtype, true, st);
     if (e != cudaSuccess) return cuda_fail(e, "dcnv3_backward launch");
     return DCNV3_OK;
 }
@@ -250,6 +260,8 @@ struct HostScratch {
     size_t bytes = 0;
     void* ws = nullptr;
     size_t ws_bytes = 0;
+    size_t ws_clean = 0;                            // bytes [0, ws_clean) are known to be zero (a call leaves its zero part zero
+                                                    // and may write anything beyond it)
     cudaStream_t stream = nullptr;                  // kernels of this slot
     // forward inputs resident / grad_out resident / forward done / backward done / outputs copied
     cudaEvent_t ev_in = nullptr, ev_go = nullptr, ev_fwd = nullptr, ev_comp = nullptr, ev_out = nullptr;
@@ -301,6 +313,7 @@ static int scratch_reserve(int device, int slot, size_t bytes, size_t ws_bytes, 
         if ((e = cudaMalloc(&s.ws, ws_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)");
         if ((e = cudaMemsetAsync(s.ws, 0, ws_bytes, s.stream)) != cudaSuccess) return cuda_fail(e, "memset(workspace)");
         s.ws_bytes = ws_bytes;
+        s.ws_clean = ws_bytes;
     }
     *out = &s;
     return 0;
@@ -349,6 +362,11 @@ int dcnv3_forward(const void* x, const void* offset, const void* mask, void* out
 size_t dcnv3_backward_workspace_bytes(const dcnv3_params* p) {
     if (check(p) != DCNV3_OK) return 0;
     return backward_ws_bytes(p);
+}
+
+size_t dcnv3_backward_workspace_zero_bytes(const dcnv3_params* p) {
+    if (check(p) != DCNV3_OK) return 0;
+    return backward_ws_zero_bytes(p);
 }
 
 int dcnv3_backward(const void* x, const void* offset, const void* mask, const void* grad_out,
@@ -487,7 +505,12 @@ static int host_run(const void* x, const void* offset, const void* mask, const v
     if (with_backward) {
         CK(cudaStreamWaitEvent(st, s->ev_go, 0), "cudaStreamWaitEvent");
         dcnv3_params pb = *p;
-        pb.flags |= DCNV3_FLAG_WORKSPACE_ZEROED;  // the slot's workspace is zeroed at allocation and stays so
+        // the slot's workspace is zeroed at allocation; a call keeps its zero part zero and scribbles on the scratch
+        // behind it, so a later call with a larger zero part re-zeroes the difference
+        const size_t zb = backward_ws_zero_bytes(p);
+        if (zb > s->ws_clean) CK(cudaMemsetAsync((char*)s->ws + s->ws_clean, 0, zb - s->ws_clean, st), "memset(workspace)");
+        s->ws_clean = zb;
+        pb.flags |= DCNV3_FLAG_WORKSPACE_ZEROED;
         if ((rc = backward_impl(d_x, d_off, d_m, d_go, d_gx, d_goff, d_gm, s->ws, s->ws_bytes, &pb, st))) return rc;
         CK(cudaEventRecord(s->ev_comp, st), "cudaEventRecord");
         CK(cudaStreamWaitEvent(sout, s->ev_comp, 0), "cudaStreamWaitEvent");

@@ -30,9 +30,11 @@ cudaError_t launch_fwd_tiled(const void* x, const void* offset, const void* mask
 // launch plans as plain numbers (dcnv3_launch_plan: CPU-side tests of the tiling logic)
 void fwd_tiled_plan(const KParams& q, int dtype, int out[8]);   // th tw bw bh halo_x halo_y grid smem_bytes
 void bwd_tiled_plan(const KParams& q, int dtype, int out[16]);  // gather: as above; scatter: tj ring_lo ring_hi box_rows grid smem_bytes threads merge
+// workspace of the tiled backward = [bwd_tiled_workspace_bytes: zero on entry, left zero on exit][scratch: no contract]
 size_t bwd_tiled_workspace_bytes(const KParams& q);
+size_t bwd_tiled_scratch_bytes(const KParams& q, int dtype);
 cudaError_t launch_bwd_tiled(const void* x, const void* offset, const void* mask, const void* grad_out,
-                             void* grad_x, void* grad_offset, void* grad_mask, void* ws, const KParams& q,
+                             void* grad_x, void* grad_offset, void* grad_mask, void* ws, void* scratch, const KParams& q,
                              int dtype, bool ws_clean, cudaStream_t st);
 
 }  // namespace dcnv3

@@ -33,10 +33,19 @@
 //
 // The common scale comes from max|grad_out| (left in the workspace header by bwd_gather_kernel):
 // G = round(go * 2^eg), 2^29 <= max|G| < 2^30.
+#include <type_traits>
+
 #include "dcnv3_kernels.h"
 #include "dcnv3_tiled.cuh"
 
 namespace dcnv3 {
+
+#ifndef DCNV3_SCATTER_THREADS
+#define DCNV3_SCATTER_THREADS 512  // 16 warps x 128 registers: a 32x32 tile is 64 blocks = 4 full rounds
+#endif
+#ifndef DCNV3_SCATTER_BATCH
+#define DCNV3_SCATTER_BATCH 9      // taps whose coordinate arithmetic is done together before their ATOMS runs (0: per-tap loop)
+#endif
 
 constexpr int kSG = 2;             // groups per scatter CTA (lane = pixel * kSG + group, 16 pixels per warp)
 constexpr int kSCell = kSG * kGC;   // accumulator ints per cell: exactly 32 banks wide, so the bank of an
@@ -53,7 +62,7 @@ struct ScatterShape {
     // pitch of the weight counters: one extra column, and odd, so that the 16 pixels of a warp -- they walk
     // down a column of cells -- spread their counters over all banks
     static constexpr int WPITCH = (PITCH + 1) | 1;
-    static constexpr int THREADS = TJ == 32 ? 640 : 256;
+    static constexpr int THREADS = TJ == 32 ? DCNV3_SCATTER_THREADS : 256;
     static constexpr int MIN_CTAS = TJ == 32 ? 1 : 2;
 };
 
@@ -72,6 +81,60 @@ struct FarWs {
     int* redo;                    // [N][chunks][tiles_y][tiles_x]  scatter CTA found hot cells
     unsigned long long* acc64;    // [N][H][W][C] fixed point, zero outside a call
 };
+
+// Transposed copy of the per-pixel side inputs, written by the gather kernel (it has them staged in shared
+// memory anyway) and read by the scatter kernel.  In the reference layout a lane's 18 offsets sit 72 bytes from its
+// neighbour's, so each of the scatter kernel's per-tap loads touches 16-18 cache lines -- measured as a quarter of
+// that kernel's time (profiles/r02_scatter_ablation.md).  Layout here: [image][pair of groups][tap][pixel][2 groups],
+// offsets as (x, y) pairs, so the 32 lanes of a scatter warp (16 consecutive pixels x 2 groups) read 256 / 128
+// contiguous bytes per tap.  Lives in the scratch tail of the workspace (no zero-on-entry contract).
+template <typename T>
+struct SideT {
+    using Pair = typename std::conditional<sizeof(T) == 4, float2, unsigned>::type;
+    Pair* off;   // [N][CS][9][H*W][2]
+    T* msk;      // [N][CS][9][H*W][2]
+    int cs;      // pairs of groups: ceil(G / 2)
+    int hw;      // pixels per image
+    __device__ __forceinline__ size_t index(int n, int pair, int pix, int gl) const {
+        return (((size_t)n * cs + pair) * kTaps * hw + pix) * 2 + gl;  // tap 0; tap p is p * 2 * hw further
+    }
+};
+template <typename T>
+__device__ __forceinline__ void side_t_store(const SideT<T>& s, size_t idx, float ox, float oy, float ml);
+template <>
+__device__ __forceinline__ void side_t_store<float>(const SideT<float>& s, size_t idx, float ox, float oy, float ml) {
+    s.off[idx] = make_float2(ox, oy);
+    s.msk[idx] = ml;
+}
+template <>
+__device__ __forceinline__ void side_t_store<__nv_bfloat16>(const SideT<__nv_bfloat16>& s, size_t idx, float ox, float oy, float ml) {
+    s.off[idx] = (__float_as_uint(ox) >> 16) | (__float_as_uint(oy) & 0xffff0000u);  // (both are exact bf16 values)
+    s.msk[idx] = __float2bfloat16_rn(ml);
+}
+template <typename T>
+__device__ __forceinline__ void side_t_load(const SideT<T>& s, size_t idx, float& ox, float& oy, float& ml);
+template <>
+__device__ __forceinline__ void side_t_load<float>(const SideT<float>& s, size_t idx, float& ox, float& oy, float& ml) {
+    const float2 o = __ldcg(s.off + idx);   // (written by the previous kernel of the stream: not through the
+    ox = o.x; oy = o.y;                     //  non-coherent path)
+    ml = __ldcg(s.msk + idx);
+}
+template <>
+__device__ __forceinline__ void side_t_load<__nv_bfloat16>(const SideT<__nv_bfloat16>& s, size_t idx, float& ox, float& oy, float& ml) {
+    const unsigned r = __ldcg(s.off + idx);
+    ox = __uint_as_float(r << 16); oy = __uint_as_float(r & 0xffff0000u);
+    ml = __uint_as_float((unsigned)__ldcg(reinterpret_cast<const unsigned short*>(s.msk) + idx) << 16);
+}
+// fp32 only: for bf16 the per-lane loads touch half as many lines to begin with, and the gather kernel's stores of
+// the copy (lane = pixel x 4 groups there: 8-byte runs) cost more than the scatter kernel gains (profiles/r02_ab.md)
+template <typename T>
+constexpr bool kUseSideT = sizeof(T) == 4;
+static size_t side_t_bytes(const KParams& q, int dtype) {
+    if (dtype != DCNV3_F32) return 0;
+    const size_t es = dtype == DCNV3_F32 ? 4 : 2;
+    const size_t entries = (size_t)q.n * ((q.G + 1) / 2) * kTaps * q.h * q.w * 2;
+    return (entries * 2 * es + 255) / 256 * 256 + (entries * es + 255) / 256 * 256;
+}
 
 // un-padded nominal input column of output row h (may be -1 at the border), integer arithmetic so
 // that every CTA agrees exactly:  floor((2h+3) * (W_in-2) / (2 H_in)) - 1
@@ -192,8 +255,8 @@ __global__ void __launch_bounds__(kTiledWarps * 32, 2)
 bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap offmap,
                   const __grid_constant__ CUtensorMap goffmap, const T* __restrict__ x,
                   const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
-                  T* __restrict__ grad_offset, T* __restrict__ grad_mask, ImgMax* __restrict__ img_max, const KParams q,
-                  const TileGeom tg) {
+                  T* __restrict__ grad_offset, T* __restrict__ grad_mask, ImgMax* __restrict__ img_max,
+                  const SideT<T> side_t, const KParams q, const TileGeom tg) {
     using C = Chunk<T>;
     using RS = RowStage<T>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -259,6 +322,9 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
                 load_piece<T>(grad_out + pg * kGC + Slab<T>::chan_of(pc, rot), go + pc * C::PAIRS);
             float ref0, ref1;
             ref_point(q, h, w, ref0, ref1);
+            // this lane's entries of the transposed side copy (real pixels and real groups only)
+            const bool t_on = kUseSideT<T> && px_l < npx && chunk * C::GQ + g_l < q.G;
+            size_t t_idx = side_t.index(n, chunk * (C::GQ / 2) + (g_l >> 1), h * q.wo + w, g_l & 1);
             if (STAGED) {
                 cp_async_wait_all();
                 __syncwarp();
@@ -285,6 +351,8 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
 #pragma unroll 1
             for (int p = 0; p < kTaps; ++p) {
                 const float cx = ox, cy = oy, cm = ml;
+                if (t_on) side_t_store<T>(side_t, t_idx, cx, cy, cm);
+                t_idx += 2 * (size_t)side_t.hw;
                 if (STAGED) {
                     if (p + 1 < kTaps) RS::tap(st, lane, p + 1, ox, oy, ml);  // (read before tap p's results land)
                 } else {
@@ -403,7 +471,11 @@ __device__ __forceinline__ TileBox make_box(const KParams& q, const BwdGeom& bg,
 // shared-memory integer add without return value: 32-bit shared address + immediate byte offset
 template <int OFF>
 __device__ __forceinline__ void red_shared_add(uint32_t addr, int v) {
+#ifdef DCNV3_X_NOATOMS
+    asm volatile("" ::"r"(addr), "r"(v), "n"(OFF) : "memory");
+#else
     asm volatile("red.shared.add.s32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(OFF) : "memory");
+#endif
 }
 
 // Weight counters.  Every tap adds ceil(|m| * 1025) -- an upper bound of 1024 * (sum of its four |Wk|) --
@@ -422,7 +494,11 @@ __device__ __forceinline__ bool cell_is_hot(const int* wsum, int cy, int cx, int
 }
 // one contribution in fixed point: round(G * Wk / 2^32), ties up (a single IMAD.HI with a constant addend)
 __device__ __forceinline__ int qmul(int g, int wq) {
+#ifdef DCNV3_X_NOHI
+    return g * wq + 0x8000;
+#else
     return (int)(((long long)g * wq + 0x80000000ll) >> 32);
+#endif
 }
 // (|wf| < 3.9 whenever the tap's cells are not hot -- weight_units() -- so the conversion cannot saturate there;
 //  for hot cells it may, deterministically, and those accumulators are discarded and recomputed)
@@ -572,10 +648,233 @@ __device__ __forceinline__ void scatter_walk(int* acc, int* wsum, const T* __res
     }
 }
 
+// ---- batched walk of the scatter kernel ---------------------------------------------------------------------
+// Inside a tap the coordinate arithmetic (a dependent chain of ~25 fp32 operations per axis, fed by global loads)
+// and the 64 ATOMS of its four landings alternate, and because every warp of the CTA runs the same instruction
+// stream at the same pace they alternate in step: while the warps sit in the chain the ATOMS pipe -- the resource
+// the kernel is bound by -- idles (ncu, round 2: 83 % busy inside the ATOMS runs, 30 % over the kernel).  Here the
+// chains of TB taps are computed together, branch free, so that they overlap one another (instruction-level
+// parallelism instead of one exposed latency per tap), their results stay in registers as TapRec, and the ATOMS
+// runs then follow back to back; the next block's inputs are requested before the last run.  Taps that are not
+// wholly inside the box (rare) are noted in a bit mask and handled after the runs by slow_tap().
+struct TapRec {
+    uint32_t base;           // lane's rotated slab address inside the anchor cell (y0, x0)
+    int wqa, wqb, wqc, wqd;  // fixed-point weights of the corners (y0,x0) (y1,x0) (y0,x1) (y1,x1)
+};
+
+template <int ROWB>
+__device__ __forceinline__ void atoms_run(const TapRec& r, const int (&G)[16]) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        const uint32_t a = r.base ^ (uint32_t)(c << 2);
+        red_shared_add<0>(a, qmul(G[c], r.wqa));
+        red_shared_add<ROWB>(a, qmul(G[c], r.wqb));
+        red_shared_add<kSCell * 4>(a, qmul(G[c], r.wqc));
+        red_shared_add<ROWB + kSCell * 4>(a, qmul(G[c], r.wqd));
+    }
+}
+
+// a tap whose 2x2 patch leaves the box: corner by corner -- shared atomics where the corner is in the box, the
+// 64-bit side buffer where it lies beyond it (outside the image the gradient is dropped)
+template <typename T, int TJ>
+__device__ __forceinline__ void slow_tap(uint32_t acc_s, uint32_t wsum_s, const T* __restrict__ offp, const T* __restrict__ mskp,
+                                      const FarWs& ws, const KParams& q, const TileBox& box, int n, int g, int px_l, int p,
+                                      float ref0, float ref1, float mx, float inv_sum, const int (&G)[16]) {
+    constexpr int PITCH = ScatterShape<TJ>::PITCH;
+    constexpr int WP = ScatterShape<TJ>::WPITCH;
+    float ox, oy, ml;
+    load_tap_inputs<T>(offp, mskp, p, ox, oy, ml);
+    const Axis axx = axis_x_live(q, ref0, p, ox);
+    const Axis axy = axis_y_live(q, ref1, p, oy);
+    const int lx = axx.i0 - q.pw - box.bx0, ly = axy.i0 - q.ph - box.by0;
+    const float mm = (q.flags & DCNV3_FLAG_MASK_LOGITS) ? expf(ml - mx) * inv_sum : ml;
+    const bool touches = (unsigned)(lx + 1) <= (unsigned)box.bw && (unsigned)(ly + 1) <= (unsigned)box.bh;
+    if (touches)  // some corner lies in the box
+        red_shared_add<(WP + 1) * kSG * 4>(wsum_s + (uint32_t)(ly * WP + lx) * (kSG * 4u), weight_units(mm));
+    const size_t img_pixels = (size_t)q.h * q.w;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        const float wf = ((k >> 1) ? axx.d0 : axx.d1) * ((k & 1) ? axy.d0 : axy.d1) * mm;
+        if (wf == 0.f) continue;
+        const int cx = lx + (k >> 1), cy = ly + (k & 1);
+        const int ax = cx + box.bx0, ay = cy + box.by0;  // un-padded image coordinates
+        if ((unsigned)cx < (unsigned)box.bw && (unsigned)cy < (unsigned)box.bh) {
+            const int wq = weight_fixed(wf);
+            const uint32_t base = acc_s + (uint32_t)(cy * PITCH + cx) * (kSCell * 4u);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) red_shared_add<0>(base ^ (uint32_t)(c << 2), qmul(G[c], wq));
+        } else if (ax >= 0 && ax < q.w && ay >= 0 && ay < q.h) {
+            side_add(ws, ((size_t)n * img_pixels + (size_t)ay * q.w + ax) * q.G + g, G, px_l, wf);
+        }
+    }
+}
+
+template <typename T, int TJ, int TB>
+__device__ __forceinline__ void scatter_walk_batched(int* acc, int* wsum, const T* __restrict__ offset,
+                                                     const T* __restrict__ mask, const T* __restrict__ grad_out,
+                                                     const SideT<T>& side_t, const FarWs& ws, const KParams& q,
+                                                     const TileBox& box, int n, int chunk, Range hh, Range hw, int eg) {
+    constexpr int PITCH = ScatterShape<TJ>::PITCH;
+    constexpr int WP = ScatterShape<TJ>::WPITCH;
+    constexpr int PXW = 32 / kSG;
+    constexpr int ROWB = PITCH * kSCell * 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g_l = lane % kSG, px_l = lane / kSG;
+    const int g = chunk * kSG + g_l;
+    if (g >= q.G) return;  // phantom group of a trailing chunk (no warp-level synchronisation in this walk)
+    const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
+    const float sg = ldexpf(1.0f, eg);
+    uint32_t acc_s = (smem_u32(acc) + (uint32_t)g_l * (kGC * 4u)) ^ ((uint32_t)px_l << 2);
+    uint32_t wsum_s = smem_u32(wsum) + (uint32_t)g_l * 4u;
+    asm volatile("" : "+r"(acc_s), "+r"(wsum_s));
+    const int nw = hw.hi - hw.lo, npix = (hh.hi - hh.lo) * nw;
+    const int nblocks = (npix + PXW - 1) / PXW;
+    const int full_rounds = nblocks / nwarps, rest = nblocks - full_rounds * nwarps;
+    const int parts = rest ? min(kTaps, nwarps / rest) : 1;  // warps per block of the last round
+    const int bx_off = q.pw + box.bx0, by_off = q.ph + box.by0;
+    const unsigned bw1 = (unsigned)(box.bw - 1), bh1 = (unsigned)(box.bh - 1);
+
+    // the work item of a round: one block of 16 pixels x 2 groups (all 9 taps), or -- last, incomplete round -- a
+    // range of its taps.  Returns false when this lane has nothing to do in that round.
+    struct Item { int h, w, p_lo, p_hi; size_t pg; bool valid; };
+    auto item_of = [&](int round) {
+        Item it;
+        it.valid = false; it.h = it.w = 0; it.pg = 0; it.p_lo = 0; it.p_hi = kTaps;
+        if (round > full_rounds) return it;
+        int blk = round * nwarps + warp;
+        if (round == full_rounds) {
+            if (warp >= rest * parts) return it;
+            const int part = warp % parts;
+            blk = round * nwarps + warp / parts;
+            it.p_lo = part * kTaps / parts;
+            it.p_hi = (part + 1) * kTaps / parts;
+        }
+        const int pix = blk * PXW + px_l;
+        if (pix >= npix) return it;
+        const int row = pix / nw;
+        it.h = hh.lo + row; it.w = hw.lo + (pix - row * nw);
+        it.pg = (((size_t)n * q.ho + it.h) * q.wo + it.w) * q.G + g;
+        it.valid = true;
+        return it;
+    };
+    struct Inputs { float ox[kTaps], oy[kTaps], ml[kTaps]; f2 gf[8]; };
+    auto load_inputs = [&](const Item& it, Inputs& in) {
+#ifdef DCNV3_X_NOLOAD
+#pragma unroll
+        for (int p = 0; p < kTaps; ++p) { in.ox[p] = (float)((it.pg + p) & 3) * 0.4f - 0.6f; in.oy[p] = (float)((it.pg >> 2) & 3) * 0.4f - 0.6f; in.ml[p] = 0.11f; }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) in.gf[c] = pack2((float)(it.pg & 15) * 0.1f, (float)c * 0.1f);
+#else
+        // from the transposed copy the gather kernel has just written: consecutive lanes, consecutive entries
+        if (kUseSideT<T>) {
+            const size_t t_idx = side_t.index(n, chunk, it.h * q.wo + it.w, g_l);
+#pragma unroll
+            for (int p = 0; p < kTaps; ++p) side_t_load<T>(side_t, t_idx + (size_t)p * 2 * side_t.hw, in.ox[p], in.oy[p], in.ml[p]);
+        } else {
+            const T* offp = offset + it.pg * 18;
+            const T* mskp = mask + it.pg * 9;
+#pragma unroll
+            for (int p = 0; p < kTaps; ++p) load_tap_inputs<T>(offp, mskp, p, in.ox[p], in.oy[p], in.ml[p]);
+        }
+        load_go<T>(grad_out + it.pg * kGC, in.gf);
+#endif
+    };
+
+    Item cur = item_of(0);
+    Inputs in;
+    if (cur.valid) load_inputs(cur, in);
+#pragma unroll 1
+    for (int round = 0; round <= full_rounds; ++round) {
+        const Item nxt = item_of(round + 1);
+        bool requested = false;
+        if (cur.valid) {
+            int G[16];
+            fixed_point_go(in.gf, sg, px_l, G);
+            float mx = 0.f, inv_sum = 1.f;
+            if (logits) {
+                mx = -INFINITY;
+#pragma unroll
+                for (int p = 0; p < kTaps; ++p) mx = fmaxf(mx, in.ml[p]);
+                float s = 0.f;
+#pragma unroll
+                for (int p = 0; p < kTaps; ++p) s += expf(in.ml[p] - mx);
+                inv_sum = 1.0f / s;
+            }
+            float ref0, ref1;
+            ref_point(q, cur.h, cur.w, ref0, ref1);
+            unsigned slow = 0u;
+#pragma unroll
+            for (int b0 = 0; b0 < kTaps; b0 += TB) {
+                TapRec rec[TB];
+                unsigned fast = 0u;
+                // ---- the chains of TB taps, branch free ----
+#pragma unroll
+                for (int t = 0; t < TB; ++t) {
+                    const int p = b0 + t;
+                    if (p >= kTaps) continue;
+#ifdef DCNV3_X_NOCOORD
+                    Axis axx, axy;
+                    axx.alive = axy.alive = true; axx.i0 = bx_off + 5 + (p / 3) + (cur.h & 15); axy.i0 = by_off + 5 + (p % 3) + (cur.w & 15);
+                    axx.d0 = in.ox[p]; axx.d1 = ref0; axy.d0 = in.oy[p]; axy.d1 = ref1;
+#else
+                    const Axis axx = axis_x_live(q, ref0, p, in.ox[p]);
+                    const Axis axy = axis_y_live(q, ref1, p, in.oy[p]);
+#endif
+                    const int lx = axx.i0 - bx_off, ly = axy.i0 - by_off;  // corner (y0,x0) relative to the box
+                    const float mm = logits ? expf(in.ml[p] - mx) * inv_sum : in.ml[p];
+                    // alive: no clipped corner pair coincides (else the tap contributes exactly 0)
+                    const bool on = axx.alive && axy.alive && mm != 0.f && p >= cur.p_lo && p < cur.p_hi;
+                    const bool inbox = (unsigned)lx < bw1 && (unsigned)ly < bh1;  // all four corners lie in the box
+                    rec[t].wqa = weight_fixed(axx.d1 * axy.d1 * mm);
+                    rec[t].wqb = weight_fixed(axx.d1 * axy.d0 * mm);
+                    rec[t].wqc = weight_fixed(axx.d0 * axy.d1 * mm);
+                    rec[t].wqd = weight_fixed(axx.d0 * axy.d0 * mm);
+                    rec[t].base = acc_s + (uint32_t)(ly * PITCH + lx) * (kSCell * 4u);  // rotation bits stay put: cell*128
+                    if (on && inbox) {
+                        fast |= 1u << t;
+                        red_shared_add<(WP + 1) * kSG * 4>(wsum_s + (uint32_t)(ly * WP + lx) * (kSG * 4u), weight_units(mm));
+                    }
+                    if (on && !inbox) slow |= 1u << p;
+                }
+                // ---- their ATOMS runs ----
+#pragma unroll
+                for (int t = 0; t < TB; ++t) {
+                    const int p = b0 + t;
+                    if (p >= kTaps) continue;
+                    if (p == kTaps - 1 && nxt.valid) {  // the next block's inputs travel under the last run (this
+                        load_inputs(nxt, in);           //  block's have all been consumed by now)
+                        requested = true;
+                    }
+                    if (fast & (1u << t)) atoms_run<ROWB>(rec[t], G);
+                }
+            }
+            if (__builtin_expect(slow != 0u, 0)) {
+                const T* offp = offset + cur.pg * 18;
+                const T* mskp = mask + cur.pg * 9;
+                do {
+                    const int p = __ffs(slow) - 1;
+                    slow &= slow - 1;
+                    slow_tap<T, TJ>(acc_s, wsum_s, offp, mskp, ws, q, box, n, g, px_l, p, ref0, ref1, mx, inv_sum, G);
+                } while (slow != 0u);
+            }
+        }
+        if (nxt.valid && !requested) load_inputs(nxt, in);
+        cur = nxt;
+    }
+}
+
+#ifdef DCNV3_SCATTER_PROFILE
+// debug build only (tools/scatter_phases.py): per-CTA phase clocks
+__device__ long long* g_scatter_prof = nullptr;
+#define PROF_MARK(k) do { if (g_scatter_prof && threadIdx.x == 0) g_scatter_prof[(size_t)blockIdx.x * 16 + (k)] = clock64(); } while (0)
+#else
+#define PROF_MARK(k) do { } while (0)
+#endif
+
 template <typename T, int TJ>
 __global__ void __launch_bounds__(ScatterShape<TJ>::THREADS, ScatterShape<TJ>::MIN_CTAS)
 bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
-                   T* __restrict__ grad_x, const FarWs ws, const KParams q, const BwdGeom bg) {
+                   T* __restrict__ grad_x, const SideT<T> side_t, const FarWs ws, const KParams q, const BwdGeom bg) {
     constexpr int PITCH = ScatterShape<TJ>::PITCH;
     constexpr int WP = ScatterShape<TJ>::WPITCH;
     // [box_rows][PITCH][kSCell] accumulator + [box_rows + 1][WP][kSG] weight counters
@@ -592,6 +891,12 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
     const TileBox box = make_box(q, bg, jx, jy);
 
     pdl_launch_dependents();
+#ifdef DCNV3_SCATTER_PROFILE
+    __shared__ long long s_wmin, s_wmax;
+    if (threadIdx.x == 0) { s_wmin = 0x7fffffffffffffffll; s_wmax = 0; }
+    PROF_MARK(0);
+    if (g_scatter_prof && threadIdx.x == 0) { unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); g_scatter_prof[(size_t)blockIdx.x * 16 + 8] = smid; }
+#endif
     // prologue without global memory traffic (overlaps the tail of the gather kernel): home ranges, zeroed box
     if (threadIdx.x < 2) tile_ranges(q, bg, jx, jy, s_home_h, s_home_w);
     {
@@ -600,13 +905,27 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
             z[i] = make_int2(0, 0);
     }
     __syncthreads();
+    PROF_MARK(1);
     pdl_wait();  // the gather kernel has left the image's max |grad_out| in the workspace
+    PROF_MARK(2);
     const unsigned go_bits = ws.img_max[n].go_bits;
     const bool nonfinite = bits_nonfinite(go_bits);  // NaN / Inf in this image's grad_out: its grad_x is NaN
     const int eg = 30 - fixed_exponent_raw(go_bits);
-    if (!nonfinite)
+    if (!nonfinite) {
+#if DCNV3_SCATTER_BATCH > 0
+        scatter_walk_batched<T, TJ, DCNV3_SCATTER_BATCH>(acc, wsum, offset, mask, grad_out, side_t, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+#else
         scatter_walk<T, 0, TJ>(acc, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+#endif
+    }
+#ifdef DCNV3_SCATTER_PROFILE
+    if ((threadIdx.x & 31) == 0) { const long long t = clock64(); atomicMin(&s_wmin, t); atomicMax(&s_wmax, t); }
+#endif
     __syncthreads();
+    PROF_MARK(3);
+#ifdef DCNV3_SCATTER_PROFILE
+    if (g_scatter_prof && threadIdx.x == 0) { g_scatter_prof[(size_t)blockIdx.x * 16 + 6] = s_wmin; g_scatter_prof[(size_t)blockIdx.x * 16 + 7] = s_wmax; }
+#endif
 
     // ---- flush: the cells of J are written exactly once; ring cells go to the side buffer ----
     // work item = 32 consecutive 4-channel pieces of one box row (4 cells x 2 groups), dealt round-robin to the warps
@@ -618,6 +937,53 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
     const int g = chunk * kSG + gl;
     const float qnan = __int_as_float(0x7fc00000);
     bool any_hot = false;
+#ifndef DCNV3_NO_FAST_FLUSH
+    // Can any cell be hot at all?  A cell's bound is the sum of four counters, so it needs one above kBudget / 4.
+    // Almost never: then the flush runs without the per-cell test, a warp per box row and with 32-bit indexing.
+    int cmax = 0;
+    for (int i = threadIdx.x; i < (bg.box_rows + 1) * WP * kSG; i += blockDim.x) cmax = max(cmax, wsum[i]);
+    if (!__syncthreads_or(cmax > kBudget / 4 || nonfinite)) {
+        const int row_elems = q.w * q.G * kGC;                // grad_x elements per image row (< 2^31: tiled_applicable)
+        const int npieces = box.bw * QPC;
+        for (int cy = warp; cy < box.bh; cy += nwarps) {
+            const int ay = box.by0 + cy;
+            if (ay < 0 || ay >= q.h) continue;               // zero ring of tf.pad: gradient dropped (Pad-grad)
+            const size_t grow = (size_t)n * q.h + ay;
+            T* gx_row = grad_x + grow * row_elems + chunk * kSCell;
+            unsigned long long* side_row = ws.acc64 + (grow * q.w * q.G + chunk * kSG) * kGC;
+            unsigned char* dirty_row = ws.dirty + grow * q.w * q.G + chunk * kSG;
+            const bool row_owned = (unsigned)(ay - box.uy0) < (unsigned)box.tjh;
+            const int* arow = acc + cy * (PITCH * kSCell);
+            for (int idx = lane; idx < npieces; idx += 32) {
+                const int cx = idx >> 3, ax = box.bx0 + cx;  // (QPC = 8; the lane keeps its piece: 32 % 8 == 0)
+                if (ax < 0 || ax >= q.w || g >= q.G) continue;
+                const int4 v = *reinterpret_cast<const int4*>(arow + idx * 4);
+                if (row_owned && (unsigned)(ax - box.ux0) < (unsigned)box.tjw) {
+                    const int e = ax * (q.G * kGC) + piece * 4;
+                    const float f0 = (float)v.x * inv_s, f1 = (float)v.y * inv_s, f2_ = (float)v.z * inv_s, f3 = (float)v.w * inv_s;
+                    if (sizeof(T) == 4) {
+                        *reinterpret_cast<float4*>(reinterpret_cast<float*>(gx_row) + e) = make_float4(f0, f1, f2_, f3);
+                    } else {
+                        uint2 r2;
+                        r2.x = pack_bf16x2(f0, f1);
+                        r2.y = pack_bf16x2(f2_, f3);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(gx_row) + e) = r2;
+                    }
+                } else if ((v.x | v.y | v.z | v.w) != 0) {
+                    unsigned long long* dst = side_row + (ax * q.G + gl) * kGC + (piece & 3) * 4;
+                    if (v.x) atomicAdd(dst + 0, (unsigned long long)(long long)v.x);
+                    if (v.y) atomicAdd(dst + 1, (unsigned long long)(long long)v.y);
+                    if (v.z) atomicAdd(dst + 2, (unsigned long long)(long long)v.z);
+                    if (v.w) atomicAdd(dst + 3, (unsigned long long)(long long)v.w);
+                    dirty_row[ax * q.G + gl] = 1;
+                }
+            }
+        }
+        __syncthreads();
+        PROF_MARK(4);
+        return;
+    }
+#endif
     for (int item = warp; item < box.bh * segs; item += nwarps) {
         const int cy = item / segs, cx = ((item - cy * segs) << 2) + (lane >> 3);
         const int ax = box.bx0 + cx, ay = box.by0 + cy;
@@ -656,7 +1022,16 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
         ws.redo[blockIdx.x] = 1;
         ws.hd->any_redo = 1u;  // (benign race: every writer stores the same value)
     }
+#ifdef DCNV3_SCATTER_PROFILE
+    __syncthreads();
+    PROF_MARK(4);
+#endif
 }
+#ifdef DCNV3_SCATTER_PROFILE
+extern "C" int dcnv3_debug_scatter_profile(long long* buf) {
+    return (int)cudaMemcpyToSymbol(g_scatter_prof, &buf, sizeof(buf));
+}
+#endif
 
 // Exact recomputation of the hot cells of one box (see header): pass 1 rebuilds the weight counters,
 // pass 2 adds the landings on hot cells to the 64-bit side buffer.  Exits at once unless the scatter
@@ -795,6 +1170,8 @@ static BwdGeom make_bwd_geom(const KParams& q) {
 static size_t flag_bytes(size_t count) { return (count * sizeof(int) + 255) / 256 * 256; }
 static size_t dirty_bytes(const KParams& q) { return ((size_t)q.n * q.h * q.w * q.G + 255) / 256 * 256; }
 
+size_t bwd_tiled_scratch_bytes(const KParams& q, int dtype) { return side_t_bytes(q, dtype); }
+
 size_t bwd_tiled_workspace_bytes(const KParams& q) {
     const size_t tiles = (size_t)q.n * ((q.w + 15) / 16) * ((q.h + 15) / 16);  // upper bound (16x16 tiles)
     const size_t chunks = (size_t)(q.G + 1) / 2;
@@ -810,14 +1187,15 @@ static size_t scatter_smem_bytes(int rows) {
 }
 
 template <typename T, int TJ>
-static cudaError_t launch_scatter(const T* offset, const T* mask, const T* grad_out, T* grad_x, const FarWs& ws,
-                                  const KParams& q, const BwdGeom& bg, unsigned grid, bool redo_is_last, cudaStream_t st) {
+static cudaError_t launch_scatter(const T* offset, const T* mask, const T* grad_out, T* grad_x, const SideT<T>& side_t,
+                                  const FarWs& ws, const KParams& q, const BwdGeom& bg, unsigned grid, bool redo_is_last,
+                                  cudaStream_t st) {
     using S = ScatterShape<TJ>;
     const size_t smem = scatter_smem_bytes<TJ>(bg.box_rows);
     cudaError_t e = ensure_max_smem((const void*)bwd_scatter_kernel<T, TJ>, (int)scatter_smem_bytes<TJ>(S::PITCH));
     if (e != cudaSuccess) return e;
     KernelTiming& kt = kernel_timing();
-    e = launch_pdl(bwd_scatter_kernel<T, TJ>, grid, S::THREADS, smem, st, offset, mask, grad_out, grad_x, ws, q, bg);
+    e = launch_pdl(bwd_scatter_kernel<T, TJ>, grid, S::THREADS, smem, st, offset, mask, grad_out, grad_x, side_t, ws, q, bg);
     if (e != cudaSuccess) return e;
     if (kt.enabled) cudaEventRecord(kt.ev[2], st);
     const unsigned redo_grid = grid < 32u ? grid : 32u;  // normally they only read one word and leave
@@ -828,8 +1206,8 @@ static cudaError_t launch_scatter(const T* offset, const T* mask, const T* grad_
 template <typename T, bool STAGED>
 static cudaError_t launch_gather_variant(const CUtensorMap& map, const CUtensorMap& offmap, const CUtensorMap& goffmap,
                                          const void* x, const void* offset, const void* mask, const void* grad_out,
-                                         void* grad_offset, void* grad_mask, ImgMax* img_max, const KParams& q,
-                                         const TileGeom& tg, cudaStream_t st) {
+                                         void* grad_offset, void* grad_mask, ImgMax* img_max, const SideT<T>& side_t,
+                                         const KParams& q, const TileGeom& tg, cudaStream_t st) {
     cudaError_t e = ensure_max_smem((const void*)bwd_gather_kernel<T, STAGED>,
                                     kMaxBoxBytes + kTiledWarps * kGatherStageBytes<T>);
     if (e != cudaSuccess) return e;
@@ -838,14 +1216,22 @@ static cudaError_t launch_gather_variant(const CUtensorMap& map, const CUtensorM
     return launch_pdl(bwd_gather_kernel<T, STAGED>, grid, kTiledWarps * 32,
                       (size_t)tg.bw * tg.bh * kCellBytes + kTiledWarps * kGatherStageBytes<T>, st, map, offmap, goffmap,
                       (const T*)x, (const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_offset, (T*)grad_mask,
-                      img_max, q, tg);
+                      img_max, side_t, q, tg);
 }
 
 template <typename T>
 static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const void* mask, const void* grad_out,
-                                      void* grad_x, void* grad_offset, void* grad_mask, void* wsp,
+                                      void* grad_x, void* grad_offset, void* grad_mask, void* wsp, void* scratch,
                                       const KParams& q, int dtype, bool ws_clean, cudaStream_t st) {
     const BwdGeom bg = make_bwd_geom(q);
+    SideT<T> side_t;
+    {
+        const size_t entries = (size_t)q.n * ((q.G + 1) / 2) * kTaps * q.h * q.w * 2;
+        side_t.off = (typename SideT<T>::Pair*)scratch;
+        side_t.msk = (T*)((char*)scratch + (entries * 2 * sizeof(T) + 255) / 256 * 256);
+        side_t.cs = (q.G + 1) / 2;
+        side_t.hw = q.h * q.w;
+    }
     const size_t tiles = (size_t)q.n * bg.tiles_x * bg.tiles_y;
     const size_t tiles_ub = (size_t)q.n * ((q.w + 15) / 16) * ((q.h + 15) / 16);
     const size_t chunks_ub = (size_t)(q.G + 1) / 2;
@@ -876,9 +1262,9 @@ static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const v
     KernelTiming& kt = kernel_timing();
     if (kt.enabled) cudaEventRecord(kt.ev[0], st);
     e = staged ? launch_gather_variant<T, true>(map, offmap, goffmap, x, offset, mask, grad_out, grad_offset, grad_mask,
-                                                ws.img_max, q, tg, st)
+                                                ws.img_max, side_t, q, tg, st)
                : launch_gather_variant<T, false>(map, offmap, goffmap, x, offset, mask, grad_out, grad_offset, grad_mask,
-                                                 ws.img_max, q, tg, st);
+                                                 ws.img_max, side_t, q, tg, st);
     if (e != cudaSuccess) return e;
 
     // ---- grad_x ----
@@ -886,10 +1272,10 @@ static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const v
     const unsigned grid_b = (unsigned)(tiles * bg.chunks);
     // a single tile owns every cell of its image: no ring, no far landings, nothing to merge
     const bool merge = bg.tiles_x * bg.tiles_y > 1;
-    e = bg.tj == 32 ? launch_scatter<T, 32>((const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_x, ws, q, bg,
-                                            grid_b, !merge, st)
-                    : launch_scatter<T, 16>((const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_x, ws, q, bg,
-                                            grid_b, !merge, st);
+    e = bg.tj == 32 ? launch_scatter<T, 32>((const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_x, side_t, ws, q,
+                                            bg, grid_b, !merge, st)
+                    : launch_scatter<T, 16>((const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_x, side_t, ws, q,
+                                            bg, grid_b, !merge, st);
     if (e != cudaSuccess) return e;
     if (kt.enabled) cudaEventRecord(kt.ev[3], st);
     if (merge) {
@@ -913,11 +1299,11 @@ void bwd_tiled_plan(const KParams& q, int dtype, int out[16]) {
 }
 
 cudaError_t launch_bwd_tiled(const void* x, const void* offset, const void* mask, const void* grad_out,
-                             void* grad_x, void* grad_offset, void* grad_mask, void* ws, const KParams& q,
+                             void* grad_x, void* grad_offset, void* grad_mask, void* ws, void* scratch, const KParams& q,
                              int dtype, bool ws_clean, cudaStream_t st) {
     return dtype == DCNV3_F32
-               ? launch_bwd_tiled_t<float>(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, dtype, ws_clean, st)
-               : launch_bwd_tiled_t<__nv_bfloat16>(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, dtype, ws_clean, st);
+               ? launch_bwd_tiled_t<float>(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, scratch, q, dtype, ws_clean, st)
+               : launch_bwd_tiled_t<__nv_bfloat16>(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, scratch, q, dtype, ws_clean, st);
 }
 
 }  // namespace dcnv3

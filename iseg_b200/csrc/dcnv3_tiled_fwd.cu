@@ -335,7 +335,8 @@ static int fwd_box_bytes(const KParams& q, int dtype) { return side_stageable(q,
 bool tiled_applicable(const KParams& q, int dtype) {
     // any group count: the last chunk may be partly empty (phantom groups are masked)
     if (!(q.P == 9 && q.kh == 3 && q.sh == 1 && q.sw == 1 && q.dh == 1 && q.dw == 1 && q.gc == kGC && q.ho == q.h &&
-          q.wo == q.w && q.ph == 1 && q.pw == 1 && q.scale > 0.f && q.scale <= 16.f && q.h <= 16384 && q.w <= 16384))
+          q.wo == q.w && q.ph == 1 && q.pw == 1 && q.scale > 0.f && q.scale <= 16.f && q.h <= 16384 && q.w <= 16384 &&
+          (long long)q.w * q.G * q.gc < (1ll << 30)))  // (32-bit element offsets inside an image row)
         return false;
     const int fwd_cells = fwd_box_bytes(q, dtype) / kCellBytes, bwd_cells = kMaxBoxBytes / kCellBytes;
     const TileGeom a = make_geom(q, dtype, 16, 16, 3.0f, fwd_cells), b = make_geom(q, dtype, 16, 16, 3.0f, bwd_cells);

@@ -222,9 +222,10 @@ def test_workspace_stays_zeroed_across_generic_and_tiled(ops):
         assert rel_err(goff.cpu().numpy(), roff) <= TOL_F32 and rel_err(gm.cpu().numpy(), rm) <= TOL_F32
     import ctypes
     prm = cabi.make_params(x.shape, (h, w), *cfg[:4], g, gc, 1.0, cabi.F32)
-    ws = cabi._workspace(t[0].device, int(cabi.lib.dcnv3_backward_workspace_bytes(ctypes.byref(prm))))  # the cached one
+    zb = int(cabi.lib.dcnv3_backward_workspace_zero_bytes(ctypes.byref(prm)))
+    ws = cabi._workspace(t[0].device, int(cabi.lib.dcnv3_backward_workspace_bytes(ctypes.byref(prm))), zb)  # the cached one
     torch.cuda.synchronize()
-    assert int(ws.count_nonzero()) == 0  # header and per-image maxima included
+    assert int(ws[:zb].count_nonzero()) == 0  # header and per-image maxima included (behind zb: scratch, no contract)
 
 
 def test_backward_bitwise_reproducible(ops):
@@ -381,10 +382,13 @@ def test_dirty_workspace_is_detected_on_request(ops):
     args = [t.data_ptr() for t in (tx, to, tm, tgo, gx, goff, gm, ws)]
     assert cabi.lib.dcnv3_backward(*args, nb, ctypes.byref(p), st) == 0
     torch.cuda.synchronize()
-    assert int(ws.count_nonzero()) == 0
+    zb = int(cabi.lib.dcnv3_backward_workspace_zero_bytes(ctypes.byref(p)))
+    assert 0 < zb <= nb and int(ws[:zb].count_nonzero()) == 0
     rx, _, _ = c_oracle.backward(x, off, m, go, groups=g, group_channels=gc)
     assert rel_err(gx.cpu().numpy(), rx) <= TOL_F32
-    ws[nb // 2] = 1  # something scribbled on it
+    # the scratch behind the zero part may hold anything (it does now) and the promise still holds
+    assert cabi.lib.dcnv3_backward(*args, nb, ctypes.byref(p), st) == 0
+    ws[zb // 2] = 1  # something scribbled on the zero part
     assert cabi.lib.dcnv3_backward(*args, nb, ctypes.byref(p), st) == cabi.ERR_WORKSPACE
     assert b"not all-zero" in cabi.lib.dcnv3_last_error()
 
