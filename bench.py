@@ -563,6 +563,15 @@ def run_ours(args, rank, world, local_rank):
     main = measure(args.dtype, sampler)
     other_dtype = "bf16" if args.dtype == "f32" else "f32"
     other = measure(other_dtype) if args.both_dtypes else None
+    if args.kernels_only:  # developer A/B aid (tools/ab_step.sh): the device-timed step and its functions, nothing else
+        if rank == 0:
+            out = {}
+            for dt, m in ((args.dtype, main), (other_dtype, other)):
+                if m is not None:
+                    out[dt] = {"ms_per_step": round(m["ms_total"] / args.steps, 4),
+                               **{f["function"]: round(f["us_per_step"], 1) for f in by_function(m["classes"], dt)}}
+            print(json.dumps(out))
+        return
     e2e = measure_e2e(args.dtype)
 
     gather = measure_gather(args.dtype) if dist is not None else None
@@ -632,6 +641,7 @@ def main():
     ap.add_argument("--no-graph", dest="graph", action="store_false")
     ap.add_argument("--one-dtype", dest="both_dtypes", action="store_false")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--kernels-only", action="store_true", help="developer aid: device-timed step only, short output")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

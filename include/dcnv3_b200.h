@@ -120,6 +120,21 @@ int dcnv3_backward(const void* x, const void* offset, const void* mask, const vo
                    void* grad_x, void* grad_offset, void* grad_mask, void* workspace,
                    size_t workspace_bytes, const dcnv3_params* p, void* cuda_stream);
 
+/* ---- the op with the layer's centre-feature-scale blend fused in (replaces dcn_v3.py:138-146 around op.py:16):
+        out = core * (1 - s) + x * s,  s = center_scale[n, h, w, g] broadcast over the group's channels
+        (center_scale: [n, h, w, groups], dtype of x; no sigmoid, as in the reference).  The backward also returns
+        grad_center_scale [n, h, w, groups]; grad_x includes the direct path grad_out * s.
+        Available where the shared-memory tiled kernels run (dcnv3_blend_supported() == 1: 3x3, stride 1,
+        dilation 1, SAME, 16 channels per group -- what InternImage-T/S/B/L instantiate); DCNV3_ERR_ARGUMENT
+        otherwise, and the caller applies the blend itself around dcnv3_forward / dcnv3_backward. ---- */
+int dcnv3_blend_supported(const dcnv3_params* p);
+int dcnv3_forward_blend(const void* x, const void* offset, const void* mask, const void* center_scale, void* out,
+                        const dcnv3_params* p, void* cuda_stream);
+int dcnv3_backward_blend(const void* x, const void* offset, const void* mask, const void* center_scale,
+                         const void* grad_out, void* grad_x, void* grad_offset, void* grad_mask,
+                         void* grad_center_scale, void* workspace, size_t workspace_bytes, const dcnv3_params* p,
+                         void* cuda_stream);
+
 /* ---- DLPack entry points: same calls, tensors described by DLManagedTensor (zero copy);
         shapes, dtype, device and contiguity are taken from / checked against the tensors ---- */
 int dcnv3_forward_dlpack(const DLManagedTensor* x, const DLManagedTensor* offset,

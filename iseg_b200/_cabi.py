@@ -55,6 +55,9 @@ def _load():
     lib.dcnv3_backward_workspace_zero_bytes.argtypes = [pp]
     lib.dcnv3_backward_workspace_zero_bytes.restype = ctypes.c_size_t
     lib.dcnv3_backward.argtypes = [vp] * 8 + [ctypes.c_size_t, pp, vp]
+    lib.dcnv3_blend_supported.argtypes = [pp]
+    lib.dcnv3_forward_blend.argtypes = [vp] * 5 + [pp, vp]
+    lib.dcnv3_backward_blend.argtypes = [vp] * 10 + [ctypes.c_size_t, pp, vp]
     scal = [ci] * 10 + [cf, cu, vp]
     lib.dcnv3_forward_dlpack.argtypes = [vp] * 4 + scal
     lib.dcnv3_backward_dlpack.argtypes = [vp] * 8 + scal
@@ -190,3 +193,64 @@ def backward(x, offset, mask, grad_out, kernel_size, strides, pad, dilation_rate
             _ws_cache.pop(_ws_key(x.device, ws_bytes), None)
     check(rc)
     return gx, goff, gm
+
+
+def _blend_params(x, offset, kernel_size, strides, pad, dilation_rate, groups, group_channels, offset_scale, flags):
+    dt = F32 if x.dtype == torch.float32 else BF16
+    return make_params(x.shape, offset.shape[1:3], kernel_size, strides, pad, dilation_rate, groups,
+                       group_channels, offset_scale, dt, flags)
+
+
+def blend_supported(x, offset, kernel_size, strides, pad, dilation_rate, groups, group_channels,
+                    offset_scale, flags=0):
+    """Can the centre-feature-scale blend (reference dcn_v3.py:138-146) run fused inside the kernels for this
+    configuration?  (Where the shared-memory tiled kernels run.)"""
+    if x.dtype not in (torch.float32, torch.bfloat16) or not x.is_cuda:
+        return False
+    p = _blend_params(x, offset, kernel_size, strides, pad, dilation_rate, groups, group_channels, offset_scale, flags)
+    return bool(lib.dcnv3_blend_supported(ctypes.byref(p)))
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def forward_blend(x, offset, mask, center_scale, kernel_size, strides, pad, dilation_rate, groups,
+                  group_channels, offset_scale, flags=0):
+    """dcnv3_forward_blend on torch CUDA tensors: core * (1 - s) + x * s, one launch."""
+    for t in (x, offset, mask, center_scale):
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == x.dtype and t.device == x.device):
+            raise DCNv3Error(ERR_LAYOUT, "dcnv3_forward_blend needs dense CUDA tensors of one dtype on one device")
+    n, ho, wo = offset.shape[:3]
+    if tuple(center_scale.shape) != (n, ho, wo, groups) or tuple(x.shape[1:3]) != (ho, wo):
+        raise ValueError("dcnv3_b200: center_scale must be [N, H, W, groups] and x must have the output's H, W")
+    p = _blend_params(x, offset, kernel_size, strides, pad, dilation_rate, groups, group_channels, offset_scale, flags)
+    out = torch.empty((n, ho, wo, groups * group_channels), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.dcnv3_forward_blend(_ptr(x), _ptr(offset), _ptr(mask), _ptr(center_scale), _ptr(out),
+                                      ctypes.byref(p), _stream(x)))
+    return out
+
+
+def backward_blend(x, offset, mask, center_scale, grad_out, kernel_size, strides, pad, dilation_rate,
+                   groups, group_channels, offset_scale, flags=0):
+    """dcnv3_backward_blend; returns (grad_x, grad_offset, grad_mask, grad_center_scale)."""
+    for t in (x, offset, mask, center_scale, grad_out):
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == x.dtype and t.device == x.device):
+            raise DCNv3Error(ERR_LAYOUT, "dcnv3_backward_blend needs dense CUDA tensors of one dtype on one device")
+    gx, goff, gm, gs = (torch.empty_like(t) for t in (x, offset, mask, center_scale))
+    p = _blend_params(x, offset, kernel_size, strides, pad, dilation_rate, groups, group_channels, offset_scale,
+                      flags | FLAG_WORKSPACE_ZEROED)
+    ws_bytes = int(lib.dcnv3_backward_workspace_bytes(ctypes.byref(p)))
+    ws = _workspace(x.device, ws_bytes, int(lib.dcnv3_backward_workspace_zero_bytes(ctypes.byref(p))))
+    rc = None
+    try:
+        with torch.cuda.device(x.device):
+            rc = lib.dcnv3_backward_blend(_ptr(x), _ptr(offset), _ptr(mask), _ptr(center_scale), _ptr(grad_out),
+                                          _ptr(gx), _ptr(goff), _ptr(gm), _ptr(gs), _ptr(ws), ws_bytes,
+                                          ctypes.byref(p), _stream(x))
+    finally:
+        if rc != 0:
+            _ws_cache.pop(_ws_key(x.device, ws_bytes), None)
+    check(rc)
+    return gx, goff, gm, gs

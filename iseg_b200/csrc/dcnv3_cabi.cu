@@ -98,15 +98,28 @@ static int check_ptr_align(const void* ptr, const char* name, size_t align = 16)
     return 0;
 }
 
+// is the centre-feature-scale blend available for these parameters?  (fused into the tiled kernels only)
+static bool blend_supported(const dcnv3_params* p) {
+    const KParams q = derive(p);
+    return tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC) && !ref_dtype_mode(p);
+}
+
 static int forward_impl(const void* x, const void* offset, const void* mask, void* out,
-                        const dcnv3_params* p, cudaStream_t st) {
+                        const dcnv3_params* p, cudaStream_t st, const void* cfs = nullptr, bool blend = false) {
     int rc = check(p);
     if (rc) return rc;
     if (p->n == 0) return DCNV3_OK;  // empty batch: nothing to do (data pointers may be NULL)
     if ((rc = check_ptr_align(x, "x")) || (rc = check_ptr_align(offset, "offset")) ||
         (rc = check_ptr_align(mask, "mask")) || (rc = check_ptr_align(out, "out")))
         return rc;
-    const KParams q = derive(p);
+    KParams q = derive(p);
+    if (blend) {
+        if ((rc = check_ptr_align(cfs, "center_scale", 4))) return rc;
+        if (!blend_supported(p))
+            return fail(DCNV3_ERR_ARGUMENT, "the fused centre-feature-scale blend needs the tiled configuration "
+                                            "(3x3, stride 1, dilation 1, SAME, 16 channels per group); see dcnv3_blend_supported");
+        q.cfs = cfs;
+    }
     const bool tiled = tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC) && !ref_dtype_mode(p);
     cudaError_t e = tiled ? launch_fwd_tiled(x, offset, mask, out, q, p->dtype, st)
                           : launch_fwd_generic(x, offset, mask, out, q, p->dtype, st);
@@ -157,7 +170,8 @@ static int check_workspace_zero(const void* ws, size_t bytes, cudaStream_t st) {
 
 static int backward_impl(const void* x, const void* offset, const void* mask, const void* grad_out,
                          void* grad_x, void* grad_offset, void* grad_mask, void* ws, size_t ws_bytes,
-                         const dcnv3_params* p, cudaStream_t st) {
+                         const dcnv3_params* p, cudaStream_t st, const void* cfs = nullptr, void* grad_cfs = nullptr,
+                         bool blend = false) {
     int rc = check(p);
     if (rc) return rc;
     if (p->n == 0) return DCNV3_OK;
@@ -174,7 +188,15 @@ static int backward_impl(const void* x, const void* offset, const void* mask, co
     if ((p->flags & DCNV3_FLAG_CHECK_WORKSPACE) && (p->flags & DCNV3_FLAG_WORKSPACE_ZEROED) &&
         (rc = check_workspace_zero(ws, zero_bytes, st)))
         return rc;
-    const KParams q = derive(p);
+    KParams q = derive(p);
+    if (blend) {
+        if ((rc = check_ptr_align(cfs, "center_scale", 4)) || (rc = check_ptr_align(grad_cfs, "grad_center_scale", 4))) return rc;
+        if (!blend_supported(p))
+            return fail(DCNV3_ERR_ARGUMENT, "the fused centre-feature-scale blend needs the tiled configuration "
+                                            "(3x3, stride 1, dilation 1, SAME, 16 channels per group); see dcnv3_blend_supported");
+        q.cfs = cfs;
+        q.grad_cfs = grad_cfs;
+    }
     const bool tiled = tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC) && !ref_dtype_mode(p);
     cudaError_t e;
     // the whole zero part, whichever path runs: both leave it zero, so the caller's next call may be either
@@ -357,6 +379,24 @@ int dcnv3_launch_plan(const dcnv3_params* p, int* plan25) {
 int dcnv3_forward(const void* x, const void* offset, const void* mask, void* out,
                   const dcnv3_params* p, void* cuda_stream) {
     return forward_impl(x, offset, mask, out, p, (cudaStream_t)cuda_stream);
+}
+
+int dcnv3_blend_supported(const dcnv3_params* p) {
+    if (check(p) != DCNV3_OK) return 0;
+    return blend_supported(p) ? 1 : 0;
+}
+
+int dcnv3_forward_blend(const void* x, const void* offset, const void* mask, const void* center_scale, void* out,
+                        const dcnv3_params* p, void* cuda_stream) {
+    return forward_impl(x, offset, mask, out, p, (cudaStream_t)cuda_stream, center_scale, true);
+}
+
+int dcnv3_backward_blend(const void* x, const void* offset, const void* mask, const void* center_scale,
+                         const void* grad_out, void* grad_x, void* grad_offset, void* grad_mask,
+                         void* grad_center_scale, void* workspace, size_t workspace_bytes, const dcnv3_params* p,
+                         void* cuda_stream) {
+    return backward_impl(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, workspace, workspace_bytes, p,
+                         (cudaStream_t)cuda_stream, center_scale, grad_center_scale, true);
 }
 
 size_t dcnv3_backward_workspace_bytes(const dcnv3_params* p) {

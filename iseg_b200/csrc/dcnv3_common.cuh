@@ -31,6 +31,11 @@ struct KParams {
     float scale;           // offset_scale
     float fx, fy;          // d xq/d offset0 = (W_in-2)*s/W_in ; d yq/d offset1 = (H_in-2)*s/H_in
     unsigned flags;
+    // centre-feature-scale blend fused around the op (reference layers/dcn_v3/dcn_v3.py:138-146; tiled kernels
+    // only): out = core * (1 - s) + x * s with s = cfs[n, h, w, g] broadcast over the group's channels.
+    // NULL = plain op.  grad_cfs is written by the gather kernel.
+    const void* cfs;
+    void* grad_cfs;
     float gs0[DCNV3_MAX_TAPS];  // (dx_p / W_in) * s   -- grid*offset_scale, channel 0 (op.py:82)
     float gs1[DCNV3_MAX_TAPS];  // (dy_p / H_in) * s
 };
@@ -116,6 +121,21 @@ __device__ __forceinline__ Tap make_tap(const KParams& q, float ref0, float ref1
     t.alive = ax.alive && ay.alive;
     t.x0 = ax.i0;
     t.y0 = ay.i0;
+    t.dx0 = t.alive ? ax.d0 : 0.0f;
+    t.dx1 = t.alive ? ax.d1 : 0.0f;
+    t.dy0 = t.alive ? ay.d0 : 0.0f;
+    t.dy1 = t.alive ? ay.d1 : 0.0f;
+    return t;
+}
+
+// The same tap for kernels that stage the zero ring (pad = 1): a live axis needs no clips (make_axis_live); a dead tap
+// gets zero deltas by selection, never by multiplication (its coordinates may be huge or NaN).
+__device__ __forceinline__ Tap make_tap_live(const KParams& q, float ref0, float ref1, int p, float offx, float offy) {
+    const Axis ax = axis_x_live(q, ref0, p, offx), ay = axis_y_live(q, ref1, p, offy);
+    Tap t;
+    t.alive = ax.alive && ay.alive;
+    t.x0 = t.alive ? ax.i0 : 0;
+    t.y0 = t.alive ? ay.i0 : 0;
     t.dx0 = t.alive ? ax.d0 : 0.0f;
     t.dx1 = t.alive ? ax.d1 : 0.0f;
     t.dy0 = t.alive ? ay.d0 : 0.0f;

@@ -44,7 +44,7 @@ namespace dcnv3 {
 #define DCNV3_SCATTER_THREADS 512  // 16 warps x 128 registers: a 32x32 tile is 64 blocks = 4 full rounds
 #endif
 #ifndef DCNV3_SCATTER_BATCH
-#define DCNV3_SCATTER_BATCH 9      // taps whose coordinate arithmetic is done together before their ATOMS runs (0: per-tap loop)
+#define DCNV3_SCATTER_BATCH 3      // taps whose coordinate arithmetic is done together before their ATOMS runs (0: per-tap loop)
 #endif
 
 constexpr int kSG = 2;             // groups per scatter CTA (lane = pixel * kSG + group, 16 pixels per warp)
@@ -221,11 +221,13 @@ __device__ __forceinline__ void load_go(const T* go, f2 (&gf)[8]) {
 #pragma unroll
     for (int pc = 0; pc < C::NPIECE; ++pc) load_piece<T>(go + pc * C::CH_PER_PIECE, gf + pc * C::PAIRS);
 }
-__device__ __forceinline__ void fixed_point_go(const f2 (&gf)[8], float sg, int rot, int (&G)[16]) {
+// (oms = 1 - centre feature scale of the (pixel, group), 1 without the blend: the core's output gradient is
+//  RN(grad_out * oms), the product whose maximum the gather kernel took for the scale sg)
+__device__ __forceinline__ void fixed_point_go(const f2 (&gf)[8], float oms, float sg, int rot, int (&G)[16]) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        G[2 * c] = __float2int_rn(lo_of(gf[c]) * sg);
-        G[2 * c + 1] = __float2int_rn(hi_of(gf[c]) * sg);
+        G[2 * c] = __float2int_rn(__fmul_rn(lo_of(gf[c]), oms) * sg);
+        G[2 * c + 1] = __float2int_rn(__fmul_rn(hi_of(gf[c]), oms) * sg);
     }
 #pragma unroll
     for (int b = 1; b < 16; b <<= 1) {  // v[i] <- v[i ^ rot]: four conditional butterfly stages
@@ -241,16 +243,16 @@ __device__ __forceinline__ void fixed_point_go(const f2 (&gf)[8], float sg, int 
     }
 }
 template <typename T>
-__device__ __forceinline__ void load_fixed_point_go(const T* go, float sg, int rot, int (&G)[16]) {
+__device__ __forceinline__ void load_fixed_point_go(const T* go, float oms, float sg, int rot, int (&G)[16]) {
     f2 gf[8];
     load_go<T>(go, gf);
-    fixed_point_go(gf, sg, rot, G);
+    fixed_point_go(gf, oms, sg, rot, G);
 }
 
 // =====================================================================================================
 // grad_offset / grad_mask
 // =====================================================================================================
-template <typename T, bool STAGED>
+template <typename T, bool STAGED, bool BLEND>
 __global__ void __launch_bounds__(kTiledWarps * 32, 2)
 bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap offmap,
                   const __grid_constant__ CUtensorMap goffmap, const T* __restrict__ x,
@@ -322,6 +324,12 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
                 load_piece<T>(grad_out + pg * kGC + Slab<T>::chan_of(pc, rot), go + pc * C::PAIRS);
             float ref0, ref1;
             ref_point(q, h, w, ref0, ref1);
+            // centre-feature-scale blend around the op (dcn_v3.py:146): the core's output gradient is go * (1 - s)
+            float cs = 0.f, oms = 1.f;
+            if (BLEND) {
+                cs = Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + pg);
+                oms = __fsub_rn(1.0f, cs);
+            }
             // this lane's entries of the transposed side copy (real pixels and real groups only)
             const bool t_on = kUseSideT<T> && px_l < npx && chunk * C::GQ + g_l < q.G;
             size_t t_idx = side_t.index(n, chunk * (C::GQ / 2) + (g_l >> 1), h * q.wo + w, g_l & 1);
@@ -359,7 +367,7 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
                     ox = ox2; oy = oy2; ml = ml2;
                     if (p + 2 < kTaps) load_tap_inputs<T>(offp, mskp, p + 2, ox2, oy2, ml2);  // two taps ahead
                 }
-                const Tap t = make_tap(q, ref0, ref1, p, cx, cy);
+                const Tap t = make_tap_live(q, ref0, ref1, p, cx, cy);
                 const int bx = t.x0 - cx0, by = t.y0 - cy0;
                 const bool inbox = bx >= 0 && bx + 1 < tg.bw && by >= 0 && by + 1 < tg.bh;
                 const float mm = logits ? expf(cm - mx) * inv_sum : cm;
@@ -401,23 +409,40 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
                     d3 = lo_of(e3) + hi_of(e3);
                 }
                 // dead taps have all four deltas zero => zero gradients
+                // (the dot products are taken with the unscaled grad_out; (1 - s) is applied to the results)
                 const float g_m = t.dx1 * t.dy1 * d0 + t.dx1 * t.dy0 * d1 + t.dx0 * t.dy1 * d2 + t.dx0 * t.dy0 * d3;
-                const float gxq = mm * (t.dy1 * (d2 - d0) + t.dy0 * (d3 - d1));
-                const float gyq = mm * (t.dx1 * (d1 - d0) + t.dx0 * (d3 - d2));
-                gm_dot_m += g_m * mm;
+                const float gxq = mm * oms * (t.dy1 * (d2 - d0) + t.dy0 * (d3 - d1));
+                const float gyq = mm * oms * (t.dx1 * (d1 - d0) + t.dx0 * (d3 - d2));
+                gm_dot_m += g_m * mm;  // = <grad_out, core output> once all taps are in
                 // results go to the lane's slot positions (lane stride 72 / 36 bytes: conflict free)
                 if (sizeof(T) == 4) {
                     *reinterpret_cast<float2*>(st + lane * RS::LANE_OFF + p * 8) = make_float2(gxq * q.fx, gyq * q.fy);
                 } else {
                     *reinterpret_cast<unsigned*>(st + lane * RS::LANE_OFF + p * 4) = pack_bf16x2(gxq * q.fx, gyq * q.fy);
                 }
-                if (logits || sizeof(T) == 4) park[lane * kTaps + p] = g_m;
-                else *reinterpret_cast<__nv_bfloat16*>(st + RS::OFF_BYTES + lane * RS::LANE_MSK + p * 2) = __float2bfloat16_rn(g_m);
+                if (logits) park[lane * kTaps + p] = g_m;
+                else if (sizeof(T) == 4) park[lane * kTaps + p] = g_m * oms;
+                else *reinterpret_cast<__nv_bfloat16*>(st + RS::OFF_BYTES + lane * RS::LANE_MSK + p * 2) = __float2bfloat16_rn(g_m * oms);
             }
             // (max |grad_out| is taken here, after the taps: the first use of the freshly loaded grad_out is then
             //  the first tap's dot products, behind its coordinate arithmetic and shared-memory loads)
+            // ... of what the scatter kernel will convert: RN(grad_out * (1 - s)), the same product there
 #pragma unroll
-            for (int c = 0; c < 8; ++c) amax = max(amax, max(abs_bits(lo_of(go[c])), abs_bits(hi_of(go[c]))));
+            for (int c = 0; c < 8; ++c)
+                amax = max(amax, max(abs_bits(__fmul_rn(lo_of(go[c]), oms)), abs_bits(__fmul_rn(hi_of(go[c]), oms))));
+            if (BLEND) {
+                // d s = sum_c grad_out[c] * (x_proj[c] - core[c]) = <grad_out, x_proj> - sum_p m_p * dL/dm_p
+                f2 dx2 = 0ull;
+#pragma unroll
+                for (int pc = 0; pc < C::NPIECE; ++pc) {
+                    f2 xo[C::PAIRS];
+                    load_piece<T>(x + pg * kGC + Slab<T>::chan_of(pc, rot), xo);
+#pragma unroll
+                    for (int j = 0; j < C::PAIRS; ++j) ffma2v(dx2, xo[j], go[pc * C::PAIRS + j]);
+                }
+                if (px_l < npx && chunk * C::GQ + g_l < q.G)
+                    Elem<T>::st(reinterpret_cast<T*>(q.grad_cfs) + pg, lo_of(dx2) + hi_of(dx2) - gm_dot_m);
+            }
             if (logits) {
                 // softmax Jacobian needs sum_p m_p*dL/dm_p: second sweep over this lane's own 9 values.  The logits
                 // are still in the slot when T is bf16 (the park is a separate area); for fp32 the park has
@@ -426,7 +451,7 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
                 for (int p = 0; p < kTaps; ++p) {
                     const float lg = (STAGED && sizeof(T) == 2) ? RS::mask_at(st, lane, p) : Elem<T>::ld(mskp + p);
                     const float mm = expf(lg - mx) * inv_sum;
-                    const float v = mm * (park[lane * kTaps + p] - gm_dot_m);
+                    const float v = mm * oms * (park[lane * kTaps + p] - gm_dot_m);
                     if (sizeof(T) == 4) park[lane * kTaps + p] = v;
                     else *reinterpret_cast<__nv_bfloat16*>(st + RS::OFF_BYTES + lane * RS::LANE_MSK + p * 2) = __float2bfloat16_rn(v);
                 }
@@ -471,11 +496,7 @@ __device__ __forceinline__ TileBox make_box(const KParams& q, const BwdGeom& bg,
 // shared-memory integer add without return value: 32-bit shared address + immediate byte offset
 template <int OFF>
 __device__ __forceinline__ void red_shared_add(uint32_t addr, int v) {
-#ifdef DCNV3_X_NOATOMS
-    asm volatile("" ::"r"(addr), "r"(v), "n"(OFF) : "memory");
-#else
     asm volatile("red.shared.add.s32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(OFF) : "memory");
-#endif
 }
 
 // Weight counters.  Every tap adds ceil(|m| * 1025) -- an upper bound of 1024 * (sum of its four |Wk|) --
@@ -494,11 +515,7 @@ __device__ __forceinline__ bool cell_is_hot(const int* wsum, int cy, int cx, int
 }
 // one contribution in fixed point: round(G * Wk / 2^32), ties up (a single IMAD.HI with a constant addend)
 __device__ __forceinline__ int qmul(int g, int wq) {
-#ifdef DCNV3_X_NOHI
-    return g * wq + 0x8000;
-#else
     return (int)(((long long)g * wq + 0x80000000ll) >> 32);
-#endif
 }
 // (|wf| < 3.9 whenever the tap's cells are not hot -- weight_units() -- so the conversion cannot saturate there;
 //  for hot cells it may, deterministically, and those accumulators are discarded and recomputed)
@@ -517,22 +534,17 @@ __device__ __forceinline__ void side_add(const FarWs& ws, size_t cellg, const in
     ws.dirty[cellg] = 1;
 }
 
-// The scatter walk over the home pixels of one tile.
-//   MODE 0 (scatter kernel): landings inside the box -> int32 shared atomics + weight counters; landings
-//                            beyond it (but inside the image) -> 64-bit side buffer
-//   MODE 1 (redo, pass 1)  : weight counters only
-//   MODE 2 (redo, pass 2)  : landings on hot cells of the box -> 64-bit side buffer
-// A work item is one block of 16 pixels x 2 groups; blocks are dealt round-robin to the warps, and the
-// blocks of the last, incomplete round are split by taps over the warps that would otherwise idle.
+// The walk of the redo kernel over the home pixels of one tile (same enumeration of blocks and taps as the scatter
+// kernel's walk below, per-tap loop, inputs straight from the reference-layout tensors):
+//   MODE 1 (pass 1): rebuilds the weight counters exactly as the scatter kernel left them
+//   MODE 2 (pass 2): landings on hot cells of the box -> 64-bit side buffer
 template <typename T, int MODE, int TJ>
-__device__ __forceinline__ void scatter_walk(int* acc, int* wsum, const T* __restrict__ offset,
-                                             const T* __restrict__ mask, const T* __restrict__ grad_out,
-                                             const FarWs& ws, const KParams& q, const TileBox& box, int n, int chunk,
-                                             Range hh, Range hw, int eg) {
-    constexpr int PITCH = ScatterShape<TJ>::PITCH;
+__device__ __forceinline__ void redo_walk(int* wsum, const T* __restrict__ offset, const T* __restrict__ mask,
+                                          const T* __restrict__ grad_out, const FarWs& ws, const KParams& q,
+                                          const TileBox& box, int n, int chunk, Range hh, Range hw, int eg) {
+    static_assert(MODE == 1 || MODE == 2, "redo passes only");
     constexpr int WP = ScatterShape<TJ>::WPITCH;  // pitch of the weight counters
     constexpr int PXW = 32 / kSG;
-    constexpr int ROWB = PITCH * kSCell * 4;  // bytes between accumulator rows
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g_l = lane % kSG, px_l = lane / kSG;
     const int g = chunk * kSG + g_l;
@@ -540,27 +552,11 @@ __device__ __forceinline__ void scatter_walk(int* acc, int* wsum, const T* __res
     const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
     const float sg = ldexpf(1.0f, eg);  // G = round(go * 2^eg), |G| < 2^30
     const size_t img_pixels = (size_t)q.h * q.w;
-    // the lane's slab inside cell 0, pre-rotated: slab bases are 64-byte aligned, so
-    // base + ((c ^ rot) * 4) == (base ^ rot*4) ^ c*4
-    uint32_t acc_s = MODE == 0 ? ((smem_u32(acc) + (uint32_t)g_l * (kGC * 4u)) ^ ((uint32_t)px_l << 2)) : 0u;
-    // the lane's counter of anchor (-1, -1)
-    uint32_t wsum_s = MODE != 2 ? smem_u32(wsum) + (uint32_t)g_l * 4u : 0u;
-    // opaque to the compiler: otherwise it re-derives both from %tid inside the tap loop (S2R latency)
-    asm volatile("" : "+r"(acc_s), "+r"(wsum_s));
+    const uint32_t wsum_s = smem_u32(wsum) + (uint32_t)g_l * 4u;  // the lane's counter of anchor (-1, -1)
     const int nw = hw.hi - hw.lo, npix = (hh.hi - hh.lo) * nw;
     const int nblocks = (npix + PXW - 1) / PXW;
-    const int full_rounds = nblocks / nwarps, rest = nblocks - full_rounds * nwarps;
-    const int parts = rest ? min(kTaps, nwarps / rest) : 1;  // warps per block of the last round
 #pragma unroll 1
-    for (int round = 0; round <= full_rounds; ++round) {
-        int blk = round * nwarps + warp, p_lo = 0, p_hi = kTaps;
-        if (round == full_rounds) {
-            if (warp >= rest * parts) break;
-            const int part = warp % parts;
-            blk = round * nwarps + warp / parts;
-            p_lo = part * kTaps / parts;
-            p_hi = (part + 1) * kTaps / parts;
-        }
+    for (int blk = warp; blk < nblocks; blk += nwarps) {
         const int pix = blk * PXW + px_l;
         if (pix >= npix) continue;
         const int row = pix / nw;
@@ -568,81 +564,42 @@ __device__ __forceinline__ void scatter_walk(int* acc, int* wsum, const T* __res
         const size_t pg = (((size_t)n * q.ho + h) * q.wo + w) * q.G + g;
         const T* offp = offset + pg * 18;
         const T* mskp = mask + pg * 9;
-        float ox, oy, ml, ox2, oy2, ml2;
-        load_tap_inputs<T>(offp, mskp, p_lo, ox, oy, ml);
-        load_tap_inputs<T>(offp, mskp, min(p_lo + 1, kTaps - 1), ox2, oy2, ml2);
         int G[16];
-        f2 gf[8];
         bool have_g = false;
-        if (MODE == 0) load_go<T>(grad_out + pg * kGC, gf);
         float mx = 0.f, inv_sum = 1.f;
         if (logits) softmax_stats9<T>(mskp, mx, inv_sum);
         float ref0, ref1;
         ref_point(q, h, w, ref0, ref1);
-        if (MODE == 0) {  // every tap of a home pixel lands: convert grad_out once, with the whole warp converged
-            fixed_point_go(gf, sg, px_l, G);
-            have_g = true;
-        }
 #pragma unroll 1
-        for (int p = p_lo; p < p_hi; ++p) {
-            const float cxo = ox, cyo = oy, cm = ml;
-            ox = ox2; oy = oy2; ml = ml2;
-            if (p + 2 < kTaps) load_tap_inputs<T>(offp, mskp, p + 2, ox2, oy2, ml2);  // two taps ahead
-            const Axis axx = axis_x_live(q, ref0, p, cxo);
-            const Axis axy = axis_y_live(q, ref1, p, cyo);
+        for (int p = 0; p < kTaps; ++p) {
+            float ox, oy, ml;
+            load_tap_inputs<T>(offp, mskp, p, ox, oy, ml);
+            const Axis axx = axis_x_live(q, ref0, p, ox);
+            const Axis axy = axis_y_live(q, ref1, p, oy);
             if (!(axx.alive && axy.alive)) continue;  // a clipped corner pair coincides: contributes exactly 0
             const int lx = axx.i0 - q.pw - box.bx0;   // corner (y0,x0) relative to the box
             const int ly = axy.i0 - q.ph - box.by0;
-            const float mm = logits ? expf(cm - mx) * inv_sum : cm;
+            const float mm = logits ? expf(ml - mx) * inv_sum : ml;
             if (mm == 0.f) continue;
-            if (MODE == 0 &&
-                __builtin_expect((unsigned)lx < (unsigned)(box.bw - 1) && (unsigned)ly < (unsigned)(box.bh - 1), 1)) {
-                // all four corners a b c d = (y0,x0) (y1,x0) (y0,x1) (y1,x1) lie in the box
-                const int cell = ly * PITCH + lx;
-                red_shared_add<(WP + 1) * kSG * 4>(wsum_s + (uint32_t)(ly * WP + lx) * (kSG * 4u), weight_units(mm));
-                const int wqa = weight_fixed(axx.d1 * axy.d1 * mm), wqb = weight_fixed(axx.d1 * axy.d0 * mm);
-                const int wqc = weight_fixed(axx.d0 * axy.d1 * mm), wqd = weight_fixed(axx.d0 * axy.d0 * mm);
-                const uint32_t base = acc_s + (uint32_t)cell * (kSCell * 4u);  // rotation bits stay put: cell*128
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const uint32_t a = base ^ (uint32_t)(c << 2);
-                    red_shared_add<0>(a, qmul(G[c], wqa));
-                    red_shared_add<ROWB>(a, qmul(G[c], wqb));
-                    red_shared_add<kSCell * 4>(a, qmul(G[c], wqc));
-                    red_shared_add<ROWB + kSCell * 4>(a, qmul(G[c], wqd));
-                }
-                continue;
-            }
-            // ---- corner by corner: part of the patch leaves the box (or one of the redo passes) ----
             const bool touches = (unsigned)(lx + 1) <= (unsigned)box.bw && (unsigned)(ly + 1) <= (unsigned)box.bh;
-            if (MODE != 2 && touches)  // some corner lies in the box
+            if (!touches) continue;  // no corner in the box: counted nowhere, and its cells are not this box's
+            if (MODE == 1) {
                 red_shared_add<(WP + 1) * kSG * 4>(wsum_s + (uint32_t)(ly * WP + lx) * (kSG * 4u), weight_units(mm));
+            }
 #pragma unroll 1
-            for (int k = 0; k < (MODE == 1 || (MODE == 2 && !touches) ? 0 : 4); ++k) {
+            for (int k = 0; k < (MODE == 2 ? 4 : 0); ++k) {
                 const float wf = ((k >> 1) ? axx.d0 : axx.d1) * ((k & 1) ? axy.d0 : axy.d1) * mm;
                 if (wf == 0.f) continue;
                 const int cx = lx + (k >> 1), cy = ly + (k & 1);
                 const int ax = cx + box.bx0, ay = cy + box.by0;  // un-padded image coordinates
-                const bool in_image = ax >= 0 && ax < q.w && ay >= 0 && ay < q.h;
-                const size_t cellg = ((size_t)n * img_pixels + (size_t)ay * q.w + ax) * q.G + g;
-                if ((unsigned)cx < (unsigned)box.bw && (unsigned)cy < (unsigned)box.bh) {
-                    if (MODE == 2) {
-                        if (in_image && cell_is_hot<WP>(wsum, cy, cx, g_l)) {
-                            if (!have_g) {
-                                load_fixed_point_go<T>(grad_out + pg * kGC, sg, px_l, G);
-                                have_g = true;
-                            }
-                            side_add(ws, cellg, G, px_l, wf);
-                        }
-                        continue;
-                    }
-                    const int wq = weight_fixed(wf);
-                    const uint32_t base = acc_s + (uint32_t)(cy * PITCH + cx) * (kSCell * 4u);
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) red_shared_add<0>(base ^ (uint32_t)(c << 2), qmul(G[c], wq));
-                } else if (MODE == 0 && in_image) {  // beyond the ring; outside the image the gradient is dropped
-                    side_add(ws, cellg, G, px_l, wf);
+                if (!((unsigned)cx < (unsigned)box.bw && (unsigned)cy < (unsigned)box.bh)) continue;
+                if (!(ax >= 0 && ax < q.w && ay >= 0 && ay < q.h) || !cell_is_hot<WP>(wsum, cy, cx, g_l)) continue;
+                if (!have_g) {
+                    const float oms = q.cfs != nullptr ? __fsub_rn(1.0f, Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + pg)) : 1.0f;
+                    load_fixed_point_go<T>(grad_out + pg * kGC, oms, sg, px_l, G);
+                    have_g = true;
                 }
+                side_add(ws, ((size_t)n * img_pixels + (size_t)ay * q.w + ax) * q.G + g, G, px_l, wf);
             }
         }
     }
@@ -709,7 +666,7 @@ __device__ __forceinline__ void slow_tap(uint32_t acc_s, uint32_t wsum_s, const 
     }
 }
 
-template <typename T, int TJ, int TB>
+template <typename T, int TJ, int TB, bool BLEND>
 __device__ __forceinline__ void scatter_walk_batched(int* acc, int* wsum, const T* __restrict__ offset,
                                                      const T* __restrict__ mask, const T* __restrict__ grad_out,
                                                      const SideT<T>& side_t, const FarWs& ws, const KParams& q,
@@ -757,14 +714,8 @@ __device__ __forceinline__ void scatter_walk_batched(int* acc, int* wsum, const 
         it.valid = true;
         return it;
     };
-    struct Inputs { float ox[kTaps], oy[kTaps], ml[kTaps]; f2 gf[8]; };
+    struct Inputs { float ox[kTaps], oy[kTaps], ml[kTaps]; f2 gf[8]; float oms; };
     auto load_inputs = [&](const Item& it, Inputs& in) {
-#ifdef DCNV3_X_NOLOAD
-#pragma unroll
-        for (int p = 0; p < kTaps; ++p) { in.ox[p] = (float)((it.pg + p) & 3) * 0.4f - 0.6f; in.oy[p] = (float)((it.pg >> 2) & 3) * 0.4f - 0.6f; in.ml[p] = 0.11f; }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) in.gf[c] = pack2((float)(it.pg & 15) * 0.1f, (float)c * 0.1f);
-#else
         // from the transposed copy the gather kernel has just written: consecutive lanes, consecutive entries
         if (kUseSideT<T>) {
             const size_t t_idx = side_t.index(n, chunk, it.h * q.wo + it.w, g_l);
@@ -777,7 +728,7 @@ __device__ __forceinline__ void scatter_walk_batched(int* acc, int* wsum, const 
             for (int p = 0; p < kTaps; ++p) load_tap_inputs<T>(offp, mskp, p, in.ox[p], in.oy[p], in.ml[p]);
         }
         load_go<T>(grad_out + it.pg * kGC, in.gf);
-#endif
+        in.oms = BLEND ? __fsub_rn(1.0f, Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + it.pg)) : 1.0f;
     };
 
     Item cur = item_of(0);
@@ -789,7 +740,7 @@ __device__ __forceinline__ void scatter_walk_batched(int* acc, int* wsum, const 
         bool requested = false;
         if (cur.valid) {
             int G[16];
-            fixed_point_go(in.gf, sg, px_l, G);
+            fixed_point_go(in.gf, in.oms, sg, px_l, G);
             float mx = 0.f, inv_sum = 1.f;
             if (logits) {
                 mx = -INFINITY;
@@ -812,14 +763,8 @@ __device__ __forceinline__ void scatter_walk_batched(int* acc, int* wsum, const 
                 for (int t = 0; t < TB; ++t) {
                     const int p = b0 + t;
                     if (p >= kTaps) continue;
-#ifdef DCNV3_X_NOCOORD
-                    Axis axx, axy;
-                    axx.alive = axy.alive = true; axx.i0 = bx_off + 5 + (p / 3) + (cur.h & 15); axy.i0 = by_off + 5 + (p % 3) + (cur.w & 15);
-                    axx.d0 = in.ox[p]; axx.d1 = ref0; axy.d0 = in.oy[p]; axy.d1 = ref1;
-#else
                     const Axis axx = axis_x_live(q, ref0, p, in.ox[p]);
                     const Axis axy = axis_y_live(q, ref1, p, in.oy[p]);
-#endif
                     const int lx = axx.i0 - bx_off, ly = axy.i0 - by_off;  // corner (y0,x0) relative to the box
                     const float mm = logits ? expf(in.ml[p] - mx) * inv_sum : in.ml[p];
                     // alive: no clipped corner pair coincides (else the tap contributes exactly 0)
@@ -841,7 +786,7 @@ __device__ __forceinline__ void scatter_walk_batched(int* acc, int* wsum, const 
                 for (int t = 0; t < TB; ++t) {
                     const int p = b0 + t;
                     if (p >= kTaps) continue;
-                    if (p == kTaps - 1 && nxt.valid) {  // the next block's inputs travel under the last run (this
+                    if (p == kTaps - 1 && nxt.valid) {     // the next block's inputs travel under the last run (this
                         load_inputs(nxt, in);           //  block's have all been consumed by now)
                         requested = true;
                     }
@@ -871,7 +816,7 @@ __device__ long long* g_scatter_prof = nullptr;
 #define PROF_MARK(k) do { } while (0)
 #endif
 
-template <typename T, int TJ>
+template <typename T, int TJ, bool BLEND>
 __global__ void __launch_bounds__(ScatterShape<TJ>::THREADS, ScatterShape<TJ>::MIN_CTAS)
 bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
                    T* __restrict__ grad_x, const SideT<T> side_t, const FarWs ws, const KParams q, const BwdGeom bg) {
@@ -912,11 +857,7 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
     const bool nonfinite = bits_nonfinite(go_bits);  // NaN / Inf in this image's grad_out: its grad_x is NaN
     const int eg = 30 - fixed_exponent_raw(go_bits);
     if (!nonfinite) {
-#if DCNV3_SCATTER_BATCH > 0
-        scatter_walk_batched<T, TJ, DCNV3_SCATTER_BATCH>(acc, wsum, offset, mask, grad_out, side_t, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
-#else
-        scatter_walk<T, 0, TJ>(acc, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
-#endif
+        scatter_walk_batched<T, TJ, DCNV3_SCATTER_BATCH, BLEND>(acc, wsum, offset, mask, grad_out, side_t, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
     }
 #ifdef DCNV3_SCATTER_PROFILE
     if ((threadIdx.x & 31) == 0) { const long long t = clock64(); atomicMin(&s_wmin, t); atomicMax(&s_wmax, t); }
@@ -937,7 +878,6 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
     const int g = chunk * kSG + gl;
     const float qnan = __int_as_float(0x7fc00000);
     bool any_hot = false;
-#ifndef DCNV3_NO_FAST_FLUSH
     // Can any cell be hot at all?  A cell's bound is the sum of four counters, so it needs one above kBudget / 4.
     // Almost never: then the flush runs without the per-cell test, a warp per box row and with 32-bit indexing.
     int cmax = 0;
@@ -960,7 +900,13 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
                 const int4 v = *reinterpret_cast<const int4*>(arow + idx * 4);
                 if (row_owned && (unsigned)(ax - box.ux0) < (unsigned)box.tjw) {
                     const int e = ax * (q.G * kGC) + piece * 4;
-                    const float f0 = (float)v.x * inv_s, f1 = (float)v.y * inv_s, f2_ = (float)v.z * inv_s, f3 = (float)v.w * inv_s;
+                    float f0 = (float)v.x * inv_s, f1 = (float)v.y * inv_s, f2_ = (float)v.z * inv_s, f3 = (float)v.w * inv_s;
+                    if (BLEND) {  // the blend's direct path: d x_proj += grad_out * s at the pixel itself
+                        const float cs = Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + (grow * q.w + ax) * q.G + g);
+                        const float4 g4 = Elem<T>::ld4(grad_out + grow * row_elems + chunk * kSCell + e);
+                        f0 = __fadd_rn(f0, __fmul_rn(g4.x, cs)); f1 = __fadd_rn(f1, __fmul_rn(g4.y, cs));
+                        f2_ = __fadd_rn(f2_, __fmul_rn(g4.z, cs)); f3 = __fadd_rn(f3, __fmul_rn(g4.w, cs));
+                    }
                     if (sizeof(T) == 4) {
                         *reinterpret_cast<float4*>(reinterpret_cast<float*>(gx_row) + e) = make_float4(f0, f1, f2_, f3);
                     } else {
@@ -983,7 +929,6 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
         PROF_MARK(4);
         return;
     }
-#endif
     for (int item = warp; item < box.bh * segs; item += nwarps) {
         const int cy = item / segs, cx = ((item - cy * segs) << 2) + (lane >> 3);
         const int ax = box.bx0 + cx, ay = box.by0 + cy;
@@ -998,8 +943,14 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
             const size_t gidx = gpix * ((size_t)q.G * kGC) + (size_t)(chunk * kSCell + piece * 4);
             const bool drop = hot || nonfinite;
             const float fill = nonfinite ? qnan : 0.f;
-            const float f0 = drop ? fill : (float)v.x * inv_s, f1 = drop ? fill : (float)v.y * inv_s;
-            const float f2_ = drop ? fill : (float)v.z * inv_s, f3 = drop ? fill : (float)v.w * inv_s;
+            float f0 = drop ? fill : (float)v.x * inv_s, f1 = drop ? fill : (float)v.y * inv_s;
+            float f2_ = drop ? fill : (float)v.z * inv_s, f3 = drop ? fill : (float)v.w * inv_s;
+            if (BLEND) {  // the blend's direct path (hot cells: the redo / merge kernels add to this)
+                const float cs = Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + gpix * q.G + g);
+                const float4 g4 = Elem<T>::ld4(grad_out + gidx);
+                f0 = __fadd_rn(f0, __fmul_rn(g4.x, cs)); f1 = __fadd_rn(f1, __fmul_rn(g4.y, cs));
+                f2_ = __fadd_rn(f2_, __fmul_rn(g4.z, cs)); f3 = __fadd_rn(f3, __fmul_rn(g4.w, cs));
+            }
             if (sizeof(T) == 4) {
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(grad_x) + gidx) = make_float4(f0, f1, f2_, f3);
             } else {
@@ -1062,9 +1013,9 @@ redo_hot_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const 
             for (int i = threadIdx.x; i < (bg.box_rows + 1) * WP * kSG; i += blockDim.x) wsum[i] = 0;
             __syncthreads();
             const int eg = 30 - fixed_exponent_raw(ws.img_max[n].go_bits);
-            scatter_walk<T, 1, TJ>(nullptr, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+            redo_walk<T, 1, TJ>(wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
             __syncthreads();
-            scatter_walk<T, 2, TJ>(nullptr, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+            redo_walk<T, 2, TJ>(wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
             __syncthreads();
             if (threadIdx.x == 0) ws.redo[tile] = 0;
             if (bg.tiles_x * bg.tiles_y == 1) {  // (otherwise merge_far_kernel folds the side buffer into grad_x)
@@ -1085,7 +1036,8 @@ redo_hot_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const 
                     const size_t idx = cellg * kGC + ch % kGC;
                     const long long v = (long long)__ldcg(ws.acc64 + idx);
                     // |v| can exceed 2^24: go through double so that the exact total is rounded once
-                    Elem<T>::st(grad_x + idx, (float)((double)v * inv_d));
+                    // (added to what the flush left there: 0, or the blend's direct term)
+                    Elem<T>::st(grad_x + idx, __fadd_rn(Elem<T>::ld_plain(grad_x + idx), (float)((double)v * inv_d)));
                     ws.acc64[idx] = 0ull;
                     ws.dirty[cellg] = 0;
                 }
@@ -1192,10 +1144,12 @@ static cudaError_t launch_scatter(const T* offset, const T* mask, const T* grad_
                                   cudaStream_t st) {
     using S = ScatterShape<TJ>;
     const size_t smem = scatter_smem_bytes<TJ>(bg.box_rows);
-    cudaError_t e = ensure_max_smem((const void*)bwd_scatter_kernel<T, TJ>, (int)scatter_smem_bytes<TJ>(S::PITCH));
+    // (two instances: the centre-feature-scale blend costs the plain op nothing)
+    auto kernel = q.cfs != nullptr ? bwd_scatter_kernel<T, TJ, true> : bwd_scatter_kernel<T, TJ, false>;
+    cudaError_t e = ensure_max_smem((const void*)kernel, (int)scatter_smem_bytes<TJ>(S::PITCH));
     if (e != cudaSuccess) return e;
     KernelTiming& kt = kernel_timing();
-    e = launch_pdl(bwd_scatter_kernel<T, TJ>, grid, S::THREADS, smem, st, offset, mask, grad_out, grad_x, side_t, ws, q, bg);
+    e = launch_pdl(kernel, grid, S::THREADS, smem, st, offset, mask, grad_out, grad_x, side_t, ws, q, bg);
     if (e != cudaSuccess) return e;
     if (kt.enabled) cudaEventRecord(kt.ev[2], st);
     const unsigned redo_grid = grid < 32u ? grid : 32u;  // normally they only read one word and leave
@@ -1208,12 +1162,12 @@ static cudaError_t launch_gather_variant(const CUtensorMap& map, const CUtensorM
                                          const void* x, const void* offset, const void* mask, const void* grad_out,
                                          void* grad_offset, void* grad_mask, ImgMax* img_max, const SideT<T>& side_t,
                                          const KParams& q, const TileGeom& tg, cudaStream_t st) {
-    cudaError_t e = ensure_max_smem((const void*)bwd_gather_kernel<T, STAGED>,
-                                    kMaxBoxBytes + kTiledWarps * kGatherStageBytes<T>);
+    auto kernel = q.cfs != nullptr ? bwd_gather_kernel<T, STAGED, true> : bwd_gather_kernel<T, STAGED, false>;
+    cudaError_t e = ensure_max_smem((const void*)kernel, kMaxBoxBytes + kTiledWarps * kGatherStageBytes<T>);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((size_t)q.n * tg.chunks * tg.tiles_h * tg.tiles_w);
     // (also leaves the per-image max |grad_out| in the workspace: the fixed-point scale of the scatter kernel)
-    return launch_pdl(bwd_gather_kernel<T, STAGED>, grid, kTiledWarps * 32,
+    return launch_pdl(kernel, grid, kTiledWarps * 32,
                       (size_t)tg.bw * tg.bh * kCellBytes + kTiledWarps * kGatherStageBytes<T>, st, map, offmap, goffmap,
                       (const T*)x, (const T*)offset, (const T*)mask, (const T*)grad_out, (T*)grad_offset, (T*)grad_mask,
                       img_max, side_t, q, tg);

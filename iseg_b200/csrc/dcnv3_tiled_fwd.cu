@@ -116,7 +116,7 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                     ox = ox2; oy = oy2; ml = ml2;
                     if (p + 2 < kTaps) load_tap_inputs<T>(offp, mskp, p + 2, ox2, oy2, ml2);  // prefetch two taps ahead
                 }
-                const Tap t = make_tap(q, ref0, ref1, p, cx, cy);
+                const Tap t = make_tap_live(q, ref0, ref1, p, cx, cy);
                 const int bx = t.x0 - cx0, by = t.y0 - cy0;
                 const bool inbox = bx >= 0 && bx + 1 < tg.bw && by >= 0 && by + 1 < tg.bh;
                 const float mm = t.alive ? (logits ? expf(cm - mx) * inv_sum : cm) : 0.f;
@@ -161,6 +161,24 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 if (it + kTiledWarps < ctx.nit) request(ctx, it + kTiledWarps);
             }
             if (valid) {
+                if (q.cfs != nullptr) {
+                    // centre-feature-scale blend (dcn_v3.py:146): core * (1 - s) + x_proj * s, the reference's three
+                    // separately rounded operations; x_proj is this pixel's own slab of x (ho == h, wo == w here)
+                    const float s = Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + pg);
+                    const float oms = __fsub_rn(1.0f, s);
+#pragma unroll
+                    for (int pc = 0; pc < C::NPIECE; ++pc) {
+                        f2 xo[C::PAIRS];
+                        load_piece<T>(x + pg * kGC + Slab<T>::chan_of(pc, rot), xo);
+#pragma unroll
+                        for (int j = 0; j < C::PAIRS; ++j) {
+                            const f2 a = acc[pc * C::PAIRS + j];
+                            acc[pc * C::PAIRS + j] =
+                                pack2(__fadd_rn(__fmul_rn(lo_of(a), oms), __fmul_rn(lo_of(xo[j]), s)),
+                                      __fadd_rn(__fmul_rn(hi_of(a), oms), __fmul_rn(hi_of(xo[j]), s)));
+                        }
+                    }
+                }
                 T* dst = out + pg * kGC;
 #pragma unroll
                 for (int pc = 0; pc < C::NPIECE; ++pc)

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .op import dcnv3_op
+from .op import dcnv3_op, dcnv3_op_center_scale
 
 LAYER_NORM_EPSILON = 1e-6
 
@@ -91,14 +91,13 @@ class DeformableConvolutionV3(nn.Module):
         mask = self.mask(x1)  # :120
         if not self.fuse_softmax:  # :121-123
             mask = torch.softmax(mask.reshape(n, h, w, self.groups, -1), dim=-1).reshape(n, h, w, -1)
-        x = dcnv3_op(x_proj, offset, mask, [self.kernel_size] * 2, [self.strides] * 2, self.padding,
-                     [self.dilation_rate] * 2, self.groups, self.filters_per_group,
-                     self.offset_scale, mask_is_logits=self.fuse_softmax)  # :125-136
-        if self.center_feature_scale:  # :138-146
-            cfs = self.center_feature_scale_proj(x1)
-            cfs = cfs.unsqueeze(-1).expand(n, h, w, self.groups, self.filters_per_group)
-            cfs = cfs.reshape(n, h, w, c)
-            x = x * (1 - cfs) + x_proj * cfs
+        args = ([self.kernel_size] * 2, [self.strides] * 2, self.padding, [self.dilation_rate] * 2, self.groups,
+                self.filters_per_group, self.offset_scale)
+        if self.center_feature_scale:  # :125-146: the op and the blend x * (1 - cfs) + x_proj * cfs in one call
+            cfs = self.center_feature_scale_proj(x1)  # [N, H, W, groups]
+            x = dcnv3_op_center_scale(x_proj, offset, mask, cfs, *args, mask_is_logits=self.fuse_softmax)
+        else:
+            x = dcnv3_op(x_proj, offset, mask, *args, mask_is_logits=self.fuse_softmax)  # :125-136
         return self.output_proj(x)  # :148
 
     call = forward

@@ -558,3 +558,77 @@ def test_full_size_properties(ops, dtype, shape, scale):
     xr2, or2, mr2 = x.clone().requires_grad_(), off.clone().requires_grad_(), mask.clone().requires_grad_()
     iseg.dcnv3_op(xr2, or2, mr2, *args).backward(go)
     assert torch.equal(xr.grad, xr2.grad) and torch.equal(orq.grad, or2.grad) and torch.equal(mr.grad, mr2.grad)
+
+
+# ---- centre-feature-scale blend fused into the kernels (reference dcn_v3.py:138-146) -------------------------
+def _blend_reference(x, off, m, cs, go, g, gc, offset_scale=1.0, logits=False):
+    """fp32 numpy restatement of `x_core * (1 - cfs) + x_proj * cfs` around the oracle's op, and its gradients:
+    the core sees grad_out * (1 - s); x also receives grad_out * s directly; d s = sum_c grad_out * (x - core)."""
+    n, h, w, c = x.shape
+    s = np.repeat(cs, gc, axis=-1).astype(np.float32)                       # [N,H,W,G] -> [N,H,W,C]
+    mm = m
+    if logits:
+        z = m.reshape(n, h, w, g, 9)
+        e = np.exp(z - z.max(-1, keepdims=True))
+        mm = (e / e.sum(-1, keepdims=True)).reshape(n, h, w, g * 9).astype(np.float32)
+    core = c_oracle.forward(x, off, mm, groups=g, group_channels=gc, offset_scale=offset_scale)
+    out = core * (np.float32(1) - s) + x * s
+    gcore = (go * (np.float32(1) - s)).astype(np.float32)
+    gx, goff, gm = c_oracle.backward(x, off, mm, gcore, groups=g, group_channels=gc, offset_scale=offset_scale)
+    gx = gx + go * s
+    if logits:  # soft-max Jacobian (dcn_v3.py:120-123)
+        gmr, mr = gm.reshape(n, h, w, g, 9), mm.reshape(n, h, w, g, 9)
+        gm = (mr * (gmr - (mr * gmr).sum(-1, keepdims=True))).reshape(n, h, w, g * 9)
+    gs = (go * (x - core)).reshape(n, h, w, g, gc).sum(-1)
+    return out, gx, goff, gm, gs
+
+
+@pytest.mark.parametrize("shape, dtype, logits", [
+    ((2, 40, 40, 4, 16), torch.float32, False),     # several scatter tiles (ring hand-over, merge kernel)
+    ((3, 17, 23, 3, 16), torch.float32, True),      # single tile, odd group count (phantom group), fused soft-max
+    ((2, 64, 48, 8, 16), torch.bfloat16, False),
+])
+def test_center_scale_blend_fused(ops, shape, dtype, logits):
+    iseg, cabi = ops
+    n, h, w, g, gc = shape
+    x, off, m, go = make_inputs(n, h, w, g, gc, sigma=1.5, seed=21)
+    rng = np.random.default_rng(5)
+    cs = rng.uniform(-0.5, 1.5, size=(n, h, w, g)).astype(np.float32)       # no sigmoid in the reference: any real
+    if logits:
+        m = rng.standard_normal(m.shape).astype(np.float32)
+    if dtype == torch.bfloat16:  # the yardstick sees the bf16-rounded inputs
+        x, off, m, go, cs = (torch.from_numpy(a).to(torch.bfloat16).float().numpy() for a in (x, off, m, go, cs))
+    tx, to, tm, ts = cuda(x, off, m, cs, dtype=dtype)
+    for t in (tx, to, tm, ts):
+        t.requires_grad_(True)
+    assert cabi.blend_supported(tx, to, (3, 3), (1, 1), (1, 1), (1, 1), g, gc, 1.0)
+    before = cabi.launch_count()
+    out = iseg.dcnv3_op_center_scale(tx, to, tm, ts, [3, 3], [1, 1], "SAME", [1, 1], g, gc, 1.0, mask_is_logits=logits)
+    assert cabi.launch_count() - before == 1  # the blend costs no launch of its own
+    out.backward(cuda(go, dtype=dtype)[0])
+    got = [t.float().cpu().numpy() for t in (out.detach(), tx.grad, to.grad, tm.grad, ts.grad)]
+    ref = _blend_reference(x, off, m, cs, go, g, gc, logits=logits)
+    tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
+    for name, a, b in zip(("out", "grad_x", "grad_offset", "grad_mask", "grad_center_scale"), got, ref):
+        assert rel_err(a, b) <= tol, name
+    # bitwise reproducible, blend included
+    tx.grad = None
+    out2 = iseg.dcnv3_op_center_scale(tx, to, tm, ts, [3, 3], [1, 1], "SAME", [1, 1], g, gc, 1.0, mask_is_logits=logits)
+    out2.backward(cuda(go, dtype=dtype)[0])
+    assert torch.equal(out2, out) and np.array_equal(tx.grad.float().cpu().numpy(), got[1])
+
+
+def test_center_scale_blend_unfused_configurations(ops):
+    """32 channels per group (InternImage-H) runs the generic kernels: the blend is then applied around the op
+    with torch operations, same values; and the C ABI says so instead of computing something else."""
+    iseg, cabi = ops
+    n, h, w, g, gc = 1, 12, 12, 2, 32
+    x, off, m, go = make_inputs(n, h, w, g, gc, seed=8)
+    cs = np.random.default_rng(2).uniform(0, 1, size=(n, h, w, g)).astype(np.float32)
+    tx, to, tm, ts = cuda(x, off, m, cs)
+    assert not cabi.blend_supported(tx, to, (3, 3), (1, 1), (1, 1), (1, 1), g, gc, 1.0)
+    out = iseg.dcnv3_op_center_scale(tx, to, tm, ts, [3, 3], [1, 1], "SAME", [1, 1], g, gc, 1.0)
+    ref = _blend_reference(x, off, m, cs, go, g, gc)[0]
+    assert rel_err(out.cpu().numpy(), ref) <= TOL_F32
+    with pytest.raises(cabi.DCNv3Error):
+        cabi.forward_blend(tx, to, tm, ts, (3, 3), (1, 1), (1, 1), (1, 1), g, gc, 1.0)
