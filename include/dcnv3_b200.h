@@ -135,6 +135,24 @@ int dcnv3_backward_blend(const void* x, const void* offset, const void* mask, co
                          void* grad_center_scale, void* workspace, size_t workspace_bytes, const dcnv3_params* p,
                          void* cuda_stream);
 
+/* ---- inference fast path of the layers around the op: each element-wise chain as one pass (no gradients) ----
+   dcnv3_dwconv_ln_act: out = act(LayerNorm(DepthwiseConv2D(x) + bias)) on NHWC [n,h,w,c] -- the x1 branch of
+        DeformableConvolutionV3.call (reference layers/dcn_v3/dcn_v3.py:115-117).  weight_kkc: [k*k][c], tap-major
+        (Keras depthwise kernel [k,k,c,1] as stored); stride 1, zero padding pad_lo before and k-1-pad_lo after
+        (Keras 'same': pad_lo = (k-1)/2); activation 0 = none, 1 = exact (erf) GELU.
+   dcnv3_layer_join: the joins of InternImageLayer.call (reference backbones/intern_image/intern_image_layer.py:126-172)
+        over [rows, channels]:
+        mode 0: out_sum = residual + gamma * y; out_norm (may be NULL) = LayerNorm(out_sum)        (pre-norm, :161-170)
+        mode 1: out_sum = residual + gamma * LayerNorm(y)                      (post-norm :127-138, res-post-norm :145-155)
+        mode 2: out_sum = LayerNorm(y)
+        gamma may be NULL (no layer scale).  All arrays have the activation dtype; channels % 4 == 0, <= 4096. */
+int dcnv3_dwconv_ln_act(const void* x, const void* weight_kkc, const void* bias, const void* ln_weight, const void* ln_bias,
+                        void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, int32_t pad_lo, float eps,
+                        int32_t activation, int32_t dtype, void* cuda_stream);
+int dcnv3_layer_join(const void* y, const void* residual, const void* gamma, const void* ln_weight, const void* ln_bias,
+                     void* out_sum, void* out_norm, int64_t rows, int32_t channels, float eps, int32_t mode, int32_t dtype,
+                     void* cuda_stream);
+
 /* ---- DLPack entry points: same calls, tensors described by DLManagedTensor (zero copy);
         shapes, dtype, device and contiguity are taken from / checked against the tensors ---- */
 int dcnv3_forward_dlpack(const DLManagedTensor* x, const DLManagedTensor* offset,

@@ -56,6 +56,8 @@ def _load():
     lib.dcnv3_backward_workspace_zero_bytes.restype = ctypes.c_size_t
     lib.dcnv3_backward.argtypes = [vp] * 8 + [ctypes.c_size_t, pp, vp]
     lib.dcnv3_blend_supported.argtypes = [pp]
+    lib.dcnv3_dwconv_ln_act.argtypes = [vp] * 6 + [ci] * 6 + [cf, ci, ci, vp]
+    lib.dcnv3_layer_join.argtypes = [vp] * 7 + [ctypes.c_int64, ci, cf, ci, ci, vp]
     lib.dcnv3_forward_blend.argtypes = [vp] * 5 + [pp, vp]
     lib.dcnv3_backward_blend.argtypes = [vp] * 10 + [ctypes.c_size_t, pp, vp]
     scal = [ci] * 10 + [cf, cu, vp]
@@ -254,3 +256,45 @@ def backward_blend(x, offset, mask, center_scale, grad_out, kernel_size, strides
             _ws_cache.pop(_ws_key(x.device, ws_bytes), None)
     check(rc)
     return gx, goff, gm, gs
+
+
+# ---- inference fast path of the layers around the op (include/dcnv3_b200.h: dcnv3_dwconv_ln_act, dcnv3_layer_join) ----
+def fused_layers_usable(x):
+    """The one-pass kernels serve dense CUDA fp32 / bf16 activations with channels % 4 == 0 (<= 4096), without
+    autograd recording (they have no backward)."""
+    return (x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and x.shape[-1] % 4 == 0
+            and x.shape[-1] <= 4096 and not torch.is_grad_enabled())
+
+
+def _dt(t):
+    return F32 if t.dtype == torch.float32 else BF16
+
+
+def _optr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def dwconv_ln_act(x, weight_kkc, bias, ln_weight, ln_bias, k, pad_lo, eps, gelu=True):
+    """act(LayerNorm(DepthwiseConv2D(x) + bias)) on NHWC in one pass (reference dcn_v3.py:115-117)."""
+    x = x.contiguous()
+    n, h, w, c = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.dcnv3_dwconv_ln_act(_ptr(x), _ptr(weight_kkc), _optr(bias), _ptr(ln_weight), _ptr(ln_bias), _ptr(out),
+                                      n, h, w, c, int(k), int(pad_lo), float(eps), 1 if gelu else 0, _dt(x), _stream(x)))
+    return out
+
+
+def layer_join(y, residual, gamma, ln_weight, ln_bias, eps, mode, want_norm=True):
+    """The joins of InternImageLayer (reference intern_image_layer.py:126-172) in one pass.
+    mode 0: (residual + gamma * y, LayerNorm of that or None); mode 1: residual + gamma * LayerNorm(y); mode 2: LayerNorm(y)."""
+    y = y.contiguous()
+    c = y.shape[-1]
+    rows = y.numel() // c
+    residual = None if residual is None else residual.contiguous()
+    out_sum = torch.empty_like(y)
+    out_norm = torch.empty_like(y) if (mode == 0 and want_norm) else None
+    with torch.cuda.device(y.device):
+        check(lib.dcnv3_layer_join(_ptr(y), _optr(residual), _optr(gamma), _optr(ln_weight), _optr(ln_bias), _ptr(out_sum),
+                                   _optr(out_norm), rows, c, float(eps), int(mode), _dt(y), _stream(y)))
+    return (out_sum, out_norm) if mode == 0 else out_sum

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ... import _cabi
 from ...layers.dcn_v3.dcn_v3 import DeformableConvolutionV3
 
 LN_EPS = 1e-6
@@ -103,7 +104,36 @@ class InternImageLayer(nn.Module):
     def _g(self, gamma, x):
         return gamma.to(x.dtype) if torch.is_tensor(gamma) else gamma
 
+    def _gamma(self, gamma, x):
+        return gamma.detach().to(x.dtype) if torch.is_tensor(gamma) else None
+
+    def forward_fused(self, x, x_norm1=None, next_norm=None):
+        """Inference fast path: the same arithmetic as `forward` in eval mode, with every
+        join of the layer -- layer scale, residual add and the LayerNorm next to it -- done by one pass of
+        `dcnv3_layer_join` instead of three element-wise kernels.  `x_norm1`: norm1(x) if the previous layer's last
+        join already produced it; `next_norm`: the LayerNorm that will consume this layer's output first (the next
+        pre-norm layer's norm1), fused into the last join.  Returns (out, next_norm(out) or None)."""
+        j, eps = _cabi.layer_join, LN_EPS
+        g1, g2 = self._gamma(self.gamma1, x), self._gamma(self.gamma2, x)
+        if self.use_post_norm:  # :126-139
+            z = j(self.dcn(x), x, g1, self.norm1.weight, self.norm1.bias, eps, 1)
+            return j(self.mlp(z), z, g2, self.norm2.weight, self.norm2.bias, eps, 1), None
+        if self.use_res_post_norm:  # :142-156
+            n1 = j(x, None, None, self.norm1.weight, self.norm1.bias, eps, 2)
+            z = j(self.dcn(n1), x, None, self.res_post_norm1.weight, self.res_post_norm1.bias, eps, 1)
+            n2 = j(z, None, None, self.norm2.weight, self.norm2.bias, eps, 2)
+            return j(self.mlp(n2), z, None, self.res_post_norm2.weight, self.res_post_norm2.bias, eps, 1), None
+        # pre-norm, :158-172
+        if x_norm1 is None:
+            x_norm1 = j(x, None, None, self.norm1.weight, self.norm1.bias, eps, 2)
+        z, n2 = j(self.dcn(x_norm1), x, g1, self.norm2.weight, self.norm2.bias, eps, 0)
+        if next_norm is None:
+            return j(self.mlp(n2), z, g2, None, None, eps, 0, want_norm=False)[0], None
+        return j(self.mlp(n2), z, g2, next_norm.weight, next_norm.bias, eps, 0)
+
     def forward(self, x):
+        if not self.training and _cabi.fused_layers_usable(x) and self.norm1.weight.dtype == x.dtype:
+            return self.forward_fused(x)[0]
         t, dp, residual = self.training, self.drop_path_rate, x
         if self.use_post_norm:  # intern_image_layer.py:126-139
             x = drop_path(self.norm1(self.dcn(x)) * self._g(self.gamma1, x), dp, t)
@@ -135,11 +165,29 @@ class InternImageBlock(nn.Module):
         self.downsample = DownsampleLayer(channels) if use_downsample else None
 
     def forward(self, x):
+        fused = (not self.training and _cabi.fused_layers_usable(x) and self.blocks[0].norm1.weight.dtype == x.dtype)
+        pending = None  # norm1(x) of the coming layer, already produced by the previous layer's last join
+        normed_is_final = False
         for i, blk in enumerate(self.blocks):
-            x = blk(x)
-            if self.post_norm_block_ids is not None and i in self.post_norm_block_ids:
+            level2 = self.post_norm_block_ids is not None and i in self.post_norm_block_ids
+            if fused:
+                # a pre-norm layer's first LayerNorm is fused into the join that ends the layer before it; the stage's
+                # closing LayerNorm into the join that ends its last layer
+                nxt = None
+                if not (blk.use_post_norm or blk.use_res_post_norm) and not level2:
+                    nxt = self.blocks[i + 1].norm1 if i + 1 < len(self.blocks) else self.norm
+                x, normed = blk.forward_fused(x, pending, nxt)
+                pending = normed if i + 1 < len(self.blocks) else None
+                if i + 1 == len(self.blocks) and normed is not None:
+                    x, normed_is_final = normed, True
+                else:
+                    normed_is_final = False
+            else:
+                x = blk(x)
+                normed_is_final = False
+            if level2:
                 x = self.post_norms[self.post_norm_block_ids.index(i)](x)
-        if self.norm is not None:
+        if self.norm is not None and not (fused and normed_is_final):
             x = self.norm(x)
         before = x
         if self.downsample is not None:

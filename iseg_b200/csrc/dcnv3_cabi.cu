@@ -399,6 +399,50 @@ int dcnv3_backward_blend(const void* x, const void* offset, const void* mask, co
                          (cudaStream_t)cuda_stream, center_scale, grad_center_scale, true);
 }
 
+int dcnv3_layer_join(const void* y, const void* residual, const void* gamma, const void* ln_weight, const void* ln_bias,
+                     void* out_sum, void* out_norm, int64_t rows, int32_t channels, float eps, int32_t mode, int32_t dtype,
+                     void* cuda_stream) {
+    if (dtype != DCNV3_F32 && dtype != DCNV3_BF16) return fail(DCNV3_ERR_DTYPE, "dtype %d not supported", dtype);
+    if (rows < 0 || channels <= 0 || channels % 4 != 0 || channels > max_ln_channels())
+        return fail(DCNV3_ERR_SHAPE, "dcnv3_layer_join: %lld rows x %d channels (channels must be a multiple of 4, <= %d)",
+                    (long long)rows, channels, max_ln_channels());
+    if (mode < 0 || mode > 2) return fail(DCNV3_ERR_ARGUMENT, "dcnv3_layer_join: mode %d", mode);
+    if (rows == 0) return DCNV3_OK;
+    int rc;
+    const size_t al = dtype == DCNV3_F32 ? 16 : 8;
+    if ((rc = check_ptr_align(y, "y", al)) || (rc = check_ptr_align(out_sum, "out_sum", al))) return rc;
+    if (mode != 2 && (rc = check_ptr_align(residual, "residual", al))) return rc;
+    if ((mode != 0 || out_norm != nullptr) && ((rc = check_ptr_align(ln_weight, "ln_weight", al)) || (rc = check_ptr_align(ln_bias, "ln_bias", al))))
+        return rc;
+    if (gamma != nullptr && (rc = check_ptr_align(gamma, "gamma", al))) return rc;
+    if (out_norm != nullptr && (rc = check_ptr_align(out_norm, "out_norm", al))) return rc;
+    const cudaError_t e = launch_ln_join(y, residual, gamma, ln_weight, ln_bias, out_sum, out_norm, rows, channels, eps, mode, dtype,
+                                         (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "dcnv3_layer_join launch");
+    return DCNV3_OK;
+}
+
+int dcnv3_dwconv_ln_act(const void* x, const void* weight_kkc, const void* bias, const void* ln_weight, const void* ln_bias,
+                        void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, int32_t pad_lo, float eps,
+                        int32_t activation, int32_t dtype, void* cuda_stream) {
+    if (dtype != DCNV3_F32 && dtype != DCNV3_BF16) return fail(DCNV3_ERR_DTYPE, "dtype %d not supported", dtype);
+    if (n < 0 || h <= 0 || w <= 0 || c <= 0 || c % 4 != 0 || c > max_ln_channels() || k <= 0 || k > 15 || pad_lo < 0 || pad_lo >= k)
+        return fail(DCNV3_ERR_SHAPE, "dcnv3_dwconv_ln_act: [%d,%d,%d,%d], kernel %d, pad %d (channels: multiple of 4, <= %d)", n, h, w,
+                    c, k, pad_lo, max_ln_channels());
+    if (activation != 0 && activation != 1) return fail(DCNV3_ERR_ARGUMENT, "activation %d (0 none, 1 gelu)", activation);
+    if (n == 0) return DCNV3_OK;
+    int rc;
+    const size_t al = dtype == DCNV3_F32 ? 16 : 8;
+    if ((rc = check_ptr_align(x, "x", al)) || (rc = check_ptr_align(weight_kkc, "weight", al)) || (rc = check_ptr_align(out, "out", al)) ||
+        (rc = check_ptr_align(ln_weight, "ln_weight", al)) || (rc = check_ptr_align(ln_bias, "ln_bias", al)))
+        return rc;
+    if (bias != nullptr && (rc = check_ptr_align(bias, "bias", al))) return rc;
+    const cudaError_t e = launch_dwconv_ln_act(x, weight_kkc, bias, ln_weight, ln_bias, out, n, h, w, c, k, pad_lo, eps, activation,
+                                               dtype, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "dcnv3_dwconv_ln_act launch");
+    return DCNV3_OK;
+}
+
 size_t dcnv3_backward_workspace_bytes(const dcnv3_params* p) {
     if (check(p) != DCNV3_OK) return 0;
     return backward_ws_bytes(p);

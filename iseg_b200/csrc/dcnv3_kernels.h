@@ -37,4 +37,14 @@ cudaError_t launch_bwd_tiled(const void* x, const void* offset, const void* mask
                              void* grad_x, void* grad_offset, void* grad_mask, void* ws, void* scratch, const KParams& q,
                              int dtype, bool ws_clean, cudaStream_t st);
 
+// raises a kernel's dynamic shared-memory limit once per (kernel, device) (dcnv3_tiled_fwd.cu)
+cudaError_t ensure_max_smem(const void* kernel, int bytes);
+
+// layer fast path (layer_fused.cu): element-wise chains around the op, one pass each
+int max_ln_channels();
+cudaError_t launch_ln_join(const void* y, const void* r, const void* gamma, const void* lw, const void* lb, void* out_sum,
+                           void* out_norm, long long rows, int C, float eps, int mode, int dtype, cudaStream_t st);
+cudaError_t launch_dwconv_ln_act(const void* x, const void* wt, const void* bias, const void* lw, const void* lb, void* out,
+                                 int N, int H, int W, int C, int k, int pad_lo, float eps, int act, int dtype, cudaStream_t st);
+
 }  // namespace dcnv3

@@ -1,0 +1,215 @@
+// Inference fast path of the layer around the DCNv3 op: the element-wise chains the
+// reference leaves to XLA, each as ONE pass over HBM.
+//
+//   dwconv_ln_act_kernel -- x1 = act(LayerNorm(DepthwiseConv2D(x) + bias))        reference layers/dcn_v3/dcn_v3.py:115-117
+//                           (the branch that feeds the offset / mask / centre-scale projections)
+//   ln_join_kernel       -- the joins of InternImageLayer (backbones/intern_image/intern_image_layer.py:126-172):
+//        mode 0 (pre-norm):       z = r + gamma * y ;           also LayerNorm(z) for the sub-layer that follows  (:161-170)
+//        mode 1 (post-norm):      z = r + gamma * LayerNorm(y)                                                    (:127-138)
+//                                 (gamma = NULL: res-post-norm, :145-155)
+//        mode 2:                  LayerNorm(y) only
+//
+// One warp per pixel, channels across the lanes in 16-byte pieces, statistics in fp32 from the values as they are
+// stored (a bf16 tensor is normalised from its bf16-rounded sums, like the unfused chain), two-pass variance.
+// Both are HBM-bound streams: algorithmic bytes (1 read + 1 write) * C * element size per pixel (+ the second output
+// of mode 0); the 3x3 neighbourhood of the depthwise convolution is served by L1 / L2.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dcnv3_b200.h"
+#include "dcnv3_common.cuh"
+#include "dcnv3_kernels.h"
+
+namespace dcnv3 {
+
+constexpr int kLnWarps = 8;
+constexpr int kMaxLnChannels = 4096;  // per-warp fp32 row in shared memory: 16 KB x 8 warps
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ float round_to(float v);
+template <>
+__device__ __forceinline__ float round_to<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float round_to<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+
+// mean and 1/sqrt(var + eps) of the warp's row (C floats in shared memory), two passes
+__device__ __forceinline__ void row_stats(const float* row, int C, int lane, float eps, float& mean, float& rstd) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += row[c];
+    mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float d = row[c] - mean;
+        q += d * d;
+    }
+    rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_join_kernel(const T* __restrict__ y, const T* __restrict__ r, const T* __restrict__ gamma,
+               const T* __restrict__ lw, const T* __restrict__ lb, T* __restrict__ out_sum, T* __restrict__ out_norm,
+               long long rows, int C, float eps, int mode) {
+    extern __shared__ float srow[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* row = srow + (size_t)warp * C;
+    for (long long p = (long long)blockIdx.x * kLnWarps + warp; p < rows; p += (long long)gridDim.x * kLnWarps) {
+        const T* yp = y + p * C;
+        const T* rp = r ? r + p * C : nullptr;
+        if (mode == 0) {
+            // z = r + gamma * y  (products and sums rounded to T like the unfused chain), then LayerNorm(z)
+            for (int c = lane * 4; c < C; c += 128) {
+                const float4 a = Elem<T>::ld4(yp + c), b = Elem<T>::ld4(rp + c);
+                float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (gamma) g = Elem<T>::ld4(gamma + c);
+                float4 z;
+                z.x = round_to<T>(b.x + round_to<T>(a.x * g.x)); z.y = round_to<T>(b.y + round_to<T>(a.y * g.y));
+                z.z = round_to<T>(b.z + round_to<T>(a.z * g.z)); z.w = round_to<T>(b.w + round_to<T>(a.w * g.w));
+                *reinterpret_cast<float4*>(row + c) = z;
+                Elem<T>::st4(out_sum + p * C + c, z);
+            }
+            __syncwarp();
+            if (out_norm != nullptr) {
+                float mean, rstd;
+                row_stats(row, C, lane, eps, mean, rstd);
+                for (int c = lane * 4; c < C; c += 128) {
+                    const float4 z = *reinterpret_cast<const float4*>(row + c);
+                    const float4 w4 = Elem<T>::ld4(lw + c), b4 = Elem<T>::ld4(lb + c);
+                    Elem<T>::st4(out_norm + p * C + c,
+                                 make_float4((z.x - mean) * rstd * w4.x + b4.x, (z.y - mean) * rstd * w4.y + b4.y,
+                                             (z.z - mean) * rstd * w4.z + b4.z, (z.w - mean) * rstd * w4.w + b4.w));
+                }
+            }
+        } else {
+            for (int c = lane * 4; c < C; c += 128) *reinterpret_cast<float4*>(row + c) = Elem<T>::ld4(yp + c);
+            __syncwarp();
+            float mean, rstd;
+            row_stats(row, C, lane, eps, mean, rstd);
+            for (int c = lane * 4; c < C; c += 128) {
+                const float4 v = *reinterpret_cast<const float4*>(row + c);
+                const float4 w4 = Elem<T>::ld4(lw + c), b4 = Elem<T>::ld4(lb + c);
+                float4 n4 = make_float4(round_to<T>((v.x - mean) * rstd * w4.x + b4.x), round_to<T>((v.y - mean) * rstd * w4.y + b4.y),
+                                        round_to<T>((v.z - mean) * rstd * w4.z + b4.z), round_to<T>((v.w - mean) * rstd * w4.w + b4.w));
+                if (mode == 1) {
+                    const float4 b = Elem<T>::ld4(rp + c);
+                    float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (gamma) g = Elem<T>::ld4(gamma + c);
+                    n4 = make_float4(b.x + round_to<T>(n4.x * g.x), b.y + round_to<T>(n4.y * g.y),
+                                     b.z + round_to<T>(n4.z * g.z), b.w + round_to<T>(n4.w * g.w));
+                }
+                Elem<T>::st4(out_sum + p * C + c, n4);
+            }
+        }
+        __syncwarp();  // the row buffer is reused by the warp's next pixel
+    }
+}
+
+// weights: [k*k][C] (tap-major, channels contiguous), tap t = ky * k + kx; zero padding pad_lo before / (k-1-pad_lo) after
+template <typename T>
+__global__ void __launch_bounds__(kLnWarps * 32)
+dwconv_ln_act_kernel(const T* __restrict__ x, const T* __restrict__ wt, const T* __restrict__ bias,
+                     const T* __restrict__ lw, const T* __restrict__ lb, T* __restrict__ out, int N, int H, int W, int C,
+                     int k, int pad_lo, float eps, int act) {
+    extern __shared__ float srow[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* row = srow + (size_t)warp * C;
+    const long long rows = (long long)N * H * W;
+    for (long long p = (long long)blockIdx.x * kLnWarps + warp; p < rows; p += (long long)gridDim.x * kLnWarps) {
+        const int wq = (int)(p % W), hq = (int)((p / W) % H);
+        const long long n = p / ((long long)W * H);
+        for (int c = lane * 4; c < C; c += 128) {
+            float4 acc = bias ? Elem<T>::ld4(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int ky = 0; ky < k; ++ky) {
+                const int yy = hq + ky - pad_lo;
+                if (yy < 0 || yy >= H) continue;
+                for (int kx = 0; kx < k; ++kx) {
+                    const int xx = wq + kx - pad_lo;
+                    if (xx < 0 || xx >= W) continue;
+                    const float4 v = Elem<T>::ld4(x + ((n * H + yy) * W + xx) * C + c);
+                    const float4 w4 = Elem<T>::ld4(wt + (size_t)(ky * k + kx) * C + c);
+                    acc.x = fmaf(v.x, w4.x, acc.x); acc.y = fmaf(v.y, w4.y, acc.y);
+                    acc.z = fmaf(v.z, w4.z, acc.z); acc.w = fmaf(v.w, w4.w, acc.w);
+                }
+            }
+            // (the unfused chain stores the convolution result in T before normalising it)
+            *reinterpret_cast<float4*>(row + c) =
+                make_float4(round_to<T>(acc.x), round_to<T>(acc.y), round_to<T>(acc.z), round_to<T>(acc.w));
+        }
+        __syncwarp();
+        float mean, rstd;
+        row_stats(row, C, lane, eps, mean, rstd);
+        for (int c = lane * 4; c < C; c += 128) {
+            const float4 v = *reinterpret_cast<const float4*>(row + c);
+            const float4 w4 = Elem<T>::ld4(lw + c), b4 = Elem<T>::ld4(lb + c);
+            float4 o = make_float4(round_to<T>((v.x - mean) * rstd * w4.x + b4.x), round_to<T>((v.y - mean) * rstd * w4.y + b4.y),
+                                   round_to<T>((v.z - mean) * rstd * w4.z + b4.z), round_to<T>((v.w - mean) * rstd * w4.w + b4.w));
+            if (act == 1) o = make_float4(gelu_erf(o.x), gelu_erf(o.y), gelu_erf(o.z), gelu_erf(o.w));
+            Elem<T>::st4(out + p * C + c, o);
+        }
+        __syncwarp();
+    }
+}
+
+static unsigned ln_grid(long long rows) {
+    const long long want = (rows + kLnWarps - 1) / kLnWarps;
+    const long long cap = 148ll * 8;  // 8 CTAs of 8 warps per SM: the grid-stride loop takes the rest
+    return (unsigned)(want < cap ? want : cap);
+}
+
+template <typename K>
+static cudaError_t ensure_row_smem(K kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return ensure_max_smem((const void*)kernel, (int)bytes);
+}
+
+cudaError_t launch_ln_join(const void* y, const void* r, const void* gamma, const void* lw, const void* lb, void* out_sum,
+                           void* out_norm, long long rows, int C, float eps, int mode, int dtype, cudaStream_t st) {
+    const size_t smem = (size_t)kLnWarps * C * sizeof(float);
+    cudaError_t e;
+    if (dtype == DCNV3_F32) {
+        if ((e = ensure_row_smem(ln_join_kernel<float>, smem)) != cudaSuccess) return e;
+        ln_join_kernel<float><<<ln_grid(rows), kLnWarps * 32, smem, st>>>(
+            (const float*)y, (const float*)r, (const float*)gamma, (const float*)lw, (const float*)lb, (float*)out_sum,
+            (float*)out_norm, rows, C, eps, mode);
+    } else {
+        using B = __nv_bfloat16;
+        if ((e = ensure_row_smem(ln_join_kernel<B>, smem)) != cudaSuccess) return e;
+        ln_join_kernel<B><<<ln_grid(rows), kLnWarps * 32, smem, st>>>((const B*)y, (const B*)r, (const B*)gamma, (const B*)lw,
+                                                                     (const B*)lb, (B*)out_sum, (B*)out_norm, rows, C, eps, mode);
+    }
+    count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dwconv_ln_act(const void* x, const void* wt, const void* bias, const void* lw, const void* lb, void* out,
+                                 int N, int H, int W, int C, int k, int pad_lo, float eps, int act, int dtype, cudaStream_t st) {
+    const size_t smem = (size_t)kLnWarps * C * sizeof(float);
+    const long long rows = (long long)N * H * W;
+    cudaError_t e;
+    if (dtype == DCNV3_F32) {
+        if ((e = ensure_row_smem(dwconv_ln_act_kernel<float>, smem)) != cudaSuccess) return e;
+        dwconv_ln_act_kernel<float><<<ln_grid(rows), kLnWarps * 32, smem, st>>>(
+            (const float*)x, (const float*)wt, (const float*)bias, (const float*)lw, (const float*)lb, (float*)out, N, H, W, C, k,
+            pad_lo, eps, act);
+    } else {
+        using B = __nv_bfloat16;
+        if ((e = ensure_row_smem(dwconv_ln_act_kernel<B>, smem)) != cudaSuccess) return e;
+        dwconv_ln_act_kernel<B><<<ln_grid(rows), kLnWarps * 32, smem, st>>>((const B*)x, (const B*)wt, (const B*)bias, (const B*)lw,
+                                                                           (const B*)lb, (B*)out, N, H, W, C, k, pad_lo, eps, act);
+    }
+    count_launch(1);
+    return cudaGetLastError();
+}
+
+int max_ln_channels() { return kMaxLnChannels; }
+
+}  // namespace dcnv3

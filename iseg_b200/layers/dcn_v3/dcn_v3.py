@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ... import _cabi
 from .op import dcnv3_op, dcnv3_op_center_scale
 
 LAYER_NORM_EPSILON = 1e-6
@@ -85,8 +86,16 @@ class DeformableConvolutionV3(nn.Module):
         n, h, w, c = inputs.shape
         x_proj = self.input_proj(inputs)  # dcn_v3.py:113
         lo, hi = self._dw_pad
-        x1 = self.dw_conv(F.pad(inputs.permute(0, 3, 1, 2), (lo, hi, lo, hi))).permute(0, 2, 3, 1)  # :115
-        x1 = self.activation(self.dw_conv_norm(x1))  # :116-117
+        k = self.depthwise_kernel_size
+        if (self.activation is F.gelu and self.padding.lower() == "same" and _cabi.fused_layers_usable(inputs)
+                and self.dw_conv.weight.dtype == inputs.dtype):
+            # inference: depthwise conv + LayerNorm + GELU in one pass over the tensor (:115-117)
+            wt = self.dw_conv.weight.detach().permute(2, 3, 0, 1).reshape(k * k, c).contiguous()  # [k*k][C], tap-major
+            x1 = _cabi.dwconv_ln_act(inputs, wt, self.dw_conv.bias, self.dw_conv_norm.weight, self.dw_conv_norm.bias,
+                                     k, lo, LAYER_NORM_EPSILON, gelu=True)
+        else:
+            x1 = self.dw_conv(F.pad(inputs.permute(0, 3, 1, 2), (lo, hi, lo, hi))).permute(0, 2, 3, 1)  # :115
+            x1 = self.activation(self.dw_conv_norm(x1))  # :116-117
         offset = self.offset(x1)  # :118
         mask = self.mask(x1)  # :120
         if not self.fuse_softmax:  # :121-123

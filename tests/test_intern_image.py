@@ -162,3 +162,84 @@ def test_graphed_inference_matches_eager():
     with torch.no_grad():
         a, b = m.blocks[2](f), stage(f)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype, tol", [(torch.float32, 2e-5), (torch.bfloat16, 3e-2)])
+def test_fused_layer_kernels_match_torch(dtype, tol):
+    """dcnv3_dwconv_ln_act and dcnv3_layer_join against the torch operations they replace
+    (reference layers/dcn_v3/dcn_v3.py:115-117, backbones/intern_image/intern_image_layer.py:126-172)."""
+    import torch.nn.functional as F
+    from iseg_b200 import _cabi
+    torch.manual_seed(3)
+    torch.backends.cudnn.allow_tf32 = False
+    n, h, w, c = 2, 13, 17, 72
+    rnd = lambda *s: torch.randn(*s, device="cuda").to(dtype)  # noqa: E731
+    x, r, gamma, lw, lb = rnd(n, h, w, c), rnd(n, h, w, c), rnd(c), rnd(c), rnd(c)
+    eps = 1e-6
+    with torch.no_grad():
+        for k, lo in ((3, 1), (5, 2), (4, 1)):   # (even kernel: Keras pads (k-1)//2 before, k//2 after)
+            wt, bias = rnd(c, 1, k, k) * 0.3, rnd(c)
+            want = F.conv2d(F.pad(x.permute(0, 3, 1, 2), (lo, k - 1 - lo, lo, k - 1 - lo)), wt, bias, groups=c).permute(0, 2, 3, 1)
+            want = F.gelu(F.layer_norm(want, (c,), lw, lb, eps))
+            got = _cabi.dwconv_ln_act(x, wt.permute(2, 3, 0, 1).reshape(k * k, c).contiguous(), bias, lw, lb, k, lo, eps)
+            assert _rel(got, want) <= tol, k
+        z = r + x * gamma
+        s0, n0 = _cabi.layer_join(x, r, gamma, lw, lb, eps, 0)
+        assert _rel(s0, z) <= tol and _rel(n0, F.layer_norm(z, (c,), lw, lb, eps)) <= tol
+        assert _rel(_cabi.layer_join(x, r, None, None, None, eps, 0, want_norm=False)[0], r + x) <= tol
+        assert _rel(_cabi.layer_join(x, r, gamma, lw, lb, eps, 1), r + F.layer_norm(x, (c,), lw, lb, eps) * gamma) <= tol
+        assert _rel(_cabi.layer_join(x, None, None, lw, lb, eps, 2), F.layer_norm(x, (c,), lw, lb, eps)) <= tol
+    with pytest.raises(ValueError):
+        _cabi.layer_join(rnd(4, 6), rnd(4, 6), None, rnd(6), rnd(6), eps, 1)   # channels % 4 != 0
+
+
+@pytest.mark.gpu
+def test_fused_inference_path_matches_unfused_layers():
+    """under torch.no_grad() in eval mode the layers run the one-pass kernels (joins and the
+    DCNv3 layer's depthwise-conv branch); with autograd recording they run the torch operations.  Same numbers for
+    the three layer variants of the reference, with and without layer scale, and for a whole stage."""
+    from iseg_b200 import _cabi
+    from iseg_b200.backbones.intern_image.intern_image import InternImageBlock, InternImageLayer
+    torch.manual_seed(4)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+    def randomise(mod):
+        for name, p in mod.named_parameters():
+            torch.nn.init.normal_(p, std=0.05 if ("offset" in name or "mask" in name) else 0.3)
+        return mod.cuda().eval()
+
+    x = torch.randn(2, 24, 20, 64, device="cuda")
+    variants = [dict(layer_scale=1.0), dict(), dict(use_post_norm=True, layer_scale=1.0),
+                dict(use_res_post_norm=True, center_feature_scale=True, depthwise_kernel_size=5)]
+    for kw in variants:
+        layer = randomise(InternImageLayer(64, 4, **kw))
+        want = layer(x)                       # autograd recording on: torch operations
+        n0 = _cabi.launch_count()
+        with torch.no_grad():
+            got = layer(x)
+        assert _cabi.launch_count() - n0 >= 4  # op + depthwise branch + two joins at least
+        assert _rel(got, want) <= 5e-5, kw
+    for kw in (dict(layer_scale=1.0), dict(use_post_norm=True, layer_scale=1.0)):
+        stage = randomise(InternImageBlock(64, 3, 4, use_downsample=True, **kw))
+        want = stage(x)
+        with torch.no_grad():
+            got = stage(x)
+        assert _rel(got[0], want[0]) <= 1e-4 and _rel(got[1], want[1]) <= 1e-4, kw
+    m = randomise(intern_image_tiny(return_endpoints=True))
+    img = torch.randn(1, 96, 128, 3, device="cuda")
+    want = m(img)
+    with torch.no_grad():
+        got = m(img)
+    assert all(_rel(a, b) <= 5e-4 for a, b in zip(got, want))
+    mb = randomise(intern_image_tiny()).to(torch.bfloat16)
+    imgb = img.to(torch.bfloat16)
+    wantb = mb(imgb)
+    with torch.no_grad():
+        gotb = mb(imgb)
+    assert torch.isfinite(gotb.float()).all() and _rel(gotb, wantb) <= 0.1
