@@ -808,6 +808,39 @@ __device__ __forceinline__ void scatter_walk_batched(int* acc, int* wsum, const 
     }
 }
 
+// Whole-image tiles (the image fits one scatter tile: every InternImage stage from 32x32 down): nobody else
+// contributes to the tile's cells -- no ring, no far landings, no merge launch -- so the CTA that found hot cells
+// recomputes them itself, right after its flush: the landings on hot cells go to the 64-bit side buffer (pass 2 of the
+// redo; the weight counters of pass 1 are still in shared memory), and are then converted and added to what the flush
+// left in grad_x (0, or the blend's direct term).  Leaves the side buffer zero again.
+template <typename T, int TJ>
+__device__ __forceinline__ void redo_own_tile(int* wsum, const T* __restrict__ offset, const T* __restrict__ mask,
+                                              const T* __restrict__ grad_out, T* __restrict__ grad_x, const FarWs& ws,
+                                              const KParams& q, const TileBox& box, int n, int chunk, Range hh, Range hw,
+                                              int eg) {
+    constexpr int PITCH = ScatterShape<TJ>::PITCH;
+    constexpr int WP = ScatterShape<TJ>::WPITCH;
+    redo_walk<T, 2, TJ>(wsum, offset, mask, grad_out, ws, q, box, n, chunk, hh, hw, eg);
+    __threadfence();
+    __syncthreads();
+    const size_t img_pixels = (size_t)q.h * q.w;
+    const double inv_d = ldexp(1.0, -(eg + kWShift - 32));
+    for (int i = threadIdx.x; i < box.bh * (PITCH * kSCell); i += blockDim.x) {
+        const int cy = i / (PITCH * kSCell), r = i - cy * (PITCH * kSCell);
+        const int cx = r / kSCell, ch = r % kSCell, gl = ch / kGC;
+        const int ax = box.bx0 + cx, ay = box.by0 + cy, g = chunk * kSG + gl;
+        if (cx >= box.bw || ax < 0 || ax >= q.w || ay < 0 || ay >= q.h || g >= q.G) continue;
+        if (!cell_is_hot<WP>(wsum, cy, cx, gl)) continue;
+        const size_t cellg = ((size_t)n * img_pixels + (size_t)(ay * q.w + ax)) * q.G + g;
+        const size_t idx = cellg * kGC + ch % kGC;
+        const long long v = (long long)__ldcg(ws.acc64 + idx);
+        // |v| can exceed 2^24: go through double so that the exact total is rounded once
+        Elem<T>::st(grad_x + idx, __fadd_rn(Elem<T>::ld_plain(grad_x + idx), (float)((double)v * inv_d)));
+        ws.acc64[idx] = 0ull;
+        ws.dirty[cellg] = 0;
+    }
+}
+
 #ifdef DCNV3_SCATTER_PROFILE
 // debug build only (tools/scatter_phases.py): per-CTA phase clocks
 __device__ long long* g_scatter_prof = nullptr;
@@ -927,6 +960,7 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
         }
         __syncthreads();
         PROF_MARK(4);
+        if (bg.tiles_x * bg.tiles_y == 1) finalize_workspace(ws, q.n);  // whole-image tile: last kernel of the call
         return;
     }
     for (int item = warp; item < box.bh * segs; item += nwarps) {
@@ -969,7 +1003,12 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
             ws.dirty[cellg] = 1;
         }
     }
-    if (any_hot) {
+    if (bg.tiles_x * bg.tiles_y == 1) {
+        // whole-image tile: hot cells are redone here and this kernel is the last one of the call
+        if (__syncthreads_or(any_hot) && !nonfinite)
+            redo_own_tile<T, TJ>(wsum, offset, mask, grad_out, grad_x, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+        finalize_workspace(ws, q.n);
+    } else if (any_hot) {
         ws.redo[blockIdx.x] = 1;
         ws.hd->any_redo = 1u;  // (benign race: every writer stores the same value)
     }
@@ -984,67 +1023,40 @@ extern "C" int dcnv3_debug_scatter_profile(long long* buf) {
 }
 #endif
 
-// Exact recomputation of the hot cells of one box (see header): pass 1 rebuilds the weight counters,
-// pass 2 adds the landings on hot cells to the 64-bit side buffer.  Exits at once unless the scatter
-// kernel flagged the CTA -- which only adversarial inputs make it do.
-// Launched with a handful of CTAs: unless some scatter CTA raised any_redo they only read that word and leave;
-// otherwise they share the flagged tiles among themselves.
+// Exact recomputation of the hot cells of the flagged boxes of images of more than one scatter tile (whole-image
+// tiles do it inside the scatter kernel, redo_own_tile): pass 1 rebuilds the weight counters, pass 2 adds the
+// landings on hot cells to the 64-bit side buffer, which merge_far_kernel then folds into grad_x.
+// Launched with a handful of CTAs: unless some scatter CTA raised any_redo -- which only adversarial inputs make it
+// do -- they only read that word and leave; otherwise they share the flagged tiles among themselves.
 template <typename T, int TJ>
 __global__ void __launch_bounds__(256)
 redo_hot_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
-                T* __restrict__ grad_x, const FarWs ws, const KParams q, const BwdGeom bg, const int n_tiles,
-                const int is_last) {
+                const FarWs ws, const KParams q, const BwdGeom bg, const int n_tiles) {
     constexpr int WP = ScatterShape<TJ>::WPITCH;
     extern __shared__ __align__(16) int wsum[];  // [box_rows + 1][WP][kSG]
     __shared__ Range s_home_h, s_home_w;
     pdl_launch_dependents();
     pdl_wait();
-    if (ws.hd->any_redo != 0u) {  // (uniform over the grid)
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            if (ws.redo[tile] == 0) continue;  // (uniform per CTA)
-            int b = tile;
-            const int jx = b % bg.tiles_x; b /= bg.tiles_x;
-            const int jy = b % bg.tiles_y; b /= bg.tiles_y;
-            const int chunk = b % bg.chunks;
-            const int n = b / bg.chunks;
-            const TileBox box = make_box(q, bg, jx, jy);
-            __syncthreads();  // the previous tile's counters and ranges are no longer read
-            if (threadIdx.x < 2) tile_ranges(q, bg, jx, jy, s_home_h, s_home_w);
-            for (int i = threadIdx.x; i < (bg.box_rows + 1) * WP * kSG; i += blockDim.x) wsum[i] = 0;
-            __syncthreads();
-            const int eg = 30 - fixed_exponent_raw(ws.img_max[n].go_bits);
-            redo_walk<T, 1, TJ>(wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
-            __syncthreads();
-            redo_walk<T, 2, TJ>(wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
-            __syncthreads();
-            if (threadIdx.x == 0) ws.redo[tile] = 0;
-            if (bg.tiles_x * bg.tiles_y == 1) {  // (otherwise merge_far_kernel folds the side buffer into grad_x)
-                // The tile is the whole image: nobody else contributes to its cells (no ring, no far landings), so
-                // there is no merge launch and this CTA converts its hot cells itself.
-                __threadfence();
-                __syncthreads();
-                constexpr int PITCH = ScatterShape<TJ>::PITCH;
-                const size_t img_pixels = (size_t)q.h * q.w;
-                const double inv_d = ldexp(1.0, -(eg + kWShift - 32));
-                for (int i = threadIdx.x; i < box.bh * (PITCH * kSCell); i += blockDim.x) {
-                    const int cy = i / (PITCH * kSCell), r = i - cy * (PITCH * kSCell);
-                    const int cx = r / kSCell, ch = r % kSCell, gl = ch / kGC;
-                    const int ax = box.bx0 + cx, ay = box.by0 + cy, g = chunk * kSG + gl;
-                    if (cx >= box.bw || ax < 0 || ax >= q.w || ay < 0 || ay >= q.h || g >= q.G) continue;
-                    if (!cell_is_hot<WP>(wsum, cy, cx, gl)) continue;
-                    const size_t cellg = ((size_t)n * img_pixels + (size_t)(ay * q.w + ax)) * q.G + g;
-                    const size_t idx = cellg * kGC + ch % kGC;
-                    const long long v = (long long)__ldcg(ws.acc64 + idx);
-                    // |v| can exceed 2^24: go through double so that the exact total is rounded once
-                    // (added to what the flush left there: 0, or the blend's direct term)
-                    Elem<T>::st(grad_x + idx, __fadd_rn(Elem<T>::ld_plain(grad_x + idx), (float)((double)v * inv_d)));
-                    ws.acc64[idx] = 0ull;
-                    ws.dirty[cellg] = 0;
-                }
-            }
-        }
+    if (ws.hd->any_redo == 0u) return;  // (uniform over the grid)
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (ws.redo[tile] == 0) continue;  // (uniform per CTA)
+        int b = tile;
+        const int jx = b % bg.tiles_x; b /= bg.tiles_x;
+        const int jy = b % bg.tiles_y; b /= bg.tiles_y;
+        const int chunk = b % bg.chunks;
+        const int n = b / bg.chunks;
+        const TileBox box = make_box(q, bg, jx, jy);
+        __syncthreads();  // the previous tile's counters and ranges are no longer read
+        if (threadIdx.x < 2) tile_ranges(q, bg, jx, jy, s_home_h, s_home_w);
+        for (int i = threadIdx.x; i < (bg.box_rows + 1) * WP * kSG; i += blockDim.x) wsum[i] = 0;
+        __syncthreads();
+        const int eg = 30 - fixed_exponent_raw(ws.img_max[n].go_bits);
+        redo_walk<T, 1, TJ>(wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+        __syncthreads();
+        redo_walk<T, 2, TJ>(wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+        __syncthreads();
+        if (threadIdx.x == 0) ws.redo[tile] = 0;
     }
-    if (is_last) finalize_workspace(ws, q.n);
 }
 
 // grad_x += side buffer for the (pixel, group)s flagged in the dirty map; leaves the side buffer and
@@ -1152,9 +1164,10 @@ static cudaError_t launch_scatter(const T* offset, const T* mask, const T* grad_
     e = launch_pdl(kernel, grid, S::THREADS, smem, st, offset, mask, grad_out, grad_x, side_t, ws, q, bg);
     if (e != cudaSuccess) return e;
     if (kt.enabled) cudaEventRecord(kt.ev[2], st);
+    if (redo_is_last) return cudaSuccess;  // whole-image tiles: the scatter kernel redoes its own hot cells and finalises
     const unsigned redo_grid = grid < 32u ? grid : 32u;  // normally they only read one word and leave
     return launch_pdl(redo_hot_kernel<T, TJ>, redo_grid, 256, (size_t)(bg.box_rows + 1) * S::WPITCH * kSG * sizeof(int), st,
-                      offset, mask, grad_out, grad_x, ws, q, bg, (int)grid, (int)redo_is_last);
+                      offset, mask, grad_out, ws, q, bg, (int)grid);
 }
 
 template <typename T, bool STAGED>
@@ -1238,7 +1251,7 @@ static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const v
         if (e != cudaSuccess) return e;
     }
     if (kt.enabled) cudaEventRecord(kt.ev[4], st);
-    count_launch(merge ? 4 : 3);
+    count_launch(merge ? 4 : 2);
     return cudaGetLastError();
 }
 
