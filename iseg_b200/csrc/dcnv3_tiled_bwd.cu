@@ -62,7 +62,8 @@ struct ScatterShape {
     // pitch of the weight counters: one extra column, and odd, so that the 16 pixels of a warp -- they walk
     // down a column of cells -- spread their counters over all banks
     static constexpr int WPITCH = (PITCH + 1) | 1;
-    static constexpr int THREADS = TJ == 32 ? DCNV3_SCATTER_THREADS : 256;
+    static constexpr int THREADS = TJ == 32 ? DCNV3_SCATTER_THREADS : 256;  // batched walk: 16 warps x 128 registers
+    static constexpr int THREADS_PER_TAP = TJ == 32 ? 640 : 256;             // per-tap walk: 20 warps x 96 registers
     static constexpr int MIN_CTAS = TJ == 32 ? 1 : 2;
 };
 
@@ -72,6 +73,7 @@ struct BwdGeom {
     int chunks;            // ceil(G / kSG)
     int ring_lo, ring_hi;  // ring of box cells kept below / above the tile (clipped to the image + zero ring)
     int box_rows;          // rows of the largest box (<= tj + ring_lo + ring_hi)
+    int narrow;            // 1: the ring serves less than |offset| <= 3 (offset_scale > 1): per-tap walk
 };
 
 struct FarWs {
@@ -331,7 +333,7 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
                 oms = __fsub_rn(1.0f, cs);
             }
             // this lane's entries of the transposed side copy (real pixels and real groups only)
-            const bool t_on = kUseSideT<T> && px_l < npx && chunk * C::GQ + g_l < q.G;
+            const bool t_on = kUseSideT<T> && side_t.off != nullptr && px_l < npx && chunk * C::GQ + g_l < q.G;
             size_t t_idx = side_t.index(n, chunk * (C::GQ / 2) + (g_l >> 1), h * q.wo + w, g_l & 1);
             if (STAGED) {
                 cp_async_wait_all();
@@ -605,6 +607,139 @@ __device__ __forceinline__ void redo_walk(int* wsum, const T* __restrict__ offse
     }
 }
 
+// ---- per-tap walk of the scatter kernel (round 1), kept for configurations whose ring cannot serve |offset| <= 3 --
+// With offset_scale 2 (InternImage-L) the 4 / 5-cell ring only covers |offset| <= 1 and a third of the taps leave the
+// box at least partly: they go corner by corner, and beyond the box through 64-bit global atomics.  There the
+// batched walk below loses (its runs are built for taps that are wholly inside; 1643 vs 979 us at 160x160 C160 G10
+// bf16, profiles/r02_scatter_study.md): this loop handles a tap's corners right where its coordinates are, with 20
+// warps to hide the global atomics.  Inputs straight from the reference-layout tensors, two taps ahead.
+// A work item is one block of 16 pixels x 2 groups; blocks are dealt round-robin to the warps, and the
+// blocks of the last, incomplete round are split by taps over the warps that would otherwise idle.
+template <typename T, int MODE, int TJ>
+__device__ __forceinline__ void scatter_walk_per_tap(int* acc, int* wsum, const T* __restrict__ offset,
+                                             const T* __restrict__ mask, const T* __restrict__ grad_out,
+                                             const FarWs& ws, const KParams& q, const TileBox& box, int n, int chunk,
+                                             Range hh, Range hw, int eg) {
+    constexpr int PITCH = ScatterShape<TJ>::PITCH;
+    constexpr int WP = ScatterShape<TJ>::WPITCH;  // pitch of the weight counters
+    constexpr int PXW = 32 / kSG;
+    constexpr int ROWB = PITCH * kSCell * 4;  // bytes between accumulator rows
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g_l = lane % kSG, px_l = lane / kSG;
+    const int g = chunk * kSG + g_l;
+    if (g >= q.G) return;  // phantom group of a trailing chunk (no warp-level synchronisation in this walk)
+    const bool logits = q.flags & DCNV3_FLAG_MASK_LOGITS;
+    const float sg = ldexpf(1.0f, eg);  // G = round(go * 2^eg), |G| < 2^30
+    const size_t img_pixels = (size_t)q.h * q.w;
+    // the lane's slab inside cell 0, pre-rotated: slab bases are 64-byte aligned, so
+    // base + ((c ^ rot) * 4) == (base ^ rot*4) ^ c*4
+    uint32_t acc_s = MODE == 0 ? ((smem_u32(acc) + (uint32_t)g_l * (kGC * 4u)) ^ ((uint32_t)px_l << 2)) : 0u;
+    // the lane's counter of anchor (-1, -1)
+    uint32_t wsum_s = MODE != 2 ? smem_u32(wsum) + (uint32_t)g_l * 4u : 0u;
+    // opaque to the compiler: otherwise it re-derives both from %tid inside the tap loop (S2R latency)
+    asm volatile("" : "+r"(acc_s), "+r"(wsum_s));
+    const int nw = hw.hi - hw.lo, npix = (hh.hi - hh.lo) * nw;
+    const int nblocks = (npix + PXW - 1) / PXW;
+    const int full_rounds = nblocks / nwarps, rest = nblocks - full_rounds * nwarps;
+    const int parts = rest ? min(kTaps, nwarps / rest) : 1;  // warps per block of the last round
+#pragma unroll 1
+    for (int round = 0; round <= full_rounds; ++round) {
+        int blk = round * nwarps + warp, p_lo = 0, p_hi = kTaps;
+        if (round == full_rounds) {
+            if (warp >= rest * parts) break;
+            const int part = warp % parts;
+            blk = round * nwarps + warp / parts;
+            p_lo = part * kTaps / parts;
+            p_hi = (part + 1) * kTaps / parts;
+        }
+        const int pix = blk * PXW + px_l;
+        if (pix >= npix) continue;
+        const int row = pix / nw;
+        const int h = hh.lo + row, w = hw.lo + (pix - row * nw);
+        const size_t pg = (((size_t)n * q.ho + h) * q.wo + w) * q.G + g;
+        const T* offp = offset + pg * 18;
+        const T* mskp = mask + pg * 9;
+        float ox, oy, ml, ox2, oy2, ml2;
+        load_tap_inputs<T>(offp, mskp, p_lo, ox, oy, ml);
+        load_tap_inputs<T>(offp, mskp, min(p_lo + 1, kTaps - 1), ox2, oy2, ml2);
+        int G[16];
+        f2 gf[8];
+        bool have_g = false;
+        if (MODE == 0) load_go<T>(grad_out + pg * kGC, gf);
+        float mx = 0.f, inv_sum = 1.f;
+        if (logits) softmax_stats9<T>(mskp, mx, inv_sum);
+        float ref0, ref1;
+        ref_point(q, h, w, ref0, ref1);
+        const float oms = q.cfs != nullptr ? __fsub_rn(1.0f, Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + pg)) : 1.0f;
+        if (MODE == 0) {  // every tap of a home pixel lands: convert grad_out once, with the whole warp converged
+            fixed_point_go(gf, oms, sg, px_l, G);
+            have_g = true;
+        }
+#pragma unroll 1
+        for (int p = p_lo; p < p_hi; ++p) {
+            const float cxo = ox, cyo = oy, cm = ml;
+            ox = ox2; oy = oy2; ml = ml2;
+            if (p + 2 < kTaps) load_tap_inputs<T>(offp, mskp, p + 2, ox2, oy2, ml2);  // two taps ahead
+            const Axis axx = axis_x_live(q, ref0, p, cxo);
+            const Axis axy = axis_y_live(q, ref1, p, cyo);
+            if (!(axx.alive && axy.alive)) continue;  // a clipped corner pair coincides: contributes exactly 0
+            const int lx = axx.i0 - q.pw - box.bx0;   // corner (y0,x0) relative to the box
+            const int ly = axy.i0 - q.ph - box.by0;
+            const float mm = logits ? expf(cm - mx) * inv_sum : cm;
+            if (mm == 0.f) continue;
+            if (MODE == 0 &&
+                __builtin_expect((unsigned)lx < (unsigned)(box.bw - 1) && (unsigned)ly < (unsigned)(box.bh - 1), 1)) {
+                // all four corners a b c d = (y0,x0) (y1,x0) (y0,x1) (y1,x1) lie in the box
+                const int cell = ly * PITCH + lx;
+                red_shared_add<(WP + 1) * kSG * 4>(wsum_s + (uint32_t)(ly * WP + lx) * (kSG * 4u), weight_units(mm));
+                const int wqa = weight_fixed(axx.d1 * axy.d1 * mm), wqb = weight_fixed(axx.d1 * axy.d0 * mm);
+                const int wqc = weight_fixed(axx.d0 * axy.d1 * mm), wqd = weight_fixed(axx.d0 * axy.d0 * mm);
+                const uint32_t base = acc_s + (uint32_t)cell * (kSCell * 4u);  // rotation bits stay put: cell*128
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const uint32_t a = base ^ (uint32_t)(c << 2);
+                    red_shared_add<0>(a, qmul(G[c], wqa));
+                    red_shared_add<ROWB>(a, qmul(G[c], wqb));
+                    red_shared_add<kSCell * 4>(a, qmul(G[c], wqc));
+                    red_shared_add<ROWB + kSCell * 4>(a, qmul(G[c], wqd));
+                }
+                continue;
+            }
+            // ---- corner by corner: part of the patch leaves the box (or one of the redo passes) ----
+            const bool touches = (unsigned)(lx + 1) <= (unsigned)box.bw && (unsigned)(ly + 1) <= (unsigned)box.bh;
+            if (MODE != 2 && touches)  // some corner lies in the box
+                red_shared_add<(WP + 1) * kSG * 4>(wsum_s + (uint32_t)(ly * WP + lx) * (kSG * 4u), weight_units(mm));
+#pragma unroll 1
+            for (int k = 0; k < (MODE == 1 || (MODE == 2 && !touches) ? 0 : 4); ++k) {
+                const float wf = ((k >> 1) ? axx.d0 : axx.d1) * ((k & 1) ? axy.d0 : axy.d1) * mm;
+                if (wf == 0.f) continue;
+                const int cx = lx + (k >> 1), cy = ly + (k & 1);
+                const int ax = cx + box.bx0, ay = cy + box.by0;  // un-padded image coordinates
+                const bool in_image = ax >= 0 && ax < q.w && ay >= 0 && ay < q.h;
+                const size_t cellg = ((size_t)n * img_pixels + (size_t)ay * q.w + ax) * q.G + g;
+                if ((unsigned)cx < (unsigned)box.bw && (unsigned)cy < (unsigned)box.bh) {
+                    if (MODE == 2) {
+                        if (in_image && cell_is_hot<WP>(wsum, cy, cx, g_l)) {
+                            if (!have_g) {
+                                load_fixed_point_go<T>(grad_out + pg * kGC, oms, sg, px_l, G);
+                                have_g = true;
+                            }
+                            side_add(ws, cellg, G, px_l, wf);
+                        }
+                        continue;
+                    }
+                    const int wq = weight_fixed(wf);
+                    const uint32_t base = acc_s + (uint32_t)(cy * PITCH + cx) * (kSCell * 4u);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) red_shared_add<0>(base ^ (uint32_t)(c << 2), qmul(G[c], wq));
+                } else if (MODE == 0 && in_image) {  // beyond the ring; outside the image the gradient is dropped
+                    side_add(ws, cellg, G, px_l, wf);
+                }
+            }
+        }
+    }
+}
+
 // ---- batched walk of the scatter kernel ---------------------------------------------------------------------
 // Inside a tap the coordinate arithmetic (a dependent chain of ~25 fp32 operations per axis, fed by global loads)
 // and the 64 ATOMS of its four landings alternate, and because every warp of the CTA runs the same instruction
@@ -849,8 +984,8 @@ __device__ long long* g_scatter_prof = nullptr;
 #define PROF_MARK(k) do { } while (0)
 #endif
 
-template <typename T, int TJ, bool BLEND>
-__global__ void __launch_bounds__(ScatterShape<TJ>::THREADS, ScatterShape<TJ>::MIN_CTAS)
+template <typename T, int TJ, bool BLEND, bool PER_TAP>
+__global__ void __launch_bounds__(PER_TAP ? ScatterShape<TJ>::THREADS_PER_TAP : ScatterShape<TJ>::THREADS, ScatterShape<TJ>::MIN_CTAS)
 bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
                    T* __restrict__ grad_x, const SideT<T> side_t, const FarWs ws, const KParams q, const BwdGeom bg) {
     constexpr int PITCH = ScatterShape<TJ>::PITCH;
@@ -868,6 +1003,7 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
     const int n = b / bg.chunks;
     const TileBox box = make_box(q, bg, jx, jy);
 
+    const bool blend = BLEND || (PER_TAP && q.cfs != nullptr);  // (the per-tap instance reads the blend at run time)
     pdl_launch_dependents();
 #ifdef DCNV3_SCATTER_PROFILE
     __shared__ long long s_wmin, s_wmax;
@@ -890,7 +1026,10 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
     const bool nonfinite = bits_nonfinite(go_bits);  // NaN / Inf in this image's grad_out: its grad_x is NaN
     const int eg = 30 - fixed_exponent_raw(go_bits);
     if (!nonfinite) {
-        scatter_walk_batched<T, TJ, DCNV3_SCATTER_BATCH, BLEND>(acc, wsum, offset, mask, grad_out, side_t, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+        if (PER_TAP)
+            scatter_walk_per_tap<T, 0, TJ>(acc, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+        else
+            scatter_walk_batched<T, TJ, DCNV3_SCATTER_BATCH, BLEND>(acc, wsum, offset, mask, grad_out, side_t, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
     }
 #ifdef DCNV3_SCATTER_PROFILE
     if ((threadIdx.x & 31) == 0) { const long long t = clock64(); atomicMin(&s_wmin, t); atomicMax(&s_wmax, t); }
@@ -934,7 +1073,7 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
                 if (row_owned && (unsigned)(ax - box.ux0) < (unsigned)box.tjw) {
                     const int e = ax * (q.G * kGC) + piece * 4;
                     float f0 = (float)v.x * inv_s, f1 = (float)v.y * inv_s, f2_ = (float)v.z * inv_s, f3 = (float)v.w * inv_s;
-                    if (BLEND) {  // the blend's direct path: d x_proj += grad_out * s at the pixel itself
+                    if (blend) {  // the blend's direct path: d x_proj += grad_out * s at the pixel itself
                         const float cs = Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + (grow * q.w + ax) * q.G + g);
                         const float4 g4 = Elem<T>::ld4(grad_out + grow * row_elems + chunk * kSCell + e);
                         f0 = __fadd_rn(f0, __fmul_rn(g4.x, cs)); f1 = __fadd_rn(f1, __fmul_rn(g4.y, cs));
@@ -979,7 +1118,7 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
             const float fill = nonfinite ? qnan : 0.f;
             float f0 = drop ? fill : (float)v.x * inv_s, f1 = drop ? fill : (float)v.y * inv_s;
             float f2_ = drop ? fill : (float)v.z * inv_s, f3 = drop ? fill : (float)v.w * inv_s;
-            if (BLEND) {  // the blend's direct path (hot cells: the redo / merge kernels add to this)
+            if (blend) {  // the blend's direct path (hot cells: the redo / merge kernels add to this)
                 const float cs = Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + gpix * q.G + g);
                 const float4 g4 = Elem<T>::ld4(grad_out + gidx);
                 f0 = __fadd_rn(f0, __fmul_rn(g4.x, cs)); f1 = __fadd_rn(f1, __fmul_rn(g4.y, cs));
@@ -1120,6 +1259,11 @@ static BwdGeom make_bwd_geom(const KParams& q) {
         bg.ring_hi = (int)floorf(d) + 2;
         if ((bg.ring_lo <= kRingLo && bg.ring_hi <= kRingHi) || reach < 1e-3f) break;
     }
+    bg.narrow = 0;
+    {   // did the loop above have to shrink the reach?
+        const float d3 = 4.0f * r;
+        bg.narrow = !((int)ceilf(d3) <= kRingLo && (int)floorf(d3) + 2 <= kRingHi);
+    }
     bg.ring_lo = min(bg.ring_lo, kRingLo);
     bg.ring_hi = min(bg.ring_hi, kRingHi);
     bg.box_rows = 0;
@@ -1157,11 +1301,15 @@ static cudaError_t launch_scatter(const T* offset, const T* mask, const T* grad_
     using S = ScatterShape<TJ>;
     const size_t smem = scatter_smem_bytes<TJ>(bg.box_rows);
     // (two instances: the centre-feature-scale blend costs the plain op nothing)
-    auto kernel = q.cfs != nullptr ? bwd_scatter_kernel<T, TJ, true> : bwd_scatter_kernel<T, TJ, false>;
+    // (instances: with / without the centre-feature-scale blend, so that it costs the plain op nothing; batched walk,
+    //  or the per-tap walk where the ring is narrow -- the blend is read at run time there)
+    auto kernel = bg.narrow ? bwd_scatter_kernel<T, TJ, false, true>
+                            : (q.cfs != nullptr ? bwd_scatter_kernel<T, TJ, true, false> : bwd_scatter_kernel<T, TJ, false, false>);
+    const unsigned threads = bg.narrow ? S::THREADS_PER_TAP : S::THREADS;
     cudaError_t e = ensure_max_smem((const void*)kernel, (int)scatter_smem_bytes<TJ>(S::PITCH));
     if (e != cudaSuccess) return e;
     KernelTiming& kt = kernel_timing();
-    e = launch_pdl(kernel, grid, S::THREADS, smem, st, offset, mask, grad_out, grad_x, side_t, ws, q, bg);
+    e = launch_pdl(kernel, grid, threads, smem, st, offset, mask, grad_out, grad_x, side_t, ws, q, bg);
     if (e != cudaSuccess) return e;
     if (kt.enabled) cudaEventRecord(kt.ev[2], st);
     if (redo_is_last) return cudaSuccess;  // whole-image tiles: the scatter kernel redoes its own hot cells and finalises
@@ -1194,7 +1342,8 @@ static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const v
     SideT<T> side_t;
     {
         const size_t entries = (size_t)q.n * ((q.G + 1) / 2) * kTaps * q.h * q.w * 2;
-        side_t.off = (typename SideT<T>::Pair*)scratch;
+        // (no copy where the per-tap walk runs: it reads the reference-layout tensors)
+        side_t.off = (kUseSideT<T> && !bg.narrow) ? (typename SideT<T>::Pair*)scratch : nullptr;
         side_t.msk = (T*)((char*)scratch + (entries * 2 * sizeof(T) + 255) / 256 * 256);
         side_t.cs = (q.G + 1) / 2;
         side_t.hw = q.h * q.w;
@@ -1261,7 +1410,7 @@ void bwd_tiled_plan(const KParams& q, int dtype, int out[16]) {
     out[8] = bg.tj; out[9] = bg.ring_lo; out[10] = bg.ring_hi; out[11] = bg.box_rows;
     out[12] = (int)((long long)q.n * bg.tiles_x * bg.tiles_y * bg.chunks);
     out[13] = (int)(bg.tj == 32 ? scatter_smem_bytes<32>(bg.box_rows) : scatter_smem_bytes<16>(bg.box_rows));
-    out[14] = bg.tj == 32 ? ScatterShape<32>::THREADS : ScatterShape<16>::THREADS;
+    out[14] = bg.tj == 32 ? (bg.narrow ? ScatterShape<32>::THREADS_PER_TAP : ScatterShape<32>::THREADS) : ScatterShape<16>::THREADS;
     out[15] = bg.tiles_x * bg.tiles_y > 1;
 }
 

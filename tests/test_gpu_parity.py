@@ -583,12 +583,13 @@ def _blend_reference(x, off, m, cs, go, g, gc, offset_scale=1.0, logits=False):
     return out, gx, goff, gm, gs
 
 
-@pytest.mark.parametrize("shape, dtype, logits", [
-    ((2, 40, 40, 4, 16), torch.float32, False),     # several scatter tiles (ring hand-over, merge kernel)
-    ((3, 17, 23, 3, 16), torch.float32, True),      # single tile, odd group count (phantom group), fused soft-max
-    ((2, 64, 48, 8, 16), torch.bfloat16, False),
+@pytest.mark.parametrize("shape, dtype, logits, scale", [
+    ((2, 40, 40, 4, 16), torch.float32, False, 1.0),     # several scatter tiles (ring hand-over, merge kernel)
+    ((3, 17, 23, 3, 16), torch.float32, True, 1.0),      # single tile, odd group count (phantom group), fused soft-max
+    ((2, 64, 48, 8, 16), torch.bfloat16, False, 1.0),
+    ((1, 48, 40, 10, 16), torch.float32, False, 2.0),    # offset_scale 2: narrow ring, the per-tap scatter walk
 ])
-def test_center_scale_blend_fused(ops, shape, dtype, logits):
+def test_center_scale_blend_fused(ops, shape, dtype, logits, scale):
     iseg, cabi = ops
     n, h, w, g, gc = shape
     x, off, m, go = make_inputs(n, h, w, g, gc, sigma=1.5, seed=21)
@@ -601,19 +602,19 @@ def test_center_scale_blend_fused(ops, shape, dtype, logits):
     tx, to, tm, ts = cuda(x, off, m, cs, dtype=dtype)
     for t in (tx, to, tm, ts):
         t.requires_grad_(True)
-    assert cabi.blend_supported(tx, to, (3, 3), (1, 1), (1, 1), (1, 1), g, gc, 1.0)
+    assert cabi.blend_supported(tx, to, (3, 3), (1, 1), (1, 1), (1, 1), g, gc, scale)
     before = cabi.launch_count()
-    out = iseg.dcnv3_op_center_scale(tx, to, tm, ts, [3, 3], [1, 1], "SAME", [1, 1], g, gc, 1.0, mask_is_logits=logits)
+    out = iseg.dcnv3_op_center_scale(tx, to, tm, ts, [3, 3], [1, 1], "SAME", [1, 1], g, gc, scale, mask_is_logits=logits)
     assert cabi.launch_count() - before == 1  # the blend costs no launch of its own
     out.backward(cuda(go, dtype=dtype)[0])
     got = [t.float().cpu().numpy() for t in (out.detach(), tx.grad, to.grad, tm.grad, ts.grad)]
-    ref = _blend_reference(x, off, m, cs, go, g, gc, logits=logits)
+    ref = _blend_reference(x, off, m, cs, go, g, gc, offset_scale=scale, logits=logits)
     tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
     for name, a, b in zip(("out", "grad_x", "grad_offset", "grad_mask", "grad_center_scale"), got, ref):
         assert rel_err(a, b) <= tol, name
     # bitwise reproducible, blend included
     tx.grad = None
-    out2 = iseg.dcnv3_op_center_scale(tx, to, tm, ts, [3, 3], [1, 1], "SAME", [1, 1], g, gc, 1.0, mask_is_logits=logits)
+    out2 = iseg.dcnv3_op_center_scale(tx, to, tm, ts, [3, 3], [1, 1], "SAME", [1, 1], g, gc, scale, mask_is_logits=logits)
     out2.backward(cuda(go, dtype=dtype)[0])
     assert torch.equal(out2, out) and np.array_equal(tx.grad.float().cpu().numpy(), got[1])
 
