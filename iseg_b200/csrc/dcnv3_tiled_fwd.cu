@@ -323,6 +323,12 @@ static TileGeom geom_at(const KParams& q, int dtype, int th, int tw, float reach
 // uses the generic kernels.
 TileGeom make_geom(const KParams& q, int dtype, int th, int tw, float reach, int max_cells) {
     TileGeom tg;
+    {   // 8-row tiles when 16x16 tiles would give fewer than four waves of CTAs (148 SMs x 2): the small InternImage
+        // stages then run 3.5 instead of 1.7 waves (-3 % gather fp32, -3.4 % bf16 step, profiles/r02_ab.md)
+        const int gq = dtype == DCNV3_F32 ? 2 : 4;
+        const long long ctas = (long long)q.n * ((q.G + gq - 1) / gq) * ((q.ho + 15) / 16) * ((q.wo + 15) / 16);
+        if (th == 16 && ctas < 4 * 296) th = 8;
+    }
     for (float r = reach; r >= 1.0f; r *= 0.75f) {
         tg = geom_at(q, dtype, th, tw, r);
         if (tg.bw * tg.bh <= max_cells) return tg;
