@@ -615,7 +615,7 @@ __device__ __forceinline__ void redo_walk(int* wsum, const T* __restrict__ offse
 // warps to hide the global atomics.  Inputs straight from the reference-layout tensors, two taps ahead.
 // A work item is one block of 16 pixels x 2 groups; blocks are dealt round-robin to the warps, and the
 // blocks of the last, incomplete round are split by taps over the warps that would otherwise idle.
-template <typename T, int MODE, int TJ>
+template <typename T, int MODE, int TJ, bool BLEND>
 __device__ __forceinline__ void scatter_walk_per_tap(int* acc, int* wsum, const T* __restrict__ offset,
                                              const T* __restrict__ mask, const T* __restrict__ grad_out,
                                              const FarWs& ws, const KParams& q, const TileBox& box, int n, int chunk,
@@ -670,7 +670,7 @@ __device__ __forceinline__ void scatter_walk_per_tap(int* acc, int* wsum, const 
         if (logits) softmax_stats9<T>(mskp, mx, inv_sum);
         float ref0, ref1;
         ref_point(q, h, w, ref0, ref1);
-        const float oms = q.cfs != nullptr ? __fsub_rn(1.0f, Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + pg)) : 1.0f;
+        const float oms = BLEND ? __fsub_rn(1.0f, Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + pg)) : 1.0f;
         if (MODE == 0) {  // every tap of a home pixel lands: convert grad_out once, with the whole warp converged
             fixed_point_go(gf, oms, sg, px_l, G);
             have_g = true;
@@ -1003,7 +1003,7 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
     const int n = b / bg.chunks;
     const TileBox box = make_box(q, bg, jx, jy);
 
-    const bool blend = BLEND || (PER_TAP && q.cfs != nullptr);  // (the per-tap instance reads the blend at run time)
+    constexpr bool blend = BLEND;
     pdl_launch_dependents();
 #ifdef DCNV3_SCATTER_PROFILE
     __shared__ long long s_wmin, s_wmax;
@@ -1027,7 +1027,7 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
     const int eg = 30 - fixed_exponent_raw(go_bits);
     if (!nonfinite) {
         if (PER_TAP)
-            scatter_walk_per_tap<T, 0, TJ>(acc, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+            scatter_walk_per_tap<T, 0, TJ, BLEND>(acc, wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
         else
             scatter_walk_batched<T, TJ, DCNV3_SCATTER_BATCH, BLEND>(acc, wsum, offset, mask, grad_out, side_t, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
     }
@@ -1053,8 +1053,11 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
     // Can any cell be hot at all?  A cell's bound is the sum of four counters, so it needs one above kBudget / 4.
     // Almost never: then the flush runs without the per-cell test, a warp per box row and with 32-bit indexing.
     int cmax = 0;
-    for (int i = threadIdx.x; i < (bg.box_rows + 1) * WP * kSG; i += blockDim.x) cmax = max(cmax, wsum[i]);
-    if (!__syncthreads_or(cmax > kBudget / 4 || nonfinite)) {
+    if (!PER_TAP)
+        for (int i = threadIdx.x; i < (bg.box_rows + 1) * WP * kSG; i += blockDim.x) cmax = max(cmax, wsum[i]);
+    // (the per-tap instance keeps the round-1 kernel body: at its 96 registers every addition to the kernel -- this
+    //  flush, the in-kernel redo below -- was measured to slow its walk down by 15-30 %, profiles/r02_scatter_study.md)
+    if (!PER_TAP && !__syncthreads_or(cmax > kBudget / 4 || nonfinite)) {
         const int row_elems = q.w * q.G * kGC;                // grad_x elements per image row (< 2^31: tiled_applicable)
         const int npieces = box.bw * QPC;
         for (int cy = warp; cy < box.bh; cy += nwarps) {
@@ -1142,7 +1145,7 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
             ws.dirty[cellg] = 1;
         }
     }
-    if (bg.tiles_x * bg.tiles_y == 1) {
+    if (!PER_TAP && bg.tiles_x * bg.tiles_y == 1) {
         // whole-image tile: hot cells are redone here and this kernel is the last one of the call
         if (__syncthreads_or(any_hot) && !nonfinite)
             redo_own_tile<T, TJ>(wsum, offset, mask, grad_out, grad_x, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
@@ -1162,22 +1165,22 @@ extern "C" int dcnv3_debug_scatter_profile(long long* buf) {
 }
 #endif
 
-// Exact recomputation of the hot cells of the flagged boxes of images of more than one scatter tile (whole-image
-// tiles do it inside the scatter kernel, redo_own_tile): pass 1 rebuilds the weight counters, pass 2 adds the
-// landings on hot cells to the 64-bit side buffer, which merge_far_kernel then folds into grad_x.
+// Exact recomputation of the hot cells of the flagged boxes (whole-image tiles of the batched scatter instance do it
+// inside the scatter kernel, redo_own_tile, and need no launch of this kernel): pass 1 rebuilds the weight counters,
+// pass 2 adds the landings on hot cells to the 64-bit side buffer, which merge_far_kernel then folds into grad_x (or,
+// for a whole-image tile, this CTA itself).
 // Launched with a handful of CTAs: unless some scatter CTA raised any_redo -- which only adversarial inputs make it
 // do -- they only read that word and leave; otherwise they share the flagged tiles among themselves.
 template <typename T, int TJ>
 __global__ void __launch_bounds__(256)
 redo_hot_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const T* __restrict__ grad_out,
-                const FarWs ws, const KParams q, const BwdGeom bg, const int n_tiles) {
+                T* __restrict__ grad_x, const FarWs ws, const KParams q, const BwdGeom bg, const int n_tiles, const int is_last) {
     constexpr int WP = ScatterShape<TJ>::WPITCH;
     extern __shared__ __align__(16) int wsum[];  // [box_rows + 1][WP][kSG]
     __shared__ Range s_home_h, s_home_w;
     pdl_launch_dependents();
     pdl_wait();
-    if (ws.hd->any_redo == 0u) return;  // (uniform over the grid)
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; ws.hd->any_redo != 0u && tile < n_tiles; tile += gridDim.x) {  // (uniform over the grid)
         if (ws.redo[tile] == 0) continue;  // (uniform per CTA)
         int b = tile;
         const int jx = b % bg.tiles_x; b /= bg.tiles_x;
@@ -1192,10 +1195,14 @@ redo_hot_kernel(const T* __restrict__ offset, const T* __restrict__ mask, const 
         const int eg = 30 - fixed_exponent_raw(ws.img_max[n].go_bits);
         redo_walk<T, 1, TJ>(wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
         __syncthreads();
-        redo_walk<T, 2, TJ>(wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+        if (bg.tiles_x * bg.tiles_y == 1)  // whole-image tile of the per-tap instance: pass 2 + conversion (no merge launch)
+            redo_own_tile<T, TJ>(wsum, offset, mask, grad_out, grad_x, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+        else
+            redo_walk<T, 2, TJ>(wsum, offset, mask, grad_out, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
         __syncthreads();
         if (threadIdx.x == 0) ws.redo[tile] = 0;
     }
+    if (is_last) finalize_workspace(ws, q.n);
 }
 
 // grad_x += side buffer for the (pixel, group)s flagged in the dirty map; leaves the side buffer and
@@ -1305,11 +1312,13 @@ static cudaError_t launch_scatter(const T* offset, const T* mask, const T* grad_
     //  or the per-tap walk where the ring is narrow -- the blend is read at run time there)
     //  bf16 always takes the per-tap walk: its per-lane loads touch half as many lines, there is no transposed copy to
     //  read, and the batched walk measured 1 % slower on the InternImage-T step and 17 % slower on InternImage-L)
-    void (*kernel)(const T*, const T*, const T*, T*, SideT<T>, FarWs, KParams, BwdGeom) = bwd_scatter_kernel<T, TJ, false, true>;
+    const bool blend = q.cfs != nullptr;
+    void (*kernel)(const T*, const T*, const T*, T*, SideT<T>, FarWs, KParams, BwdGeom) =
+        blend ? bwd_scatter_kernel<T, TJ, true, true> : bwd_scatter_kernel<T, TJ, false, true>;
     bool per_tap = true;
     if constexpr (sizeof(T) == 4) {
         per_tap = bg.narrow != 0;
-        if (!per_tap) kernel = q.cfs != nullptr ? bwd_scatter_kernel<T, TJ, true, false> : bwd_scatter_kernel<T, TJ, false, false>;
+        if (!per_tap) kernel = blend ? bwd_scatter_kernel<T, TJ, true, false> : bwd_scatter_kernel<T, TJ, false, false>;
     }
     const unsigned threads = per_tap ? S::THREADS_PER_TAP : S::THREADS;
     cudaError_t e = ensure_max_smem((const void*)kernel, (int)scatter_smem_bytes<TJ>(S::PITCH));
@@ -1318,10 +1327,12 @@ static cudaError_t launch_scatter(const T* offset, const T* mask, const T* grad_
     e = launch_pdl(kernel, grid, threads, smem, st, offset, mask, grad_out, grad_x, side_t, ws, q, bg);
     if (e != cudaSuccess) return e;
     if (kt.enabled) cudaEventRecord(kt.ev[2], st);
-    if (redo_is_last) return cudaSuccess;  // whole-image tiles: the scatter kernel redoes its own hot cells and finalises
+    // whole-image tiles of the batched instance: the scatter kernel redoes its own hot cells and finalises the workspace
+    if (redo_is_last && !per_tap) return cudaSuccess;
+    count_launch(1);
     const unsigned redo_grid = grid < 32u ? grid : 32u;  // normally they only read one word and leave
     return launch_pdl(redo_hot_kernel<T, TJ>, redo_grid, 256, (size_t)(bg.box_rows + 1) * S::WPITCH * kSG * sizeof(int), st,
-                      offset, mask, grad_out, ws, q, bg, (int)grid);
+                      offset, mask, grad_out, grad_x, ws, q, bg, (int)grid, (int)redo_is_last);
 }
 
 template <typename T, bool STAGED>
@@ -1406,7 +1417,7 @@ static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const v
         if (e != cudaSuccess) return e;
     }
     if (kt.enabled) cudaEventRecord(kt.ev[4], st);
-    count_launch(merge ? 4 : 2);
+    count_launch(merge ? 3 : 2);  // gather, scatter (+ merge); the redo launch counts itself
     return cudaGetLastError();
 }
 

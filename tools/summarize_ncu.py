@@ -37,10 +37,10 @@ def raw_rows(rep):
     return rows[0], rows[1], rows[2:]
 
 
-def full(rep, dst, shape):
+def full(rep, dst, shape, dtype="f32"):
     hdr, units, rows = raw_rows(rep)
     idx = {h: i for i, h in enumerate(hdr)}
-    md = [f"# ncu --set full --clock-control none, {shape}, fp32, batch 16 (source: {rep})", ""]
+    md = [f"# ncu --set full --clock-control none, {shape}, {dtype}, batch 16 (source: {rep})", ""]
     traffic = {}
     for r in rows:
         name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("dcnv3::", "")
@@ -57,7 +57,7 @@ def full(rep, dst, shape):
             v, u = float(r[idx[m]]), units[idx[m]]
             return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
         short = name.split("<")[0].replace("_kernel", "")
-        traffic[f"f32:{short} {shape}"] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+        traffic[f"{dtype}:{short} {shape}"] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
     open(dst + ".md", "w").write("\n".join(md) + "\n")
     return traffic
 
@@ -91,7 +91,7 @@ def launch_list(path, dst):
 
 if __name__ == "__main__":
     if sys.argv[1] == "full":
-        t = full(sys.argv[2], sys.argv[3], sys.argv[4])
+        t = full(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else "f32")
         tp = "profiles/traffic.json"
         try:
             cur = json.load(open(tp))
