@@ -25,3 +25,16 @@ torch.cuda.synchronize(); print("_cabi.forward: %.1f us"%((time.perf_counter()-t
 t0=time.perf_counter()
 for _ in range(N): _cabi.backward(xd,od,md,go,*cfg)
 torch.cuda.synchronize(); print("_cabi.backward: %.1f us"%((time.perf_counter()-t0)/N*1e6))
+# bare C ABI (raw pointers, prebuilt parameter block): what the library itself costs on the host per call
+import ctypes
+p=_cabi.make_params(xd.shape,(h,w),*cfg[:4],g,16,1.0,_cabi.F32,_cabi.FLAG_WORKSPACE_ZEROED)
+out=torch.empty_like(xd); gx=torch.empty_like(xd); goff=torch.empty_like(od); gm=torch.empty_like(md)
+wsb=int(_cabi.lib.dcnv3_backward_workspace_bytes(ctypes.byref(p))); ws=torch.zeros(wsb,dtype=torch.uint8,device="cuda")
+st=ctypes.c_void_p(torch.cuda.current_stream().cuda_stream); vp=lambda t: ctypes.c_void_p(t.data_ptr())
+fa=[vp(t) for t in (xd,od,md,out)]; ba=[vp(t) for t in (xd,od,md,go,gx,goff,gm,ws)]
+torch.cuda.synchronize(); t0=time.perf_counter()
+for _ in range(N): _cabi.lib.dcnv3_forward(*fa,ctypes.byref(p),st)
+torch.cuda.synchronize(); print("dcnv3_forward (raw pointers): %.1f us"%((time.perf_counter()-t0)/N*1e6))
+t0=time.perf_counter()
+for _ in range(N): _cabi.lib.dcnv3_backward(*ba,wsb,ctypes.byref(p),st)
+torch.cuda.synchronize(); print("dcnv3_backward (raw pointers): %.1f us"%((time.perf_counter()-t0)/N*1e6))
