@@ -153,6 +153,22 @@ int dcnv3_layer_join(const void* y, const void* residual, const void* gamma, con
                      void* out_sum, void* out_norm, int64_t rows, int32_t channels, float eps, int32_t mode, int32_t dtype,
                      void* cuda_stream);
 
+/* ---- sibling gather op: the sampling + aggregation of the reference's deformable multi-head self-attention
+        (layers/deformable_multihead_self_attention.py:102-175 _bilinear_sample, then :233-235), fused:
+            out[n,h,w,hd,:] = sum_p attn[n,h,w,hd,p] * bilinear(value[n,:,:,hd,:], y[n,h,w,hd,p], x[n,h,w,hd,p])
+        value / out / grad_value: [n,h,w,heads*head_channels]; y, x, attn and their gradients: [n,h,w,heads*points];
+        absolute pixel coordinates, neighbour indices clamped to the image, weights from the fractional parts (that
+        function's conventions).  The backward is bitwise reproducible (64-bit fixed-point integer atomics, scale per
+        image); its workspace must be all-zero on entry and is left all-zero (DCNV3_FLAG_WORKSPACE_ZEROED as above). ---- */
+size_t dcnv3_deform_attn_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t heads, int32_t head_channels);
+int dcnv3_deform_attn_forward(const void* value, const void* y, const void* x, const void* attn, void* out, int32_t n,
+                              int32_t h, int32_t w, int32_t heads, int32_t points, int32_t head_channels, int32_t dtype,
+                              void* cuda_stream);
+int dcnv3_deform_attn_backward(const void* value, const void* y, const void* x, const void* attn, const void* grad_out,
+                               void* grad_value, void* grad_y, void* grad_x, void* grad_attn, void* workspace,
+                               size_t workspace_bytes, int32_t n, int32_t h, int32_t w, int32_t heads, int32_t points,
+                               int32_t head_channels, int32_t dtype, uint32_t flags, void* cuda_stream);
+
 /* ---- DLPack entry points: same calls, tensors described by DLManagedTensor (zero copy);
         shapes, dtype, device and contiguity are taken from / checked against the tensors ---- */
 int dcnv3_forward_dlpack(const DLManagedTensor* x, const DLManagedTensor* offset,

@@ -443,6 +443,62 @@ int dcnv3_dwconv_ln_act(const void* x, const void* weight_kkc, const void* bias,
     return DCNV3_OK;
 }
 
+static int check_deform_attn(int32_t n, int32_t h, int32_t w, int32_t heads, int32_t points, int32_t c, int32_t dtype) {
+    if (dtype != DCNV3_F32 && dtype != DCNV3_BF16) return fail(DCNV3_ERR_DTYPE, "dtype %d not supported", dtype);
+    if (n < 0 || h <= 0 || w <= 0 || heads <= 0 || points <= 0 || c <= 0)
+        return fail(DCNV3_ERR_SHAPE, "deform_attn: value [%d,%d,%d,%d*%d], %d points", n, h, w, heads, c, points);
+    if ((long long)h * w * heads * ((long long)c > points ? c : points) >= (1ll << 40))
+        return fail(DCNV3_ERR_SHAPE, "deform_attn: image too large");
+    return 0;
+}
+
+size_t dcnv3_deform_attn_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t heads, int32_t head_channels) {
+    if (n < 0 || h <= 0 || w <= 0 || heads <= 0 || head_channels <= 0) return 0;
+    return (deform_attn_workspace_bytes(n, h, w, heads, head_channels) + 255) / 256 * 256;
+}
+
+int dcnv3_deform_attn_forward(const void* value, const void* y, const void* x, const void* attn, void* out, int32_t n,
+                              int32_t h, int32_t w, int32_t heads, int32_t points, int32_t head_channels, int32_t dtype,
+                              void* cuda_stream) {
+    int rc = check_deform_attn(n, h, w, heads, points, head_channels, dtype);
+    if (rc) return rc;
+    if (n == 0) return DCNV3_OK;
+    const size_t al = (head_channels % 4 == 0) ? (dtype == DCNV3_F32 ? 16 : 8) : (dtype == DCNV3_F32 ? 4 : 2);
+    if ((rc = check_ptr_align(value, "value", al)) || (rc = check_ptr_align(out, "out", al)) || (rc = check_ptr_align(y, "y", 2)) ||
+        (rc = check_ptr_align(x, "x", 2)) || (rc = check_ptr_align(attn, "attn", 2)))
+        return rc;
+    const cudaError_t e = launch_deform_attn_fwd(value, y, x, attn, out, n, h, w, heads, points, head_channels, dtype,
+                                                 (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "dcnv3_deform_attn_forward launch");
+    return DCNV3_OK;
+}
+
+int dcnv3_deform_attn_backward(const void* value, const void* y, const void* x, const void* attn, const void* grad_out,
+                               void* grad_value, void* grad_y, void* grad_x, void* grad_attn, void* workspace,
+                               size_t workspace_bytes, int32_t n, int32_t h, int32_t w, int32_t heads, int32_t points,
+                               int32_t head_channels, int32_t dtype, uint32_t flags, void* cuda_stream) {
+    int rc = check_deform_attn(n, h, w, heads, points, head_channels, dtype);
+    if (rc) return rc;
+    if (n == 0) return DCNV3_OK;
+    if ((rc = check_ptr_align(value, "value", 2)) || (rc = check_ptr_align(y, "y", 2)) || (rc = check_ptr_align(x, "x", 2)) ||
+        (rc = check_ptr_align(attn, "attn", 2)) || (rc = check_ptr_align(grad_out, "grad_out", 2)) ||
+        (rc = check_ptr_align(grad_value, "grad_value", 2)) || (rc = check_ptr_align(grad_y, "grad_y", 2)) ||
+        (rc = check_ptr_align(grad_x, "grad_x", 2)) || (rc = check_ptr_align(grad_attn, "grad_attn", 2)))
+        return rc;
+    const size_t need = dcnv3_deform_attn_workspace_bytes(n, h, w, heads, head_channels);
+    if (workspace == nullptr || workspace_bytes < need)
+        return fail(DCNV3_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+    if ((rc = check_ptr_align(workspace, "workspace", 256))) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    cudaError_t e;
+    if (!(flags & DCNV3_FLAG_WORKSPACE_ZEROED) && (e = cudaMemsetAsync(workspace, 0, need, st)) != cudaSuccess)
+        return cuda_fail(e, "memset(workspace)");
+    e = launch_deform_attn_bwd(value, y, x, attn, grad_out, grad_value, grad_y, grad_x, grad_attn, workspace, n, h, w, heads, points,
+                               head_channels, dtype, st);
+    if (e != cudaSuccess) return cuda_fail(e, "dcnv3_deform_attn_backward launch");
+    return DCNV3_OK;
+}
+
 size_t dcnv3_backward_workspace_bytes(const dcnv3_params* p) {
     if (check(p) != DCNV3_OK) return 0;
     return backward_ws_bytes(p);

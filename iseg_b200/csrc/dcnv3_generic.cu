@@ -315,4 +315,187 @@ cudaError_t launch_bwd_generic(const void* x, const void* offset, const void* ma
                : launch_bwd_generic_t<__nv_bfloat16>(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, q, ws_clean, st);
 }
 
+// =====================================================================================================
+// Sibling gather op: the sampling + aggregation of iSeg's deformable multi-head
+// self-attention, reference layers/deformable_multihead_self_attention.py:102-175 (_bilinear_sample) followed by
+// :233-235 (sum over the points, weighted by the attention weights) -- fused, so that the [N,H,W,heads,P,C]
+// intermediate of the reference never exists:
+//     out[n,h,w,hd,:] = sum_p attn[n,h,w,hd,p] * bilinear(value[n,:,:,hd,:], y[n,h,w,hd,p], x[n,h,w,hd,p])
+// Conventions are that function's, not DCNv3's: absolute pixel coordinates, the four neighbour INDICES clamped to
+// the image (:128-131), the weights taken from the unclamped fractional parts (:133-136: wy1 = y - floor(y)).
+// Same skeleton as the generic DCNv3 kernels: thread per (pixel, head[, 4 channels]) forward; thread per
+// (pixel, head, point) backward with grad_value accumulated in 64-bit fixed point (integer global atomics: bitwise
+// reproducible, scale per image) and converted by fixed_to_float_kernel.
+// =====================================================================================================
+struct DaParams {
+    int n, h, w, heads, points, c;   // c = channels per head
+};
+
+struct DaTap {
+    int y0, x0, y1, x1;              // clamped neighbour indices
+    float wy0, wy1, wx0, wx1;
+};
+__device__ __forceinline__ DaTap da_tap(const DaParams& q, float y, float x) {
+    DaTap t;
+    const float fy = floorf(y), fx = floorf(x);
+    t.wy1 = __fsub_rn(y, fy); t.wx1 = __fsub_rn(x, fx);          // :133-134
+    t.wy0 = __fsub_rn(1.0f, t.wy1); t.wx0 = __fsub_rn(1.0f, t.wx1);  // :135-136
+    // cast to int then clip (:128-131); the float is clamped first so that huge or non-finite coordinates stay defined
+    const float hy = (float)(q.h - 1), hx = (float)(q.w - 1);
+    t.y0 = (int)fminf(fmaxf(fy, 0.f), hy); t.y1 = (int)fminf(fmaxf(fy + 1.0f, 0.f), hy);
+    t.x0 = (int)fminf(fmaxf(fx, 0.f), hx); t.x1 = (int)fminf(fmaxf(fx + 1.0f, 0.f), hx);
+    return t;
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+deform_attn_fwd_kernel(const T* __restrict__ value, const T* __restrict__ ys, const T* __restrict__ xs,
+                       const T* __restrict__ attn, T* __restrict__ out, const DaParams q) {
+    const int cpt = q.c / VEC;
+    const size_t total = (size_t)q.n * q.h * q.w * q.heads * cpt;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cq = (int)(idx % cpt) * VEC;
+    const size_t ph = idx / cpt;                      // (pixel, head)
+    const int hd = (int)(ph % q.heads);
+    const size_t n = ph / ((size_t)q.heads * q.w * q.h);
+    const size_t row = (size_t)q.w * q.heads * q.c, img = (size_t)q.h * row;
+    const T* vbase = value + n * img + (size_t)hd * q.c + cq;
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    for (int p = 0; p < q.points; ++p) {
+        const size_t pi = ph * q.points + p;
+        const DaTap t = da_tap(q, Elem<T>::ld(ys + pi), Elem<T>::ld(xs + pi));
+        const float a = Elem<T>::ld(attn + pi);
+        const float w00 = __fmul_rn(t.wy0, t.wx0), w01 = __fmul_rn(t.wy0, t.wx1);   // :162-165
+        const float w10 = __fmul_rn(t.wy1, t.wx0), w11 = __fmul_rn(t.wy1, t.wx1);
+        const T* p00 = vbase + (size_t)t.y0 * row + (size_t)t.x0 * q.heads * q.c;
+        const T* p01 = vbase + (size_t)t.y0 * row + (size_t)t.x1 * q.heads * q.c;
+        const T* p10 = vbase + (size_t)t.y1 * row + (size_t)t.x0 * q.heads * q.c;
+        const T* p11 = vbase + (size_t)t.y1 * row + (size_t)t.x1 * q.heads * q.c;
+        float v00[VEC], v01[VEC], v10[VEC], v11[VEC];
+        if (VEC == 4) {
+            const float4 a4 = Elem<T>::ld4(p00), b4 = Elem<T>::ld4(p01), c4 = Elem<T>::ld4(p10), d4 = Elem<T>::ld4(p11);
+            v00[0] = a4.x; v00[1] = a4.y; v00[2] = a4.z; v00[3] = a4.w;
+            v01[0] = b4.x; v01[1] = b4.y; v01[2] = b4.z; v01[3] = b4.w;
+            v10[0] = c4.x; v10[1] = c4.y; v10[2] = c4.z; v10[3] = c4.w;
+            v11[0] = d4.x; v11[1] = d4.y; v11[2] = d4.z; v11[3] = d4.w;
+        } else {
+            v00[0] = Elem<T>::ld(p00); v01[0] = Elem<T>::ld(p01); v10[0] = Elem<T>::ld(p10); v11[0] = Elem<T>::ld(p11);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            // :167 (left to right), then x attention weight and the sum over the points (:234-235)
+            const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w00, v00[v]), __fmul_rn(w01, v01[v])), __fmul_rn(w10, v10[v])),
+                                      __fmul_rn(w11, v11[v]));
+            acc[v] = __fadd_rn(acc[v], __fmul_rn(s, a));
+        }
+    }
+    T* o = out + ph * q.c + cq;
+    if (VEC == 4) Elem<T>::st4(o, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    else Elem<T>::st(o, acc[0]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+deform_attn_bwd_kernel(const T* __restrict__ value, const T* __restrict__ ys, const T* __restrict__ xs,
+                       const T* __restrict__ attn, const T* __restrict__ grad_out, T* __restrict__ grad_y,
+                       T* __restrict__ grad_x, T* __restrict__ grad_attn, const ImgMax* __restrict__ img_max,
+                       unsigned long long* __restrict__ acc64, const DaParams q) {
+    const size_t total = (size_t)q.n * q.h * q.w * q.heads * q.points;
+    const size_t pi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= total) return;
+    const size_t ph = pi / q.points;
+    const int hd = (int)(ph % q.heads);
+    const size_t n = ph / ((size_t)q.heads * q.w * q.h);
+    const int e = fixed_exponent(img_max[n], false);   // the image's own scale: max|grad_out| * max|attn|
+    const size_t row = (size_t)q.w * q.heads * q.c, img = (size_t)q.h * row;
+    const DaTap t = da_tap(q, Elem<T>::ld(ys + pi), Elem<T>::ld(xs + pi));
+    const float a = Elem<T>::ld(attn + pi);
+    const float w00 = __fmul_rn(t.wy0, t.wx0), w01 = __fmul_rn(t.wy0, t.wx1);
+    const float w10 = __fmul_rn(t.wy1, t.wx0), w11 = __fmul_rn(t.wy1, t.wx1);
+    const size_t o00 = n * img + (size_t)t.y0 * row + ((size_t)t.x0 * q.heads + hd) * q.c;
+    const size_t o01 = n * img + (size_t)t.y0 * row + ((size_t)t.x1 * q.heads + hd) * q.c;
+    const size_t o10 = n * img + (size_t)t.y1 * row + ((size_t)t.x0 * q.heads + hd) * q.c;
+    const size_t o11 = n * img + (size_t)t.y1 * row + ((size_t)t.x1 * q.heads + hd) * q.c;
+    const T* go = grad_out + ph * q.c;
+    float s = 0.f, gy = 0.f, gx = 0.f;
+    for (int c = 0; c < q.c; ++c) {
+        const float g = Elem<T>::ld(go + c);
+        const float v00 = Elem<T>::ld(value + o00 + c), v01 = Elem<T>::ld(value + o01 + c);
+        const float v10 = Elem<T>::ld(value + o10 + c), v11 = Elem<T>::ld(value + o11 + c);
+        s += g * (w00 * v00 + w01 * v01 + w10 * v10 + w11 * v11);
+        gy += g * ((v10 - v00) * t.wx0 + (v11 - v01) * t.wx1);   // d/dy: wy1 = y - floor(y), wy0 = 1 - wy1
+        gx += g * ((v01 - v00) * t.wy0 + (v11 - v10) * t.wy1);
+        const float ga = g * a;
+        atomicAdd(acc64 + o00 + c, (unsigned long long)to_fixed(ga * w00, e));
+        atomicAdd(acc64 + o01 + c, (unsigned long long)to_fixed(ga * w01, e));
+        atomicAdd(acc64 + o10 + c, (unsigned long long)to_fixed(ga * w10, e));
+        atomicAdd(acc64 + o11 + c, (unsigned long long)to_fixed(ga * w11, e));
+    }
+    Elem<T>::st(grad_attn + pi, s);
+    Elem<T>::st(grad_y + pi, a * gy);
+    Elem<T>::st(grad_x + pi, a * gx);
+}
+
+size_t deform_attn_workspace_bytes(int n, int h, int w, int heads, int c) {
+    return sizeof(WsHeader) + img_max_bytes(n) + sizeof(long long) * (size_t)n * h * w * heads * c;
+}
+
+template <typename T>
+static cudaError_t launch_deform_attn_fwd_t(const void* value, const void* ys, const void* xs, const void* attn, void* out,
+                                            const DaParams& q, cudaStream_t st) {
+    const size_t ph = (size_t)q.n * q.h * q.w * q.heads;
+    if (ph == 0) return cudaSuccess;
+    if (q.c % 4 == 0)
+        deform_attn_fwd_kernel<T, 4><<<blocks_for(ph * (q.c / 4), 256), 256, 0, st>>>((const T*)value, (const T*)ys, (const T*)xs,
+                                                                                    (const T*)attn, (T*)out, q);
+    else
+        deform_attn_fwd_kernel<T, 1><<<blocks_for(ph * q.c, 256), 256, 0, st>>>((const T*)value, (const T*)ys, (const T*)xs,
+                                                                              (const T*)attn, (T*)out, q);
+    count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_deform_attn_fwd(const void* value, const void* ys, const void* xs, const void* attn, void* out, int n, int h,
+                                   int w, int heads, int points, int c, int dtype, cudaStream_t st) {
+    const DaParams q = {n, h, w, heads, points, c};
+    return dtype == DCNV3_F32 ? launch_deform_attn_fwd_t<float>(value, ys, xs, attn, out, q, st)
+                              : launch_deform_attn_fwd_t<__nv_bfloat16>(value, ys, xs, attn, out, q, st);
+}
+
+template <typename T>
+static cudaError_t launch_deform_attn_bwd_t(const void* value, const void* ys, const void* xs, const void* attn,
+                                            const void* grad_out, void* grad_value, void* grad_y, void* grad_x, void* grad_attn,
+                                            void* ws, const DaParams& q, cudaStream_t st) {
+    const size_t n_v = (size_t)q.n * q.h * q.w * q.heads * q.c, n_p = (size_t)q.n * q.h * q.w * q.heads * q.points;
+    if (n_v == 0) return cudaSuccess;
+    const size_t prefix = sizeof(WsHeader) + img_max_bytes(q.n);
+    ImgMax* img_max = (ImgMax*)((char*)ws + sizeof(WsHeader));
+    unsigned long long* acc = (unsigned long long*)((char*)ws + prefix);
+    const size_t per_image = n_v / q.n, pts_per_image = n_p / q.n;
+    const unsigned nb = (unsigned)max((size_t)1, min((size_t)148 * 8 / q.n + 1, (per_image + 255) / 256));
+    // max |grad_out| and max |attn| per image -> the image's fixed-point scale
+    amax_kernel<T><<<dim3(nb, min(q.n, 65535)), 256, 0, st>>>((const T*)grad_out, per_image, (const T*)attn, pts_per_image, img_max, q.n);
+    if (n_p > 0)
+        deform_attn_bwd_kernel<T><<<blocks_for(n_p, 128), 128, 0, st>>>((const T*)value, (const T*)ys, (const T*)xs, (const T*)attn,
+                                                                        (const T*)grad_out, (T*)grad_y, (T*)grad_x, (T*)grad_attn,
+                                                                        img_max, acc, q);
+    const unsigned nb2 = (unsigned)max((size_t)1, min((size_t)148 * 16 / q.n + 1, (per_image + 255) / 256));
+    fixed_to_float_kernel<T><<<dim3(nb2, min(q.n, 65535)), 256, 0, st>>>((long long*)acc, img_max, (T*)grad_value, per_image, 0u, q.n);
+    count_launch(3);
+    cudaError_t err = cudaMemsetAsync(ws, 0, prefix, st);  // leave the workspace all-zero
+    return err != cudaSuccess ? err : cudaGetLastError();
+}
+
+cudaError_t launch_deform_attn_bwd(const void* value, const void* ys, const void* xs, const void* attn, const void* grad_out,
+                                   void* grad_value, void* grad_y, void* grad_x, void* grad_attn, void* ws, int n, int h, int w,
+                                   int heads, int points, int c, int dtype, cudaStream_t st) {
+    const DaParams q = {n, h, w, heads, points, c};
+    return dtype == DCNV3_F32
+               ? launch_deform_attn_bwd_t<float>(value, ys, xs, attn, grad_out, grad_value, grad_y, grad_x, grad_attn, ws, q, st)
+               : launch_deform_attn_bwd_t<__nv_bfloat16>(value, ys, xs, attn, grad_out, grad_value, grad_y, grad_x, grad_attn, ws, q, st);
+}
+
 }  // namespace dcnv3

@@ -47,4 +47,12 @@ cudaError_t launch_ln_join(const void* y, const void* r, const void* gamma, cons
 cudaError_t launch_dwconv_ln_act(const void* x, const void* wt, const void* bias, const void* lw, const void* lb, void* out,
                                  int N, int H, int W, int C, int k, int pad_lo, float eps, int act, int dtype, cudaStream_t st);
 
+// sibling gather op (dcnv3_generic.cu): sampling + aggregation of iSeg's deformable multi-head self-attention
+size_t deform_attn_workspace_bytes(int n, int h, int w, int heads, int c);
+cudaError_t launch_deform_attn_fwd(const void* value, const void* ys, const void* xs, const void* attn, void* out, int n, int h,
+                                   int w, int heads, int points, int c, int dtype, cudaStream_t st);
+cudaError_t launch_deform_attn_bwd(const void* value, const void* ys, const void* xs, const void* attn, const void* grad_out,
+                                   void* grad_value, void* grad_y, void* grad_x, void* grad_attn, void* ws, int n, int h, int w,
+                                   int heads, int points, int c, int dtype, cudaStream_t st);
+
 }  // namespace dcnv3

@@ -114,3 +114,64 @@ def run_op(x, offset, mask, kernel_size=(3, 3), strides=(1, 1), padding="SAME",
         return out.detach().numpy()
     out.backward(torch.from_numpy(np.ascontiguousarray(grad_out)))
     return (out.detach().numpy(), tx.grad.numpy(), to.grad.numpy(), tm.grad.numpy())
+
+
+# ---- sibling op: the sampler of the reference's deformable multi-head self-attention --------
+_loaded_dmsa = None
+
+
+def load_deform_attn():
+    """The reference's DeformableMultiHeadSelfAttentionLayer class, loaded from
+    /root/reference/layers/deformable_multihead_self_attention.py over the shim.  The helpers that file imports from
+    the rest of the library (NaN scrubbing, check_numerics, the Keras-3 switch) are stand-ins: `_bilinear_sample`
+    (:102-175), the only method used, touches none of them."""
+    global _loaded_dmsa
+    if _loaded_dmsa is not None:
+        return _loaded_dmsa
+    ref = load()
+    tf = ref.tf
+    import torch
+
+    # primitives only this file needs
+    if not hasattr(tf, "broadcast_to"):
+        tf.broadcast_to = lambda x, shape, name=None: tf.convert_to_tensor(torch.broadcast_to(x, tuple(int(v) for v in shape)))
+    if not hasattr(tf, "gather_nd"):
+        tf.gather_nd = tf.raw_ops.GatherNd
+    keras = types.ModuleType("keras")
+    keras.backend = types.SimpleNamespace(epsilon=lambda: 1e-7)
+    keras.layers = tf.keras.layers
+    sys.modules.setdefault("keras", keras)
+    iseg = sys.modules["iseg"]
+    iseg.check_numerics = lambda x, *a, **k: x
+    ou = types.ModuleType("iseg.utils.op_utils")
+    ou.replace_nan_or_inf = lambda x, *a, **k: x
+    ou.safed_softmax = lambda x, *a, **k: tf.nn.softmax(x)
+    sys.modules["iseg.utils.op_utils"] = ou
+    vu = types.ModuleType("iseg.utils.version_utils")
+    vu.is_keras3 = lambda: True
+    sys.modules["iseg.utils.version_utils"] = vu
+    mod = _load_file("iseg.layers.deformable_multihead_self_attention",
+                     os.path.join(REFERENCE_ROOT, "layers", "deformable_multihead_self_attention.py"))
+    _loaded_dmsa = mod.DeformableMultiHeadSelfAttentionLayer
+    return _loaded_dmsa
+
+
+def run_deform_attn(value, y, x, attn, grad_out=None):
+    """Reference `_bilinear_sample(value, y, x)` (:102-175) followed by the two statements that aggregate it
+    (:233-235: `tf.reduce_sum(sampled * tf.expand_dims(attn, -1), axis=-2)`).  Returns out, or (out, grad_value, grad_y,
+    grad_x, grad_attn) when grad_out is given (torch autograd through that graph, standing in for TF autodiff)."""
+    import numpy as np
+    import torch
+
+    cls = load_deform_attn()
+    tf = load().tf
+    tv, ty, tx, ta = (tf.convert_to_tensor(torch.from_numpy(np.ascontiguousarray(a))) for a in (value, y, x, attn))
+    if grad_out is not None:
+        for t in (tv, ty, tx, ta):
+            t.requires_grad_(True)
+    sampled = cls._bilinear_sample(None, tv, ty, tx)                       # [N,H,W,heads,P,C]
+    out = tf.reduce_sum(sampled * tf.expand_dims(ta, axis=-1), axis=-2)    # :233-235
+    if grad_out is None:
+        return out.detach().numpy()
+    out.backward(torch.from_numpy(np.ascontiguousarray(grad_out)))
+    return (out.detach().numpy(), tv.grad.numpy(), ty.grad.numpy(), tx.grad.numpy(), ta.grad.numpy())

@@ -231,6 +231,33 @@ def make_sliding_indices():
     json.dump(cases, open(os.path.join(OUT, "sliding_indices.json"), "w"), indent=0, sort_keys=True)
 
 
+# sibling op: the sampler of the reference's deformable multi-head self-attention.
+# name: (N, H, W, heads, points, C_head, how far outside the image the coordinates may lie, dtype, seed)
+DMSA_CASES = {
+    "inside_9x11_h3p4c8": (2, 9, 11, 3, 4, 8, 0.0, "f4", 20),     # what the layer produces: clipped to the image (:229-230)
+    "border_7x9_h2p5c5_f64": (1, 7, 9, 2, 5, 5, 2.5, "f8", 21),   # beyond the border: clamped neighbour indices (:128-131)
+    "border_12x10_h4p4c16": (2, 12, 10, 4, 4, 16, 3.0, "f4", 22),
+    "tiny_1x1_h1p2c4": (1, 1, 1, 1, 2, 4, 1.0, "f4", 23),
+}
+
+
+def make_dmsa_case(name, spec):
+    n, h, w, heads, p, c, beyond, dt, seed = spec
+    rng = np.random.default_rng(seed)
+    dtype = np.float64 if dt == "f8" else np.float32
+    value = rng.standard_normal((n, h, w, heads, c)).astype(dtype)
+    y = rng.uniform(-beyond, h - 1 + beyond, (n, h, w, heads, p)).astype(dtype)
+    x = rng.uniform(-beyond, w - 1 + beyond, (n, h, w, heads, p)).astype(dtype)
+    y.reshape(-1)[::7] = np.round(y.reshape(-1)[::7])  # exact integers: floor(y) == y, weight 0 on the upper neighbour
+    z = rng.standard_normal((n, h, w, heads, p))
+    e = np.exp(z - z.max(-1, keepdims=True))
+    attn = (e / e.sum(-1, keepdims=True)).astype(dtype)
+    grad_out = rng.standard_normal((n, h, w, heads, c)).astype(dtype)
+    out, gv, gy, gx, ga = ref_runner.run_deform_attn(value, y, x, attn, grad_out)
+    np.savez_compressed(os.path.join(OUT, f"dmsa_{name}.npz"), value=value, y=y, x=x, attn=attn, grad_out=grad_out, out=out,
+                        grad_value=gv, grad_y=gy, grad_x=gx, grad_attn=ga)
+
+
 if __name__ == "__main__":
     assert ref_runner.available(), "needs /root/reference"
     for nm, sp in OP_CASES.items():
@@ -242,4 +269,7 @@ if __name__ == "__main__":
     make_kats()
     make_layer_case()
     make_sliding_indices()
+    for nm, sp in DMSA_CASES.items():
+        make_dmsa_case(nm, sp)
+        print("wrote dmsa", nm)
     print("done")

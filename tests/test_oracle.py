@@ -1,5 +1,8 @@
 """The oracle against the golden vectors (outputs of the reference's own source, see
 tests/golden/make_golden.py), and the three restatements against each other.  CPU only."""
+import glob
+import os
+
 import numpy as np
 import pytest
 
@@ -142,3 +145,32 @@ def test_reference_rejects_bad_padding():
         ref.dcnv3_op(tx, to, tm, [3, 3], [1, 1], 1, [1, 1], 1, 4, 1.0)
     with pytest.raises(ValueError):
         ref.dcnv3_op(tx, to, tm, [3, 3], [1, 1], "full", [1, 1], 1, 4, 1.0)
+
+
+# ---- sibling op: deformable-attention sampler ---------------------------------------------
+DMSA = sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(GOLDEN, "dmsa_*.npz")))
+
+
+@pytest.mark.parametrize("name", DMSA)
+def test_deform_attn_oracle_matches_reference_fixtures(name):
+    """oracle/deform_attn_oracle.py against what the reference's own `_bilinear_sample` (+ the two aggregation
+    statements after it) produced: forward to the last bit or two, gradients to rounding (the fixture's scatter runs in the tensor
+    dtype, the oracle's in float64)."""
+    from oracle import deform_attn_oracle as D
+    z = np.load(os.path.join(GOLDEN, f"dmsa_{name}.npz"))
+    out = D.forward(z["value"], z["y"], z["x"], z["attn"])
+    # (same products and sums as the reference; only the order inside reduce_sum over the points is the library's)
+    assert out.dtype == z["out"].dtype and rel_err(out, z["out"]) <= (1e-15 if out.dtype == np.float64 else 2e-7)
+    tol = 1e-13 if out.dtype == np.float64 else 2e-6
+    for got, key in zip(D.backward(z["value"], z["y"], z["x"], z["attn"], z["grad_out"]),
+                        ("grad_value", "grad_y", "grad_x", "grad_attn")):
+        assert rel_err(got, z[key]) <= tol, key
+
+
+@pytest.mark.needs_reference
+def test_deform_attn_fixture_regenerates():
+    from oracle import ref_runner
+    z = np.load(os.path.join(GOLDEN, "dmsa_border_7x9_h2p5c5_f64.npz"))
+    res = ref_runner.run_deform_attn(z["value"], z["y"], z["x"], z["attn"], z["grad_out"])
+    for got, key in zip(res, ("out", "grad_value", "grad_y", "grad_x", "grad_attn")):
+        assert np.array_equal(got, z[key]), key
