@@ -410,7 +410,7 @@ def run_ours(args, rank, world, local_rank):
                     for name, v in zip(("bwd_gather", "bwd_scatter", "bwd_redo_hot", "bwd_merge_far"), ms4):
                         # whole-image scatter tiles (<= 32x32): no merge launch, and no redo launch in fp32
                         if (name in ("bwd_gather", "bwd_scatter") or max(l.shape[0], l.shape[1]) > 32
-                                or (name == "bwd_redo_hot" and v > 1e-3)):
+                                or (name == "bwd_redo_hot" and dtype == "bf16")):
                             classes.setdefault((name,) + l.shape, []).append(float(v))
             cabi.check(lib.dcnv3_set_kernel_timing(0))
             table = []
