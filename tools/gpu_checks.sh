@@ -11,6 +11,8 @@ OFFSET_SCALE=2 run compute-sanitizer --tool memcheck python tools/prof_one.py 40
 for s in "49 97 64 4 2 f32" "16 16 64 4 3 f32" "40 33 64 4 2 bf16"; do
   run compute-sanitizer --tool racecheck python tools/prof_one.py $s 1
 done
+echo "== compute-sanitizer --tool memcheck pytest tests/test_gpu_deform_attn.py -k golden" >> $out
+compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_deform_attn.py -q -k golden 2>&1 | grep -E "ERROR SUMMARY|passed|failed" | tail -2 >> $out
 echo "== fuzz" >> $out
 timeout $((secs + 120)) python tools/fuzz_gpu.py $secs 11 2>&1 | tail -3 >> $out
 cat $out
