@@ -169,6 +169,21 @@ int dcnv3_deform_attn_backward(const void* value, const void* y, const void* x, 
                                size_t workspace_bytes, int32_t n, int32_t h, int32_t w, int32_t heads, int32_t points,
                                int32_t head_channels, int32_t dtype, uint32_t flags, void* cuda_stream);
 
+/* ---- sibling gather op: the sampling stage of the reference's DCNv2 (layers/dcn_v2.py:137-247, between the offset
+        convolution and the contraction with the kernel):
+            out[n,i,j,k,:] = mask[n,i,j,k] * bilinear(zero-padded x[n], i + ph + py_k + oy, j + pw + px_k + ox)
+        x / grad_x: [n,h,w,channels]; offsets: [n,h,w,kh*kw*2] ((oy, ox) per tap, the first 2*kh*kw channels of the
+        offset convolution, :144-146); mask: [n,h,w,kh*kw] (after the sigmoid, :148); out / grad_out: [n,h,w,kh*kw*channels]
+        (the `map_all` of :247).  Tap order, clipping of indices and coordinate to [0, h+1] x [0, w+1] and the weights from
+        the clipped values are that function's.  Odd kernels 3..15.  Deterministic backward, workspace as above. ---- */
+size_t dcnv3_dcnv2_sample_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t channels);
+int dcnv3_dcnv2_sample_forward(const void* x, const void* offsets, const void* mask, void* out, int32_t n, int32_t h, int32_t w,
+                               int32_t channels, int32_t kh, int32_t kw, int32_t dtype, void* cuda_stream);
+int dcnv3_dcnv2_sample_backward(const void* x, const void* offsets, const void* mask, const void* grad_out, void* grad_x,
+                                void* grad_offsets, void* grad_mask, void* workspace, size_t workspace_bytes, int32_t n,
+                                int32_t h, int32_t w, int32_t channels, int32_t kh, int32_t kw, int32_t dtype, uint32_t flags,
+                                void* cuda_stream);
+
 /* ---- DLPack entry points: same calls, tensors described by DLManagedTensor (zero copy);
         shapes, dtype, device and contiguity are taken from / checked against the tensors ---- */
 int dcnv3_forward_dlpack(const DLManagedTensor* x, const DLManagedTensor* offset,

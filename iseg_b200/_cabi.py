@@ -56,6 +56,10 @@ def _load():
     lib.dcnv3_backward_workspace_zero_bytes.restype = ctypes.c_size_t
     lib.dcnv3_backward.argtypes = [vp] * 8 + [ctypes.c_size_t, pp, vp]
     lib.dcnv3_blend_supported.argtypes = [pp]
+    lib.dcnv3_dcnv2_sample_workspace_bytes.argtypes = [ci] * 4
+    lib.dcnv3_dcnv2_sample_workspace_bytes.restype = ctypes.c_size_t
+    lib.dcnv3_dcnv2_sample_forward.argtypes = [vp] * 4 + [ci] * 7 + [vp]
+    lib.dcnv3_dcnv2_sample_backward.argtypes = [vp] * 8 + [ctypes.c_size_t] + [ci] * 7 + [cu, vp]
     lib.dcnv3_deform_attn_workspace_bytes.argtypes = [ci] * 5
     lib.dcnv3_deform_attn_workspace_bytes.restype = ctypes.c_size_t
     lib.dcnv3_deform_attn_forward.argtypes = [vp] * 5 + [ci] * 7 + [vp]

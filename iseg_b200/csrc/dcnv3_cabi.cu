@@ -499,6 +499,58 @@ int dcnv3_deform_attn_backward(const void* value, const void* y, const void* x, 
     return DCNV3_OK;
 }
 
+static int check_dcnv2(int32_t n, int32_t h, int32_t w, int32_t c, int32_t kh, int32_t kw, int32_t dtype) {
+    if (dtype != DCNV3_F32 && dtype != DCNV3_BF16) return fail(DCNV3_ERR_DTYPE, "dtype %d not supported", dtype);
+    if (n < 0 || h <= 0 || w <= 0 || c <= 0 || kh < 3 || kw < 3 || kh % 2 == 0 || kw % 2 == 0 || kh > 15 || kw > 15)
+        return fail(DCNV3_ERR_SHAPE, "dcnv2_sample: x [%d,%d,%d,%d], kernel %dx%d (odd, 3..15: the clip range of "
+                                     "layers/dcn_v2.py:165-177 lies inside the padded image only then)", n, h, w, c, kh, kw);
+    if ((long long)h * w * c * kh * kw >= (1ll << 40)) return fail(DCNV3_ERR_SHAPE, "dcnv2_sample: image too large");
+    return 0;
+}
+
+size_t dcnv3_dcnv2_sample_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t channels) {
+    if (n < 0 || h <= 0 || w <= 0 || channels <= 0) return 0;
+    return (dcnv2_sample_workspace_bytes(n, h, w, channels) + 255) / 256 * 256;
+}
+
+int dcnv3_dcnv2_sample_forward(const void* x, const void* offsets, const void* mask, void* out, int32_t n, int32_t h, int32_t w,
+                               int32_t channels, int32_t kh, int32_t kw, int32_t dtype, void* cuda_stream) {
+    int rc = check_dcnv2(n, h, w, channels, kh, kw, dtype);
+    if (rc) return rc;
+    if (n == 0) return DCNV3_OK;
+    if ((rc = check_ptr_align(x, "x", 2)) || (rc = check_ptr_align(offsets, "offsets", 2)) || (rc = check_ptr_align(mask, "mask", 2)) ||
+        (rc = check_ptr_align(out, "out", 2)))
+        return rc;
+    const cudaError_t e = launch_dcnv2_sample_fwd(x, offsets, mask, out, n, h, w, channels, kh, kw, dtype, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "dcnv3_dcnv2_sample_forward launch");
+    return DCNV3_OK;
+}
+
+int dcnv3_dcnv2_sample_backward(const void* x, const void* offsets, const void* mask, const void* grad_out, void* grad_x,
+                                void* grad_offsets, void* grad_mask, void* workspace, size_t workspace_bytes, int32_t n,
+                                int32_t h, int32_t w, int32_t channels, int32_t kh, int32_t kw, int32_t dtype, uint32_t flags,
+                                void* cuda_stream) {
+    int rc = check_dcnv2(n, h, w, channels, kh, kw, dtype);
+    if (rc) return rc;
+    if (n == 0) return DCNV3_OK;
+    if ((rc = check_ptr_align(x, "x", 2)) || (rc = check_ptr_align(offsets, "offsets", 2)) || (rc = check_ptr_align(mask, "mask", 2)) ||
+        (rc = check_ptr_align(grad_out, "grad_out", 2)) || (rc = check_ptr_align(grad_x, "grad_x", 2)) ||
+        (rc = check_ptr_align(grad_offsets, "grad_offsets", 2)) || (rc = check_ptr_align(grad_mask, "grad_mask", 2)))
+        return rc;
+    const size_t need = dcnv3_dcnv2_sample_workspace_bytes(n, h, w, channels);
+    if (workspace == nullptr || workspace_bytes < need)
+        return fail(DCNV3_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+    if ((rc = check_ptr_align(workspace, "workspace", 256))) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    cudaError_t e;
+    if (!(flags & DCNV3_FLAG_WORKSPACE_ZEROED) && (e = cudaMemsetAsync(workspace, 0, need, st)) != cudaSuccess)
+        return cuda_fail(e, "memset(workspace)");
+    e = launch_dcnv2_sample_bwd(x, offsets, mask, grad_out, grad_x, grad_offsets, grad_mask, workspace, n, h, w, channels, kh, kw,
+                                dtype, st);
+    if (e != cudaSuccess) return cuda_fail(e, "dcnv3_dcnv2_sample_backward launch");
+    return DCNV3_OK;
+}
+
 size_t dcnv3_backward_workspace_bytes(const dcnv3_params* p) {
     if (check(p) != DCNV3_OK) return 0;
     return backward_ws_bytes(p);

@@ -498,4 +498,158 @@ cudaError_t launch_deform_attn_bwd(const void* value, const void* ys, const void
                : launch_deform_attn_bwd_t<__nv_bfloat16>(value, ys, xs, attn, grad_out, grad_value, grad_y, grad_x, grad_attn, ws, q, st);
 }
 
+// =====================================================================================================
+// Sibling gather op: the sampling stage of iSeg's DCNv2, reference layers/dcn_v2.py:137-247
+// (everything between the offset convolution :128-135 and the contraction with the kernel :249-271):
+//     map[n,i,j,k,:] = mask[n,i,j,k] * bilinear(pad(x)[n], i + ph + py_k + oy[n,i,j,k], j + pw + px_k + ox[n,i,j,k])
+// with that function's conventions: coordinates in the zero-padded image (:219), tap k = row-major over (py, px)
+// (:110-111), all four neighbour indices AND the coordinate itself clipped to [0, H+1] x [0, W+1] (:165-175), weights
+// from the clipped values (:193-211).  The padded image is never materialised (out-of-image neighbours read as 0).
+// =====================================================================================================
+struct D2Params {
+    int n, h, w, c, kh, kw;
+};
+struct D2Tap {
+    int y0, x0, y1, x1;            // clipped neighbour indices, padded coordinates
+    float d0y, d1y, d0x, d1x;      // :193-194 from the clipped coordinate
+    float iny, inx;                // 1 where the coordinate passes the clip (gradient of tf.clip_by_value)
+};
+__device__ __forceinline__ D2Tap d2_tap(const D2Params& q, int i, int j, int k, float oy, float ox) {
+    const int ph = (q.kh - 1) / 2, pw = (q.kw - 1) / 2;
+    const float gy = __fadd_rn((float)(i + ph + (k / q.kw - ph)), oy);   // :157-163 (integer sums, cast, + offset)
+    const float gx = __fadd_rn((float)(j + pw + (k % q.kw - pw)), ox);
+    const float hb = (float)(q.h + 1), wb = (float)(q.w + 1);             // :139-142
+    const float fy = floorf(gy), fx = floorf(gx);
+    const float y1 = fminf(fmaxf(fy + 1.0f, 0.f), hb), x1 = fminf(fmaxf(fx + 1.0f, 0.f), wb);   // :166-170
+    const float y0 = fminf(fmaxf(fy, 0.f), hb), x0 = fminf(fmaxf(fx, 0.f), wb);               // :174
+    const float gyc = fminf(fmaxf(gy, 0.f), hb), gxc = fminf(fmaxf(gx, 0.f), wb);             // :177
+    D2Tap t;
+    t.y0 = (int)y0; t.y1 = (int)y1; t.x0 = (int)x0; t.x1 = (int)x1;
+    t.d0y = __fsub_rn(gyc, y0); t.d1y = __fsub_rn(y1, gyc);
+    t.d0x = __fsub_rn(gxc, x0); t.d1x = __fsub_rn(x1, gxc);
+    t.iny = (gy >= 0.f && gy <= hb) ? 1.f : 0.f;
+    t.inx = (gx >= 0.f && gx <= wb) ? 1.f : 0.f;
+    return t;
+}
+// element offset of padded pixel (yp, xp) in the un-padded image, or -1 in the zero border (or beyond it)
+__device__ __forceinline__ long long d2_pixel(const D2Params& q, size_t n, int yp, int xp) {
+    const int y = yp - (q.kh - 1) / 2, x = xp - (q.kw - 1) / 2;
+    if (y < 0 || y >= q.h || x < 0 || x >= q.w) return -1;
+    return (long long)(((n * q.h + y) * q.w + x) * (size_t)q.c);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dcnv2_sample_fwd_kernel(const T* __restrict__ x, const T* __restrict__ offs, const T* __restrict__ mask, T* __restrict__ out,
+                        const D2Params q) {
+    const int ks = q.kh * q.kw;
+    const size_t total = (size_t)q.n * q.h * q.w * ks * q.c;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % q.c);
+    const size_t pk = idx / q.c;                     // (pixel, tap)
+    const int k = (int)(pk % ks);
+    const size_t pix = pk / ks;
+    const int j = (int)(pix % q.w), i = (int)((pix / q.w) % q.h);
+    const size_t n = pix / ((size_t)q.w * q.h);
+    const D2Tap t = d2_tap(q, i, j, k, Elem<T>::ld(offs + pk * 2), Elem<T>::ld(offs + pk * 2 + 1));
+    auto v = [&](int yp, int xp) {
+        const long long o = d2_pixel(q, n, yp, xp);
+        return o < 0 ? 0.f : Elem<T>::ld(x + o + c);
+    };
+    // :193-211 weights, :231-236 [1,4] x [4,C] product in the order of the index list (:180-184), then x mask (:238)
+    float s = __fmul_rn(__fmul_rn(t.d0y, t.d0x), v(t.y1, t.x1));
+    s = __fadd_rn(s, __fmul_rn(__fmul_rn(t.d0y, t.d1x), v(t.y1, t.x0)));
+    s = __fadd_rn(s, __fmul_rn(__fmul_rn(t.d1y, t.d0x), v(t.y0, t.x1)));
+    s = __fadd_rn(s, __fmul_rn(__fmul_rn(t.d1y, t.d1x), v(t.y0, t.x0)));
+    Elem<T>::st(out + idx, __fmul_rn(s, Elem<T>::ld(mask + pk)));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+dcnv2_sample_bwd_kernel(const T* __restrict__ x, const T* __restrict__ offs, const T* __restrict__ mask,
+                        const T* __restrict__ grad_out, T* __restrict__ grad_offs, T* __restrict__ grad_mask,
+                        const ImgMax* __restrict__ img_max, unsigned long long* __restrict__ acc64, const D2Params q) {
+    const int ks = q.kh * q.kw;
+    const size_t total = (size_t)q.n * q.h * q.w * ks;
+    const size_t pk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pk >= total) return;
+    const int k = (int)(pk % ks);
+    const size_t pix = pk / ks;
+    const int j = (int)(pix % q.w), i = (int)((pix / q.w) % q.h);
+    const size_t n = pix / ((size_t)q.w * q.h);
+    const int e = fixed_exponent(img_max[n], false);
+    const D2Tap t = d2_tap(q, i, j, k, Elem<T>::ld(offs + pk * 2), Elem<T>::ld(offs + pk * 2 + 1));
+    const float m = Elem<T>::ld(mask + pk);
+    const long long o11 = d2_pixel(q, n, t.y1, t.x1), o10 = d2_pixel(q, n, t.y1, t.x0);
+    const long long o01 = d2_pixel(q, n, t.y0, t.x1), o00 = d2_pixel(q, n, t.y0, t.x0);
+    const float w11 = t.d0y * t.d0x, w10 = t.d0y * t.d1x, w01 = t.d1y * t.d0x, w00 = t.d1y * t.d1x;
+    const T* go = grad_out + pk * q.c;
+    float gs = 0.f, gy = 0.f, gx = 0.f;
+    for (int c = 0; c < q.c; ++c) {
+        const float g = Elem<T>::ld(go + c);
+        const float v11 = o11 < 0 ? 0.f : Elem<T>::ld(x + o11 + c), v10 = o10 < 0 ? 0.f : Elem<T>::ld(x + o10 + c);
+        const float v01 = o01 < 0 ? 0.f : Elem<T>::ld(x + o01 + c), v00 = o00 < 0 ? 0.f : Elem<T>::ld(x + o00 + c);
+        gs += g * (w11 * v11 + w10 * v10 + w01 * v01 + w00 * v00);
+        gy += g * ((t.d0x * v11 + t.d1x * v10) - (t.d0x * v01 + t.d1x * v00));   // d/d(clipped y): d0y up, d1y down
+        gx += g * ((t.d0y * v11 + t.d1y * v01) - (t.d0y * v10 + t.d1y * v00));
+        const float gm = g * m;
+        if (o11 >= 0) atomicAdd(acc64 + o11 + c, (unsigned long long)to_fixed(gm * w11, e));
+        if (o10 >= 0) atomicAdd(acc64 + o10 + c, (unsigned long long)to_fixed(gm * w10, e));
+        if (o01 >= 0) atomicAdd(acc64 + o01 + c, (unsigned long long)to_fixed(gm * w01, e));
+        if (o00 >= 0) atomicAdd(acc64 + o00 + c, (unsigned long long)to_fixed(gm * w00, e));
+    }
+    Elem<T>::st(grad_mask + pk, gs);
+    Elem<T>::st(grad_offs + pk * 2, m * gy * t.iny);
+    Elem<T>::st(grad_offs + pk * 2 + 1, m * gx * t.inx);
+}
+
+size_t dcnv2_sample_workspace_bytes(int n, int h, int w, int c) {
+    return sizeof(WsHeader) + img_max_bytes(n) + sizeof(long long) * (size_t)n * h * w * c;
+}
+
+template <typename T>
+static cudaError_t launch_dcnv2_fwd_t(const void* x, const void* offs, const void* mask, void* out, const D2Params& q,
+                                      cudaStream_t st) {
+    const size_t total = (size_t)q.n * q.h * q.w * q.kh * q.kw * q.c;
+    if (total == 0) return cudaSuccess;
+    dcnv2_sample_fwd_kernel<T><<<blocks_for(total, 256), 256, 0, st>>>((const T*)x, (const T*)offs, (const T*)mask, (T*)out, q);
+    count_launch(1);
+    return cudaGetLastError();
+}
+cudaError_t launch_dcnv2_sample_fwd(const void* x, const void* offs, const void* mask, void* out, int n, int h, int w, int c,
+                                    int kh, int kw, int dtype, cudaStream_t st) {
+    const D2Params q = {n, h, w, c, kh, kw};
+    return dtype == DCNV3_F32 ? launch_dcnv2_fwd_t<float>(x, offs, mask, out, q, st)
+                              : launch_dcnv2_fwd_t<__nv_bfloat16>(x, offs, mask, out, q, st);
+}
+
+template <typename T>
+static cudaError_t launch_dcnv2_bwd_t(const void* x, const void* offs, const void* mask, const void* grad_out, void* grad_x,
+                                      void* grad_offs, void* grad_mask, void* ws, const D2Params& q, cudaStream_t st) {
+    const int ks = q.kh * q.kw;
+    const size_t n_x = (size_t)q.n * q.h * q.w * q.c, n_pk = (size_t)q.n * q.h * q.w * ks;
+    if (n_x == 0) return cudaSuccess;
+    const size_t prefix = sizeof(WsHeader) + img_max_bytes(q.n);
+    ImgMax* img_max = (ImgMax*)((char*)ws + sizeof(WsHeader));
+    unsigned long long* acc = (unsigned long long*)((char*)ws + prefix);
+    const size_t per_image = n_x / q.n, go_per_image = per_image * ks, m_per_image = n_pk / q.n;
+    const unsigned nb = (unsigned)max((size_t)1, min((size_t)148 * 8 / q.n + 1, (go_per_image + 255) / 256));
+    amax_kernel<T><<<dim3(nb, min(q.n, 65535)), 256, 0, st>>>((const T*)grad_out, go_per_image, (const T*)mask, m_per_image, img_max, q.n);
+    dcnv2_sample_bwd_kernel<T><<<blocks_for(n_pk, 128), 128, 0, st>>>((const T*)x, (const T*)offs, (const T*)mask, (const T*)grad_out,
+                                                                      (T*)grad_offs, (T*)grad_mask, img_max, acc, q);
+    const unsigned nb2 = (unsigned)max((size_t)1, min((size_t)148 * 16 / q.n + 1, (per_image + 255) / 256));
+    fixed_to_float_kernel<T><<<dim3(nb2, min(q.n, 65535)), 256, 0, st>>>((long long*)acc, img_max, (T*)grad_x, per_image, 0u, q.n);
+    count_launch(3);
+    cudaError_t err = cudaMemsetAsync(ws, 0, prefix, st);
+    return err != cudaSuccess ? err : cudaGetLastError();
+}
+cudaError_t launch_dcnv2_sample_bwd(const void* x, const void* offs, const void* mask, const void* grad_out, void* grad_x,
+                                    void* grad_offs, void* grad_mask, void* ws, int n, int h, int w, int c, int kh, int kw,
+                                    int dtype, cudaStream_t st) {
+    const D2Params q = {n, h, w, c, kh, kw};
+    return dtype == DCNV3_F32 ? launch_dcnv2_bwd_t<float>(x, offs, mask, grad_out, grad_x, grad_offs, grad_mask, ws, q, st)
+                              : launch_dcnv2_bwd_t<__nv_bfloat16>(x, offs, mask, grad_out, grad_x, grad_offs, grad_mask, ws, q, st);
+}
+
 }  // namespace dcnv3

@@ -55,4 +55,12 @@ cudaError_t launch_deform_attn_bwd(const void* value, const void* ys, const void
                                    void* grad_value, void* grad_y, void* grad_x, void* grad_attn, void* ws, int n, int h, int w,
                                    int heads, int points, int c, int dtype, cudaStream_t st);
 
+// sibling gather op (dcnv3_generic.cu): the sampling stage of iSeg's DCNv2
+size_t dcnv2_sample_workspace_bytes(int n, int h, int w, int c);
+cudaError_t launch_dcnv2_sample_fwd(const void* x, const void* offs, const void* mask, void* out, int n, int h, int w, int c,
+                                    int kh, int kw, int dtype, cudaStream_t st);
+cudaError_t launch_dcnv2_sample_bwd(const void* x, const void* offs, const void* mask, const void* grad_out, void* grad_x,
+                                    void* grad_offs, void* grad_mask, void* ws, int n, int h, int w, int c, int kh, int kw,
+                                    int dtype, cudaStream_t st);
+
 }  // namespace dcnv3

@@ -175,3 +175,80 @@ def run_deform_attn(value, y, x, attn, grad_out=None):
         return out.detach().numpy()
     out.backward(torch.from_numpy(np.ascontiguousarray(grad_out)))
     return (out.detach().numpy(), tv.grad.numpy(), ty.grad.numpy(), tx.grad.numpy(), ta.grad.numpy())
+
+
+# ---- sibling op: DCNv2 ------------------------------------------------------------------------
+_loaded_dcnv2 = None
+
+
+def load_dcn_v2():
+    """The reference's DCNv2 layer class, loaded from /root/reference/layers/dcn_v2.py over the shim.  Stand-ins: a
+    minimal keras Layer with add_weight (zeros / glorot initialisers), `keras.activations.get`, and the three helpers
+    the file imports from iseg.utils."""
+    global _loaded_dcnv2
+    if _loaded_dcnv2 is not None:
+        return _loaded_dcnv2
+    ref = load()
+    tf = ref.tf
+    import torch
+
+    class Layer:
+        def __init__(self, *args, name=None, **kwargs):
+            self.name = name
+
+        def add_weight(self, name=None, shape=None, initializer="zeros", regularizer=None, trainable=True, dtype="float32"):
+            return tf.convert_to_tensor(torch.zeros(tuple(int(v) for v in shape), dtype=torch.float32))
+
+        def build(self, input_shape):
+            self.built = True
+
+    keras = sys.modules.get("keras") or types.ModuleType("keras")
+    keras.layers = types.SimpleNamespace(Layer=Layer, **{k: getattr(tf.keras.layers, k) for k in ("Dense",)})
+    keras.activations = types.SimpleNamespace(get=lambda a: (lambda t: t) if a is None else a)
+    keras.backend = types.SimpleNamespace(epsilon=lambda: 1e-7)
+    sys.modules["keras"] = keras
+    vu = types.ModuleType("iseg.utils.version_utils")
+    vu.is_keras3 = lambda: True
+    sys.modules["iseg.utils.version_utils"] = vu
+    val = types.ModuleType("iseg.utils.value_utils")
+    val.values_to_tuple_2d = lambda v: tuple(v) if isinstance(v, (list, tuple)) else (v, v)   # utils/value_utils.py:22-31
+    sys.modules["iseg.utils.value_utils"] = val
+    k3 = sys.modules["iseg.utils.keras3_utils"]
+
+    class Keras3_Layer_Wrapper(Layer):   # utils/keras3_utils.py:32: keras Layer that rewrites '/' in the name
+        def __init__(self, trainable=True, name=None, dtype=None, dynamic=False, **kwargs):
+            super().__init__(name=None if name is None else name.replace("/", "."))
+
+    k3.Keras3_Layer_Wrapper = Keras3_Layer_Wrapper
+    mod = _load_file("iseg.layers.dcn_v2", os.path.join(REFERENCE_ROOT, "layers", "dcn_v2.py"))
+    _loaded_dcnv2 = mod.DCNv2
+    return _loaded_dcnv2
+
+
+def run_dcn_v2(x, kernel, bias, offset_kernel, offset_bias, dilation_rate=1, grads_for=None):
+    """Reference DCNv2 (`layers/dcn_v2.py`): the class's own build() (:61-113: weights, patch offsets) and _forward()
+    (:121-265) on numpy inputs, with the given weights written over the freshly built ones.  Returns the output
+    [N,H,W,filters], or (out, grad_x, grad_kernel, grad_bias, grad_offset_kernel, grad_offset_bias) when `grads_for`
+    (a grad_out array) is given."""
+    import numpy as np
+    import torch
+
+    cls = load_dcn_v2()
+    tf = load().tf
+    kh, kw, ic, oc = kernel.shape
+    layer = cls(oc, (kh, kw), dilation_rate=dilation_rate, use_bias=bias is not None)
+    layer.build((None, None, None, ic))
+    t = lambda a: tf.convert_to_tensor(torch.from_numpy(np.ascontiguousarray(a)))  # noqa: E731
+    tx = t(x)
+    layer.kernel, layer.offset_kernel, layer.offset_bias = t(kernel), t(offset_kernel), t(offset_bias)
+    if bias is not None:
+        layer.bias = t(bias)
+    leaves = [tx, layer.kernel] + ([layer.bias] if bias is not None else []) + [layer.offset_kernel, layer.offset_bias]
+    if grads_for is not None:
+        for v in leaves:
+            v.requires_grad_(True)
+    out = layer.call(tx)
+    if grads_for is None:
+        return out.detach().numpy()
+    out.backward(torch.from_numpy(np.ascontiguousarray(grads_for)))
+    return (out.detach().numpy(),) + tuple(v.grad.numpy() for v in leaves)

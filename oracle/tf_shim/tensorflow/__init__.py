@@ -198,6 +198,83 @@ def _mul(x, y, name=None):
 raw_ops = _types.SimpleNamespace(Pack=_pack, GatherNd=_gather_nd, Mul=_mul)
 
 
+# ---- primitives of the sibling gather ops (layers/deformable_multihead_self_attention.py, layers/dcn_v2.py) ----
+gather_nd = _gather_nd
+
+
+def broadcast_to(x, shape, name=None):  # noqa: A002
+    return _t(_torch.broadcast_to(_t(x), tuple(int(v) for v in shape)))
+
+
+_DTYPE_NAMES = {"int32": int32, "int64": int64, "float32": float32, "float64": float64, "bfloat16": bfloat16, "float16": float16}
+
+
+def constant(value, dtype=None, shape=None, name=None):  # noqa: A002
+    return _t(value, _DTYPE_NAMES.get(dtype, dtype))
+
+
+def add(x, y, name=None):
+    return _t(x) + _t(y)
+
+
+def multiply(x, y, name=None):
+    return x * y
+
+
+def matmul(a, b, name=None):
+    return _torch.matmul(a, b)
+
+
+def squeeze(x, axis=None, name=None):
+    return _torch.squeeze(x) if axis is None else _torch.squeeze(x, dim=axis)
+
+
+def concat(values, axis, name=None):
+    return _torch.cat([_t(v) for v in values], dim=axis)
+
+
+def split(value, num_or_size_splits, axis=0, name=None):
+    if isinstance(num_or_size_splits, int):
+        return list(_torch.chunk(value, num_or_size_splits, dim=axis))
+    return list(_torch.split(value, [int(v) for v in num_or_size_splits], dim=axis))
+
+
+def unstack(value, num=None, axis=0, name=None):
+    return list(_torch.unbind(value, dim=axis))
+
+
+def ones_like(x, dtype=None, name=None):
+    return _t(_torch.ones_like(x, dtype=dtype))
+
+
+def tanh(x, name=None):
+    return _torch.tanh(x)
+
+
+class _InitScope:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def init_scope():
+    return _InitScope()
+
+
+def _conv2d(input, filters, strides, padding, dilations=None, name=None):  # noqa: A002
+    """tf.nn.conv2d, NHWC x HWIO, stride 1, 'SAME' with an odd kernel (what layers/dcn_v2.py:128-134 calls)."""
+    st = [int(v) for v in (strides if isinstance(strides, (list, tuple)) else [strides] * 4)]
+    assert padding == "SAME" and all(v == 1 for v in st), (padding, st)
+    dil = [int(v) for v in (dilations or (1, 1))][-2:]
+    kh, kw = int(filters.shape[0]), int(filters.shape[1])
+    assert kh % 2 == 1 and kw % 2 == 1
+    y = _torch.nn.functional.conv2d(input.permute(0, 3, 1, 2), filters.permute(3, 2, 0, 1), None, 1,
+                                    (dil[0] * (kh - 1) // 2, dil[1] * (kw - 1) // 2), tuple(dil))
+    return _t(y.permute(0, 2, 3, 1).contiguous())
+
+
 def _gelu(x, approximate=False, name=None):
     return _torch.nn.functional.gelu(x, approximate="tanh" if approximate else "none")
 
@@ -206,7 +283,7 @@ def _softmax(x, axis=-1, name=None):
     return _torch.softmax(x, dim=axis)
 
 
-nn = _types.SimpleNamespace(gelu=_gelu, softmax=_softmax)
+nn = _types.SimpleNamespace(gelu=_gelu, softmax=_softmax, sigmoid=lambda x, name=None: _torch.sigmoid(x), conv2d=_conv2d)
 
 
 def zeros_initializer():

@@ -258,6 +258,31 @@ def make_dmsa_case(name, spec):
                         grad_value=gv, grad_y=gy, grad_x=gx, grad_attn=ga)
 
 
+# sibling op: the reference's DCNv2 layer, build() + _forward() (layers/dcn_v2.py:61-113, :121-265).
+# name: (N, H, W, C_in, filters, k, offset spread, dtype, seed)
+DCNV2_CASES = {
+    "k3_8x9_c6_o5": (2, 8, 9, 6, 5, 3, 1.5, "f4", 30),
+    "k3_far_7x7_c4_o3_f64": (1, 7, 7, 4, 3, 3, 6.0, "f8", 31),    # offsets far beyond the image: every clip in play
+    "k5_9x8_c3_o4": (1, 9, 8, 3, 4, 5, 2.0, "f4", 32),            # 5x5: the [0, H+1] clip range inside a pad-2 image
+}
+
+
+def make_dcnv2_case(name, spec):
+    n, h, w, ic, oc, k, spread, dt, seed = spec
+    rng = np.random.default_rng(seed)
+    dtype = np.float64 if dt == "f8" else np.float32
+    x = rng.standard_normal((n, h, w, ic)).astype(dtype)
+    kernel = (rng.standard_normal((k, k, ic, oc)) * 0.3).astype(dtype)
+    bias = rng.standard_normal(oc).astype(dtype)
+    offset_kernel = (rng.standard_normal((k, k, ic, 3 * k * k)) * 0.15).astype(dtype)
+    offset_bias = (rng.standard_normal(3 * k * k) * spread).astype(dtype)
+    grad_out = rng.standard_normal((n, h, w, oc)).astype(dtype)
+    out, gx, gk, gb, gok, gob = ref_runner.run_dcn_v2(x, kernel, bias, offset_kernel, offset_bias, grads_for=grad_out)
+    np.savez_compressed(os.path.join(OUT, f"dcnv2_{name}.npz"), x=x, kernel=kernel, bias=bias, offset_kernel=offset_kernel,
+                        offset_bias=offset_bias, grad_out=grad_out, out=out, grad_x=gx, grad_kernel=gk, grad_bias=gb,
+                        grad_offset_kernel=gok, grad_offset_bias=gob)
+
+
 if __name__ == "__main__":
     assert ref_runner.available(), "needs /root/reference"
     for nm, sp in OP_CASES.items():
@@ -269,6 +294,9 @@ if __name__ == "__main__":
     make_kats()
     make_layer_case()
     make_sliding_indices()
+    for nm, sp in DCNV2_CASES.items():
+        make_dcnv2_case(nm, sp)
+        print("wrote dcnv2", nm)
     for nm, sp in DMSA_CASES.items():
         make_dmsa_case(nm, sp)
         print("wrote dmsa", nm)

@@ -174,3 +174,47 @@ def test_deform_attn_fixture_regenerates():
     res = ref_runner.run_deform_attn(z["value"], z["y"], z["x"], z["attn"], z["grad_out"])
     for got, key in zip(res, ("out", "grad_value", "grad_y", "grad_x", "grad_attn")):
         assert np.array_equal(got, z[key]), key
+
+
+# ---- sibling op: DCNv2 -------------------------------------------------------------------------
+DCNV2 = sorted(os.path.basename(p)[6:-4] for p in glob.glob(os.path.join(GOLDEN, "dcnv2_*.npz")))
+
+
+@pytest.mark.parametrize("name", DCNV2)
+def test_dcnv2_oracle_matches_reference_fixtures(name):
+    """oracle/dcnv2_oracle.py::layer_forward against what the reference's own DCNv2.build() + _forward() produced."""
+    from oracle import dcnv2_oracle as D
+    z = np.load(os.path.join(GOLDEN, f"dcnv2_{name}.npz"))
+    out = D.layer_forward(z["x"], z["kernel"], z["bias"], z["offset_kernel"], z["offset_bias"])
+    assert rel_err(out, z["out"]) <= (1e-14 if out.dtype == np.float64 else 3e-6)
+
+
+def test_dcnv2_oracle_sampler_gradient_by_finite_differences():
+    from oracle import dcnv2_oracle as D
+    rng = np.random.default_rng(3)
+    n, h, w, c, k = 1, 5, 6, 3, 3
+    x = rng.standard_normal((n, h, w, c))
+    offs = rng.uniform(-2.5, 2.5, (n, h, w, k * k, 2))
+    mask = rng.uniform(0.1, 0.9, (n, h, w, k * k))
+    go = rng.standard_normal((n, h, w, k * k, c))
+    gx, goff, gm = D.sample_backward(x, offs, mask, go, k, k)
+    f = lambda xx, oo, mm: float((D.sample_forward(xx, oo, mm, k, k) * go).sum())  # noqa: E731
+    eps = 1e-6
+    for arr, grad, idxs in ((x, gx, [(0, 2, 3, 1), (0, 0, 0, 0), (0, 4, 5, 2)]), (mask, gm, [(0, 1, 1, 4), (0, 4, 0, 8)]),
+                            (offs, goff, [(0, 2, 2, 4, 0), (0, 0, 5, 0, 1), (0, 3, 1, 7, 1)])):
+        for idx in idxs:
+            a, b = arr.copy(), arr.copy()
+            a[idx] += eps
+            b[idx] -= eps
+            args = lambda v: (v if arr is x else x, v if arr is offs else offs, v if arr is mask else mask)  # noqa: E731
+            fd = (f(*args(a)) - f(*args(b))) / (2 * eps)
+            assert abs(fd - grad[idx]) <= 1e-6 * max(1.0, abs(fd)), (idx, fd, grad[idx])
+
+
+@pytest.mark.needs_reference
+def test_dcnv2_fixture_regenerates():
+    from oracle import ref_runner
+    z = np.load(os.path.join(GOLDEN, "dcnv2_k3_far_7x7_c4_o3_f64.npz"))
+    res = ref_runner.run_dcn_v2(z["x"], z["kernel"], z["bias"], z["offset_kernel"], z["offset_bias"], grads_for=z["grad_out"])
+    for got, key in zip(res, ("out", "grad_x", "grad_kernel", "grad_bias", "grad_offset_kernel", "grad_offset_bias")):
+        assert np.array_equal(got, z[key]), key
