@@ -139,16 +139,67 @@ def cfg5(strategy):
             "output_shape": list(out.shape), "finite": bool(torch.isfinite(out).all().item())}
 
 
+def siblings(strategy):
+    """The two sibling gather ops at a representative shape each: forward + backward through the torch
+    ops, CUDA events, algorithmic bytes (every tensor read or written once) / time against the measured HBM peak.  They
+    run generic thread-per-point kernels and are not tuned; this is the measurement, not a target."""
+    from iseg_b200.layers.dcn_v2 import dcnv2_sample
+    from iseg_b200.layers.deformable_attention import deform_attn_sample
+    dev = strategy.device
+    gen = torch.Generator(device=dev).manual_seed(0)
+    r = lambda *s: torch.randn(*s, device=dev, generator=gen)  # noqa: E731
+    out = []
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except (OSError, KeyError, ValueError):
+        peak = None
+    # deformable attention: batch 16, 64x64, 8 heads x 32 channels, 4 points
+    n, h, w, heads, pts, c = 16, 64, 64, 8, 4, 32
+    value = r(n, h, w, heads, c).requires_grad_()
+    y = (torch.rand(n, h, w, heads, pts, device=dev, generator=gen) * (h - 1)).requires_grad_()
+    x = (torch.rand(n, h, w, heads, pts, device=dev, generator=gen) * (w - 1)).requires_grad_()
+    attn = torch.softmax(r(n, h, w, heads, pts), -1).requires_grad_()
+    go = r(n, h, w, heads, c)
+
+    def da():
+        for t in (value, y, x, attn):
+            t.grad = None
+        deform_attn_sample(value, y, x, attn).backward(go)
+
+    ms = timed(da, 20, 3, strategy)
+    nbytes = 4 * (n * h * w * heads * (4 * c + 6 * pts))  # value, out, grad_out, grad_value + 3 point tensors and their gradients
+    out.append({"config": "sibling: deform_attn_sample fwd+bwd, batch 16, 64x64, 8 heads x 32 ch, 4 points, fp32", "ms": ms,
+                "algo_gbs": nbytes / (ms * 1e-3) * 1e-9, "frac_of_hbm_peak": None if peak is None else nbytes / (ms * 1e-3) * 1e-9 / peak})
+    # DCNv2 sampler: batch 16, 64x64, 128 channels, 3x3
+    n, h, w, c, k = 16, 64, 64, 128, 3
+    xx = r(n, h, w, c).requires_grad_()
+    offs = (r(n, h, w, k * k, 2)).requires_grad_()
+    mask = torch.sigmoid(r(n, h, w, k * k)).requires_grad_()
+    go2 = r(n, h, w, k * k, c)
+
+    def d2():
+        for t in (xx, offs, mask):
+            t.grad = None
+        dcnv2_sample(xx, offs, mask, k).backward(go2)
+
+    ms = timed(d2, 20, 3, strategy)
+    nbytes = 4 * (n * h * w * (2 * c + 2 * k * k * c + 6 * k * k))  # x, grad_x, map_all, its gradient, offsets / mask and gradients
+    out.append({"config": "sibling: dcnv2_sample fwd+bwd, batch 16, 64x64, 128 channels, 3x3, fp32", "ms": ms,
+                "algo_gbs": nbytes / (ms * 1e-3) * 1e-9, "frac_of_hbm_peak": None if peak is None else nbytes / (ms * 1e-3) * 1e-9 / peak})
+    return out
+
+
 def main():
-    which = [a for a in sys.argv[1:] if a.startswith("cfg")] or ["cfg3", "cfg4", "cfg5"]
+    which = [a for a in sys.argv[1:] if a.startswith("cfg") or a == "siblings"] or ["cfg3", "cfg4", "cfg5"]
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     strategy = BatchShardStrategy()
     t0 = time.time()
     for name in which:
-        res = {"cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}[name](strategy)
+        res = {"cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "siblings": siblings}[name](strategy)
         torch.cuda.empty_cache()
         if strategy.rank == 0:
-            print(json.dumps(res))
+            for line in (res if isinstance(res, list) else [res]):
+                print(json.dumps(line))
     if strategy.rank == 0:
         print(f"# {time.time() - t0:.1f} s", file=sys.stderr)
     if strategy.world_size > 1:
