@@ -397,15 +397,20 @@ deform_attn_fwd_kernel(const T* __restrict__ value, const T* __restrict__ ys, co
     else Elem<T>::st(o, acc[0]);
 }
 
+// A group of LPP lanes (a power of two <= 32, about the channels per head) works on one (pixel, head, point): lane = channel,
+// so that the four corner reads and the four 64-bit atomic adds of a channel step are contiguous runs (one 256-byte run per
+// corner for 32 channels instead of 32 scattered words); the three dot products are reduced by shuffles inside the group.
 template <typename T>
 __global__ void __launch_bounds__(128)
 deform_attn_bwd_kernel(const T* __restrict__ value, const T* __restrict__ ys, const T* __restrict__ xs,
                        const T* __restrict__ attn, const T* __restrict__ grad_out, T* __restrict__ grad_y,
                        T* __restrict__ grad_x, T* __restrict__ grad_attn, const ImgMax* __restrict__ img_max,
-                       unsigned long long* __restrict__ acc64, const DaParams q) {
+                       unsigned long long* __restrict__ acc64, const DaParams q, const int lpp) {
     const size_t total = (size_t)q.n * q.h * q.w * q.heads * q.points;
-    const size_t pi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pi >= total) return;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = tid / lpp < total;              // (whole groups are in or out: blockDim is a multiple of lpp;
+    const size_t pi = valid ? tid / lpp : total - 1;    //  lanes past the end shadow the last point and write nothing,
+    const int cl = (int)(tid % lpp);                    //  so that the full-warp shuffles below stay well defined)
     const size_t ph = pi / q.points;
     const int hd = (int)(ph % q.heads);
     const size_t n = ph / ((size_t)q.heads * q.w * q.h);
@@ -421,7 +426,7 @@ deform_attn_bwd_kernel(const T* __restrict__ value, const T* __restrict__ ys, co
     const size_t o11 = n * img + (size_t)t.y1 * row + ((size_t)t.x1 * q.heads + hd) * q.c;
     const T* go = grad_out + ph * q.c;
     float s = 0.f, gy = 0.f, gx = 0.f;
-    for (int c = 0; c < q.c; ++c) {
+    for (int c = valid ? cl : q.c; c < q.c; c += lpp) {
         const float g = Elem<T>::ld(go + c);
         const float v00 = Elem<T>::ld(value + o00 + c), v01 = Elem<T>::ld(value + o01 + c);
         const float v10 = Elem<T>::ld(value + o10 + c), v11 = Elem<T>::ld(value + o11 + c);
@@ -434,9 +439,22 @@ deform_attn_bwd_kernel(const T* __restrict__ value, const T* __restrict__ ys, co
         atomicAdd(acc64 + o10 + c, (unsigned long long)to_fixed(ga * w10, e));
         atomicAdd(acc64 + o11 + c, (unsigned long long)to_fixed(ga * w11, e));
     }
-    Elem<T>::st(grad_attn + pi, s);
-    Elem<T>::st(grad_y + pi, a * gy);
-    Elem<T>::st(grad_x + pi, a * gx);
+    for (int o = lpp >> 1; o > 0; o >>= 1) {           // (fixed tree: the sums do not depend on scheduling)
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        gy += __shfl_xor_sync(0xffffffffu, gy, o);
+        gx += __shfl_xor_sync(0xffffffffu, gx, o);
+    }
+    if (cl == 0 && valid) {
+        Elem<T>::st(grad_attn + pi, s);
+        Elem<T>::st(grad_y + pi, a * gy);
+        Elem<T>::st(grad_x + pi, a * gx);
+    }
+}
+
+static int lanes_per_point(int c) {
+    int l = 1;
+    while (l < c && l < 32) l <<= 1;
+    return l;
 }
 
 size_t deform_attn_workspace_bytes(int n, int h, int w, int heads, int c) {
@@ -478,10 +496,12 @@ static cudaError_t launch_deform_attn_bwd_t(const void* value, const void* ys, c
     const unsigned nb = (unsigned)max((size_t)1, min((size_t)148 * 8 / q.n + 1, (per_image + 255) / 256));
     // max |grad_out| and max |attn| per image -> the image's fixed-point scale
     amax_kernel<T><<<dim3(nb, min(q.n, 65535)), 256, 0, st>>>((const T*)grad_out, per_image, (const T*)attn, pts_per_image, img_max, q.n);
-    if (n_p > 0)
-        deform_attn_bwd_kernel<T><<<blocks_for(n_p, 128), 128, 0, st>>>((const T*)value, (const T*)ys, (const T*)xs, (const T*)attn,
-                                                                        (const T*)grad_out, (T*)grad_y, (T*)grad_x, (T*)grad_attn,
-                                                                        img_max, acc, q);
+    if (n_p > 0) {
+        const int lpp = lanes_per_point(q.c);
+        deform_attn_bwd_kernel<T><<<blocks_for(n_p * lpp, 128), 128, 0, st>>>((const T*)value, (const T*)ys, (const T*)xs,
+                                                                              (const T*)attn, (const T*)grad_out, (T*)grad_y,
+                                                                              (T*)grad_x, (T*)grad_attn, img_max, acc, q, lpp);
+    }
     const unsigned nb2 = (unsigned)max((size_t)1, min((size_t)148 * 16 / q.n + 1, (per_image + 255) / 256));
     fixed_to_float_kernel<T><<<dim3(nb2, min(q.n, 65535)), 256, 0, st>>>((long long*)acc, img_max, (T*)grad_value, per_image, 0u, q.n);
     count_launch(3);
@@ -565,15 +585,19 @@ dcnv2_sample_fwd_kernel(const T* __restrict__ x, const T* __restrict__ offs, con
     Elem<T>::st(out + idx, __fmul_rn(s, Elem<T>::ld(mask + pk)));
 }
 
+// (lane group per (pixel, tap), lane = channel: see deform_attn_bwd_kernel)
 template <typename T>
 __global__ void __launch_bounds__(128)
 dcnv2_sample_bwd_kernel(const T* __restrict__ x, const T* __restrict__ offs, const T* __restrict__ mask,
                         const T* __restrict__ grad_out, T* __restrict__ grad_offs, T* __restrict__ grad_mask,
-                        const ImgMax* __restrict__ img_max, unsigned long long* __restrict__ acc64, const D2Params q) {
+                        const ImgMax* __restrict__ img_max, unsigned long long* __restrict__ acc64, const D2Params q,
+                        const int lpp) {
     const int ks = q.kh * q.kw;
     const size_t total = (size_t)q.n * q.h * q.w * ks;
-    const size_t pk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pk >= total) return;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = tid / lpp < total;
+    const size_t pk = valid ? tid / lpp : total - 1;
+    const int cl = (int)(tid % lpp);
     const int k = (int)(pk % ks);
     const size_t pix = pk / ks;
     const int j = (int)(pix % q.w), i = (int)((pix / q.w) % q.h);
@@ -586,7 +610,7 @@ dcnv2_sample_bwd_kernel(const T* __restrict__ x, const T* __restrict__ offs, con
     const float w11 = t.d0y * t.d0x, w10 = t.d0y * t.d1x, w01 = t.d1y * t.d0x, w00 = t.d1y * t.d1x;
     const T* go = grad_out + pk * q.c;
     float gs = 0.f, gy = 0.f, gx = 0.f;
-    for (int c = 0; c < q.c; ++c) {
+    for (int c = valid ? cl : q.c; c < q.c; c += lpp) {
         const float g = Elem<T>::ld(go + c);
         const float v11 = o11 < 0 ? 0.f : Elem<T>::ld(x + o11 + c), v10 = o10 < 0 ? 0.f : Elem<T>::ld(x + o10 + c);
         const float v01 = o01 < 0 ? 0.f : Elem<T>::ld(x + o01 + c), v00 = o00 < 0 ? 0.f : Elem<T>::ld(x + o00 + c);
@@ -599,9 +623,16 @@ dcnv2_sample_bwd_kernel(const T* __restrict__ x, const T* __restrict__ offs, con
         if (o01 >= 0) atomicAdd(acc64 + o01 + c, (unsigned long long)to_fixed(gm * w01, e));
         if (o00 >= 0) atomicAdd(acc64 + o00 + c, (unsigned long long)to_fixed(gm * w00, e));
     }
-    Elem<T>::st(grad_mask + pk, gs);
-    Elem<T>::st(grad_offs + pk * 2, m * gy * t.iny);
-    Elem<T>::st(grad_offs + pk * 2 + 1, m * gx * t.inx);
+    for (int o = lpp >> 1; o > 0; o >>= 1) {
+        gs += __shfl_xor_sync(0xffffffffu, gs, o);
+        gy += __shfl_xor_sync(0xffffffffu, gy, o);
+        gx += __shfl_xor_sync(0xffffffffu, gx, o);
+    }
+    if (cl == 0 && valid) {
+        Elem<T>::st(grad_mask + pk, gs);
+        Elem<T>::st(grad_offs + pk * 2, m * gy * t.iny);
+        Elem<T>::st(grad_offs + pk * 2 + 1, m * gx * t.inx);
+    }
 }
 
 size_t dcnv2_sample_workspace_bytes(int n, int h, int w, int c) {
@@ -636,8 +667,10 @@ static cudaError_t launch_dcnv2_bwd_t(const void* x, const void* offs, const voi
     const size_t per_image = n_x / q.n, go_per_image = per_image * ks, m_per_image = n_pk / q.n;
     const unsigned nb = (unsigned)max((size_t)1, min((size_t)148 * 8 / q.n + 1, (go_per_image + 255) / 256));
     amax_kernel<T><<<dim3(nb, min(q.n, 65535)), 256, 0, st>>>((const T*)grad_out, go_per_image, (const T*)mask, m_per_image, img_max, q.n);
-    dcnv2_sample_bwd_kernel<T><<<blocks_for(n_pk, 128), 128, 0, st>>>((const T*)x, (const T*)offs, (const T*)mask, (const T*)grad_out,
-                                                                      (T*)grad_offs, (T*)grad_mask, img_max, acc, q);
+    const int lpp = lanes_per_point(q.c);
+    dcnv2_sample_bwd_kernel<T><<<blocks_for(n_pk * lpp, 128), 128, 0, st>>>((const T*)x, (const T*)offs, (const T*)mask,
+                                                                            (const T*)grad_out, (T*)grad_offs, (T*)grad_mask,
+                                                                            img_max, acc, q, lpp);
     const unsigned nb2 = (unsigned)max((size_t)1, min((size_t)148 * 16 / q.n + 1, (per_image + 255) / 256));
     fixed_to_float_kernel<T><<<dim3(nb2, min(q.n, 65535)), 256, 0, st>>>((long long*)acc, img_max, (T*)grad_x, per_image, 0u, q.n);
     count_launch(3);
