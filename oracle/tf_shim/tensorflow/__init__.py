@@ -1,8 +1,9 @@
 """Minimal stand-in for the `tensorflow` module, backed by torch CPU tensors.
 
 TEST INFRASTRUCTURE ONLY.  TensorFlow is not installed in the authoring container, so the
-reference's own DCNv3 files (/root/reference/layers/dcn_v3/{op,utils,dcn_v3}.py) cannot be imported
-as they are.  This package implements exactly the TF primitives those three files touch, with the
+reference's own DCNv3 files (/root/reference/layers/dcn_v3/{op,utils,dcn_v3}.py) -- and the two sibling
+gather layers, layers/deformable_multihead_self_attention.py and layers/dcn_v2.py -- cannot be imported
+as they are.  This package implements exactly the TF primitives those files touch, with the
 semantics TF documents for them, so that `oracle/ref_runner.py` can execute the UNMODIFIED reference
 source here and freeze its outputs (and, through torch autograd, the gradients TF autodiff would
 produce) as golden fixtures under tests/golden/.
