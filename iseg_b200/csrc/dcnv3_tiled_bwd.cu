@@ -891,6 +891,15 @@ __device__ __forceinline__ void scatter_walk_batched(int* acc, int* wsum, const 
             unsigned slow = 0u;
 #pragma unroll
             for (int b0 = 0; b0 < kTaps; b0 += TB) {
+                // a warp of the last, split round owns only some of the taps: batches wholly outside its range are
+                // skipped (warp-uniform)
+                if (!(b0 < cur.p_hi && b0 + TB > cur.p_lo)) {
+                    if (b0 + TB >= kTaps && nxt.valid) {  // (the request that normally rides under tap 8's run)
+                        load_inputs(nxt, in);
+                        requested = true;
+                    }
+                    continue;
+                }
                 TapRec rec[TB];
                 unsigned fast = 0u;
                 // ---- the chains of TB taps, branch free ----
