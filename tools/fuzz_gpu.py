@@ -58,22 +58,42 @@ def main():
         dt = torch.bfloat16 if bf16 else torch.float32
         tx, to = (torch.from_numpy(a).to("cuda", dt).requires_grad_() for a in (x, off))
         tm = torch.from_numpy(m if kind == "logits" else mask).to("cuda", dt).requires_grad_()
-        out = iseg_b200.dcnv3_op(tx, to, tm, [3, 3], [1, 1], "SAME", [1, 1], g, 16, scale, mask_is_logits=kind == "logits")
+        blend = kind != "raw" and rng.random() < 0.3   # the centre-feature-scale blend fused around the op
+        cs = ts = None
+        if blend:
+            cs = rng.uniform(-0.5, 1.5, (n, h, w, g)).astype(np.float32)
+            if bf16:
+                cs = torch.from_numpy(cs).bfloat16().float().numpy()
+            ts = torch.from_numpy(cs).to("cuda", dt).requires_grad_()
+            out = iseg_b200.dcnv3_op_center_scale(tx, to, tm, ts, [3, 3], [1, 1], "SAME", [1, 1], g, 16, scale,
+                                                  mask_is_logits=kind == "logits")
+        else:
+            out = iseg_b200.dcnv3_op(tx, to, tm, [3, 3], [1, 1], "SAME", [1, 1], g, 16, scale, mask_is_logits=kind == "logits")
         out.backward(torch.from_numpy(go).to("cuda", dt))
         ref_out = c_oracle.forward(x, off, mask, **kw)
-        _, roff, rm = c_oracle.backward(x, off, mask, go, **kw)
-        rx, _, _ = O.backward(x, off, mask, go, accumulate=np.float64, **kw) if h * w * n * g < 60000 else \
-            c_oracle.backward(x, off, mask, go, **kw)
+        go_core = go
+        if blend:  # out = core * (1 - s) + x * s; the core sees grad_out * (1 - s), x also grad_out * s, d s = sum go * (x - core)
+            s16 = np.repeat(cs, 16, axis=-1)
+            rs = (go * (x - ref_out)).reshape(n, h, w, g, 16).sum(-1)
+            go_core = (go * (np.float32(1) - s16)).astype(np.float32)
+            ref_out = ref_out * (np.float32(1) - s16) + x * s16
+        _, roff, rm = c_oracle.backward(x, off, mask, go_core, **kw)
+        rx, _, _ = O.backward(x, off, mask, go_core, accumulate=np.float64, **kw) if h * w * n * g < 60000 else \
+            c_oracle.backward(x, off, mask, go_core, **kw)
+        if blend:
+            rx = rx + go * s16
         if kind == "logits":  # softmax Jacobian
             mm, gg = mask.reshape(n, h, w, g, 9), rm.reshape(n, h, w, g, 9)
             rm = (mm * (gg - (mm * gg).sum(-1, keepdims=True))).reshape(n, h, w, g * 9)
         tol = 1e-2 if bf16 else (1e-5 if kind != "raw" else 3e-5)
         errs = {"out": rel(out.detach().float().cpu().numpy(), ref_out), "gx": rel(tx.grad.float().cpu().numpy(), rx),
                 "goff": rel(to.grad.float().cpu().numpy(), roff), "gm": rel(tm.grad.float().cpu().numpy(), rm)}
+        if blend:
+            errs["gs"] = rel(ts.grad.float().cpu().numpy(), rs)
         bad = {k: v for k, v in errs.items() if not v <= tol}
         if bad:
             fails += 1
-            print("FAIL", dict(n=n, h=h, w=w, g=g, scale=scale, sigma=sigma, bf16=bf16, mask=kind), bad, flush=True)
+            print("FAIL", dict(n=n, h=h, w=w, g=g, scale=scale, sigma=sigma, bf16=bf16, mask=kind, blend=blend), bad, flush=True)
     print(f"fuzz: {trials} trials, {fails} failures, {time.time() - t0:.0f} s")
     sys.exit(1 if fails else 0)
 
