@@ -165,6 +165,187 @@ static unsigned ln_grid(long long rows) {
     return (unsigned)(want < cap ? want : cap);
 }
 
+// ---- register-resident variants (channels <= 128 * QPL, QPL = 4-channel pieces per lane) ---------------------------------
+// The row-buffer kernels above loop over a row's pieces with a run-time trip count, one dependent load at a time: latency
+// bound (ncu on the InternImage-B forward: 25 % of the HBM rate).  Here the pieces of a pixel live in registers, the trip
+// counts are compile-time constants, and every global load of a pixel is in flight before the first use.
+template <int QPL>
+__device__ __forceinline__ void reg_stats(const float4 (&v)[QPL], const bool (&on)[QPL], int C, float eps, float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < QPL; ++i)
+        if (on[i]) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < QPL; ++i)
+        if (on[i]) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+}
+template <typename T>
+__device__ __forceinline__ float4 norm4(float4 v, float mean, float rstd, float4 w, float4 b) {
+    return make_float4(round_to<T>((v.x - mean) * rstd * w.x + b.x), round_to<T>((v.y - mean) * rstd * w.y + b.y),
+                       round_to<T>((v.z - mean) * rstd * w.z + b.z), round_to<T>((v.w - mean) * rstd * w.w + b.w));
+}
+
+template <typename T, int QPL>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_join_reg_kernel(const T* __restrict__ y, const T* __restrict__ r, const T* __restrict__ gamma,
+                   const T* __restrict__ lw, const T* __restrict__ lb, T* __restrict__ out_sum, T* __restrict__ out_norm,
+                   long long rows, int C, float eps, int mode) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr bool CACHE = QPL <= 2;   // the lane's channels are the same for every row: few pieces -> parameters in registers
+    constexpr int NC = CACHE ? QPL : 1;
+    bool on[QPL];
+    float4 cg[NC], cw[NC], cb[NC];
+#pragma unroll
+    for (int i = 0; i < QPL; ++i) on[i] = (lane + 32 * i) * 4 < C;
+    auto param = [&](const T* base, int i, float fill) {
+        return (on[i] && base) ? Elem<T>::ld4(base + (lane + 32 * i) * 4) : make_float4(fill, fill, fill, fill);
+    };
+    if (CACHE) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) { cg[i] = param(gamma, i, 1.f); cw[i] = param(lw, i, 1.f); cb[i] = param(lb, i, 0.f); }
+    }
+    for (long long p = (long long)blockIdx.x * kLnWarps + warp; p < rows; p += (long long)gridDim.x * kLnWarps) {
+        float4 a[QPL], b[QPL];
+        // (parameters at use: from the registers above, or L1-resident loads)
+        auto G4 = [&](int i) { return CACHE ? cg[i % NC] : param(gamma, i, 1.f); };
+        auto W4 = [&](int i) { return CACHE ? cw[i % NC] : param(lw, i, 1.f); };
+        auto B4 = [&](int i) { return CACHE ? cb[i % NC] : param(lb, i, 0.f); };
+#pragma unroll
+        for (int i = 0; i < QPL; ++i) {
+            const int c = (lane + 32 * i) * 4;
+            a[i] = on[i] ? Elem<T>::ld4(y + p * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            b[i] = (on[i] && mode != 2) ? Elem<T>::ld4(r + p * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float mean, rstd;
+        if (mode == 0) {
+#pragma unroll
+            for (int i = 0; i < QPL; ++i) {
+                const float4 g4 = G4(i);
+                a[i] = make_float4(round_to<T>(b[i].x + round_to<T>(a[i].x * g4.x)), round_to<T>(b[i].y + round_to<T>(a[i].y * g4.y)),
+                                   round_to<T>(b[i].z + round_to<T>(a[i].z * g4.z)), round_to<T>(b[i].w + round_to<T>(a[i].w * g4.w)));
+                if (on[i]) Elem<T>::st4(out_sum + p * C + (lane + 32 * i) * 4, a[i]);
+            }
+            if (out_norm != nullptr) {
+                reg_stats<QPL>(a, on, C, eps, mean, rstd);
+#pragma unroll
+                for (int i = 0; i < QPL; ++i)
+                    if (on[i]) Elem<T>::st4(out_norm + p * C + (lane + 32 * i) * 4, norm4<T>(a[i], mean, rstd, W4(i), B4(i)));
+            }
+        } else {
+            reg_stats<QPL>(a, on, C, eps, mean, rstd);
+#pragma unroll
+            for (int i = 0; i < QPL; ++i) {
+                float4 n4 = norm4<T>(a[i], mean, rstd, W4(i), B4(i));
+                if (mode == 1) {
+                    const float4 g4 = G4(i);
+                    n4 = make_float4(b[i].x + round_to<T>(n4.x * g4.x), b[i].y + round_to<T>(n4.y * g4.y),
+                                     b[i].z + round_to<T>(n4.z * g4.z), b[i].w + round_to<T>(n4.w * g4.w));
+                }
+                if (on[i]) Elem<T>::st4(out_sum + p * C + (lane + 32 * i) * 4, n4);
+            }
+        }
+    }
+}
+
+// 3x3 depthwise convolution, weights [9][C] staged as fp32 in shared memory once per CTA (every pixel reuses them)
+template <typename T, int QPL>
+__global__ void __launch_bounds__(kLnWarps * 32)
+dwconv3_ln_act_reg_kernel(const T* __restrict__ x, const T* __restrict__ wt, const T* __restrict__ bias,
+                          const T* __restrict__ lw, const T* __restrict__ lb, T* __restrict__ out, int N, int H, int W, int C,
+                          int pad_lo, float eps, int act) {
+    extern __shared__ float swt[];   // [9][C]
+    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) swt[i] = Elem<T>::ld(wt + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool on[QPL];
+#pragma unroll
+    for (int i = 0; i < QPL; ++i) on[i] = (lane + 32 * i) * 4 < C;
+    auto param = [&](const T* base, int i, float fill) {   // (L1-resident after the first pixel)
+        return (on[i] && base) ? Elem<T>::ld4(base + (lane + 32 * i) * 4) : make_float4(fill, fill, fill, fill);
+    };
+    const long long rows = (long long)N * H * W;
+    for (long long p = (long long)blockIdx.x * kLnWarps + warp; p < rows; p += (long long)gridDim.x * kLnWarps) {
+        const int wq = (int)(p % W), hq = (int)((p / W) % H);
+        const long long n = p / ((long long)W * H);
+        bool in[9];
+        long long base[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {   // (warp-uniform border tests)
+            const int yy = hq + t / 3 - pad_lo, xx = wq + t % 3 - pad_lo;
+            in[t] = yy >= 0 && yy < H && xx >= 0 && xx < W;
+            base[t] = ((n * H + yy) * W + xx) * C;
+        }
+        float4 acc[QPL];
+#pragma unroll
+        for (int i = 0; i < QPL; ++i) {
+            const int c = (lane + 32 * i) * 4;
+            float4 v[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t)   // the nine loads of a piece first, then its arithmetic
+                v[t] = (in[t] && on[i]) ? Elem<T>::ld4(x + base[t] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            acc[i] = param(bias, i, 0.f);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float4 k4 = on[i] ? *reinterpret_cast<const float4*>(swt + t * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                acc[i].x = fmaf(v[t].x, k4.x, acc[i].x); acc[i].y = fmaf(v[t].y, k4.y, acc[i].y);
+                acc[i].z = fmaf(v[t].z, k4.z, acc[i].z); acc[i].w = fmaf(v[t].w, k4.w, acc[i].w);
+            }
+            // (the unfused chain stores the convolution result in T before normalising it)
+            acc[i] = make_float4(round_to<T>(acc[i].x), round_to<T>(acc[i].y), round_to<T>(acc[i].z), round_to<T>(acc[i].w));
+        }
+        float mean, rstd;
+        reg_stats<QPL>(acc, on, C, eps, mean, rstd);
+#pragma unroll
+        for (int i = 0; i < QPL; ++i) {
+            float4 o = norm4<T>(acc[i], mean, rstd, param(lw, i, 1.f), param(lb, i, 0.f));
+            if (act == 1) o = make_float4(gelu_erf(o.x), gelu_erf(o.y), gelu_erf(o.z), gelu_erf(o.w));
+            if (on[i]) Elem<T>::st4(out + p * C + (lane + 32 * i) * 4, o);
+        }
+    }
+}
+
+template <typename T, int QPL>
+static cudaError_t launch_ln_join_reg(const void* y, const void* r, const void* gamma, const void* lw, const void* lb, void* out_sum,
+                                      void* out_norm, long long rows, int C, float eps, int mode, cudaStream_t st) {
+    ln_join_reg_kernel<T, QPL><<<ln_grid(rows), kLnWarps * 32, 0, st>>>((const T*)y, (const T*)r, (const T*)gamma, (const T*)lw,
+                                                                        (const T*)lb, (T*)out_sum, (T*)out_norm, rows, C, eps, mode);
+    return cudaGetLastError();
+}
+template <typename T>
+static bool try_ln_join_reg(const void* y, const void* r, const void* gamma, const void* lw, const void* lb, void* out_sum,
+                            void* out_norm, long long rows, int C, float eps, int mode, cudaStream_t st, cudaError_t& e) {
+    if (C <= 128) e = launch_ln_join_reg<T, 1>(y, r, gamma, lw, lb, out_sum, out_norm, rows, C, eps, mode, st);
+    else if (C <= 256) e = launch_ln_join_reg<T, 2>(y, r, gamma, lw, lb, out_sum, out_norm, rows, C, eps, mode, st);
+    else if (C <= 512) e = launch_ln_join_reg<T, 4>(y, r, gamma, lw, lb, out_sum, out_norm, rows, C, eps, mode, st);
+    else if (C <= 1024) e = launch_ln_join_reg<T, 8>(y, r, gamma, lw, lb, out_sum, out_norm, rows, C, eps, mode, st);
+    else return false;
+    return true;
+}
+template <typename T, int QPL>
+static cudaError_t launch_dwconv3_reg(const void* x, const void* wt, const void* bias, const void* lw, const void* lb, void* out,
+                                      int N, int H, int W, int C, int pad_lo, float eps, int act, cudaStream_t st) {
+    const size_t smem = (size_t)9 * C * sizeof(float);
+    dwconv3_ln_act_reg_kernel<T, QPL><<<ln_grid((long long)N * H * W), kLnWarps * 32, smem, st>>>(
+        (const T*)x, (const T*)wt, (const T*)bias, (const T*)lw, (const T*)lb, (T*)out, N, H, W, C, pad_lo, eps, act);
+    return cudaGetLastError();
+}
+template <typename T>
+static bool try_dwconv3_reg(const void* x, const void* wt, const void* bias, const void* lw, const void* lb, void* out, int N, int H,
+                            int W, int C, int k, int pad_lo, float eps, int act, cudaStream_t st, cudaError_t& e) {
+    if (k != 3 || C > 1024) return false;   // (weights in shared memory: 36 KB at 1024 channels)
+    if (C <= 128) e = launch_dwconv3_reg<T, 1>(x, wt, bias, lw, lb, out, N, H, W, C, pad_lo, eps, act, st);
+    else if (C <= 256) e = launch_dwconv3_reg<T, 2>(x, wt, bias, lw, lb, out, N, H, W, C, pad_lo, eps, act, st);
+    else if (C <= 512) e = launch_dwconv3_reg<T, 4>(x, wt, bias, lw, lb, out, N, H, W, C, pad_lo, eps, act, st);
+    else e = launch_dwconv3_reg<T, 8>(x, wt, bias, lw, lb, out, N, H, W, C, pad_lo, eps, act, st);
+    return true;
+}
+
 template <typename K>
 static cudaError_t ensure_row_smem(K kernel, size_t bytes) {
     if (bytes <= 48 * 1024) return cudaSuccess;
@@ -175,6 +356,11 @@ cudaError_t launch_ln_join(const void* y, const void* r, const void* gamma, cons
                            void* out_norm, long long rows, int C, float eps, int mode, int dtype, cudaStream_t st) {
     const size_t smem = (size_t)kLnWarps * C * sizeof(float);
     cudaError_t e;
+    if (dtype == DCNV3_F32 ? try_ln_join_reg<float>(y, r, gamma, lw, lb, out_sum, out_norm, rows, C, eps, mode, st, e)
+                           : try_ln_join_reg<__nv_bfloat16>(y, r, gamma, lw, lb, out_sum, out_norm, rows, C, eps, mode, st, e)) {
+        count_launch(1);
+        return e;
+    }
     if (dtype == DCNV3_F32) {
         if ((e = ensure_row_smem(ln_join_kernel<float>, smem)) != cudaSuccess) return e;
         ln_join_kernel<float><<<ln_grid(rows), kLnWarps * 32, smem, st>>>(
@@ -195,6 +381,11 @@ cudaError_t launch_dwconv_ln_act(const void* x, const void* wt, const void* bias
     const size_t smem = (size_t)kLnWarps * C * sizeof(float);
     const long long rows = (long long)N * H * W;
     cudaError_t e;
+    if (dtype == DCNV3_F32 ? try_dwconv3_reg<float>(x, wt, bias, lw, lb, out, N, H, W, C, k, pad_lo, eps, act, st, e)
+                           : try_dwconv3_reg<__nv_bfloat16>(x, wt, bias, lw, lb, out, N, H, W, C, k, pad_lo, eps, act, st, e)) {
+        count_launch(1);
+        return e;
+    }
     if (dtype == DCNV3_F32) {
         if ((e = ensure_row_smem(dwconv_ln_act_kernel<float>, smem)) != cudaSuccess) return e;
         dwconv_ln_act_kernel<float><<<ln_grid(rows), kLnWarps * 32, smem, st>>>(

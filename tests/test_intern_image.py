@@ -169,15 +169,16 @@ def _rel(a, b):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("c", [72, 200, 448, 896, 1280])   # 1 / 2 / 4 / 8 pieces per lane in registers, row buffer beyond
 @pytest.mark.parametrize("dtype, tol", [(torch.float32, 2e-5), (torch.bfloat16, 3e-2)])
-def test_fused_layer_kernels_match_torch(dtype, tol):
+def test_fused_layer_kernels_match_torch(dtype, tol, c):
     """dcnv3_dwconv_ln_act and dcnv3_layer_join against the torch operations they replace
     (reference layers/dcn_v3/dcn_v3.py:115-117, backbones/intern_image/intern_image_layer.py:126-172)."""
     import torch.nn.functional as F
     from iseg_b200 import _cabi
     torch.manual_seed(3)
     torch.backends.cudnn.allow_tf32 = False
-    n, h, w, c = 2, 13, 17, 72
+    n, h, w = 2, 13, 17
     rnd = lambda *s: torch.randn(*s, device="cuda").to(dtype)  # noqa: E731
     x, r, gamma, lw, lb = rnd(n, h, w, c), rnd(n, h, w, c), rnd(c), rnd(c), rnd(c)
     eps = 1e-6
