@@ -30,6 +30,13 @@ def _conv_same_s2(conv, x_nhwc):
     return conv(x).permute(0, 2, 3, 1)
 
 
+def _layer_norm(norm, x):
+    """LayerNorm over the channels: the one-pass kernel (`dcnv3_layer_join` mode 2) on the inference path, torch otherwise."""
+    if not norm.training and _cabi.fused_layers_usable(x) and norm.weight.dtype == x.dtype:
+        return _cabi.layer_join(x, None, None, norm.weight, norm.bias, norm.eps, 2)
+    return norm(x)
+
+
 def drop_path(x, drop_prob, training):
     """reference utils/drops.py:8-22 (per-sample, training only)."""
     if not training or drop_prob == 0.0:
@@ -50,9 +57,9 @@ class StemLayer(nn.Module):
         self.activation = activation
 
     def forward(self, x):
-        x = self.activation(self.norm1(_conv_same_s2(self.conv1, x)))
+        x = self.activation(_layer_norm(self.norm1, _conv_same_s2(self.conv1, x)))
         mid = x
-        return self.norm2(_conv_same_s2(self.conv2, x)), mid
+        return _layer_norm(self.norm2, _conv_same_s2(self.conv2, x)), mid
 
 
 class DownsampleLayer(nn.Module):
@@ -62,7 +69,7 @@ class DownsampleLayer(nn.Module):
         self.norm = nn.LayerNorm(channels * 2, eps=LN_EPS)
 
     def forward(self, x):
-        return self.norm(_conv_same_s2(self.conv, x))
+        return _layer_norm(self.norm, _conv_same_s2(self.conv, x))
 
 
 class MLPLayer(nn.Module):
@@ -186,9 +193,9 @@ class InternImageBlock(nn.Module):
                 x = blk(x)
                 normed_is_final = False
             if level2:
-                x = self.post_norms[self.post_norm_block_ids.index(i)](x)
+                x = _layer_norm(self.post_norms[self.post_norm_block_ids.index(i)], x)
         if self.norm is not None and not (fused and normed_is_final):
-            x = self.norm(x)
+            x = _layer_norm(self.norm, x)
         before = x
         if self.downsample is not None:
             x = self.downsample(x)
