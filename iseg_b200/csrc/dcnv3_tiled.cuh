@@ -235,9 +235,46 @@ struct Slab<__nv_bfloat16> {
             v[4 * k + 3] = bf16x2_to_f2(r.w);
         }
     }
+    // the same 16 channels left packed: word 4k+j = channels (2j, 2j+1) of rotated piece k
+    static __device__ __forceinline__ void load_packed(const unsigned char* base, int rot, unsigned (&v)[8]) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint4 r = *reinterpret_cast<const uint4*>(base + (((k + rot) & 1) << 4));
+            v[4 * k + 0] = r.x; v[4 * k + 1] = r.y; v[4 * k + 2] = r.z; v[4 * k + 3] = r.w;
+        }
+    }
     static __device__ __forceinline__ int rot_of(int px) { return px & 1; }
     static __device__ __forceinline__ int chan_of(int k, int rot) { return ((k + rot) & 1) * 8; }
 };
+
+// ---- bf16 operands straight from their packed words (PTX fma.rn.f32.bf16, SASS FHFMA.BF16, sm_100+): the
+//      product of two bf16 values is exact in fp32 and the accumulator is fp32, so a packed slab needs no
+//      shift / mask instructions to become fp32 pairs first (those were 28 % of the bf16 forward's instructions).
+//      Gather kernel: slab x grad_out, both bf16 tensors -- bit-identical to the unpacked FFMA2 form.
+//      Forward: the second operand is the tap's corner weight (bilinear weight x mask, computed in fp32), rounded
+//      ONCE to bf16 -- the operand precision of a bf16 tensor-core product, and finer than the reference, which
+//      under mixed_bfloat16 rounds the bilinear weight, the mask product and every partial sum to bf16
+//      (utils.py:195-206).  Measured against the fp32 oracle on bf16 inputs: rms 1.66e-3 -> 2.19e-3 of rms(out),
+//      max 3.5e-3 -> 4.6e-3 of max|out| (the output's own rounding to bf16 is the 1.66e-3); bar 1e-2.
+//      -DDCNV3_BF16_MIXED=0 / -DDCNV3_BF16_FWD_W=0 rebuild the unpacked forms (profiles/r02_ab.md has the A/B).
+#ifndef DCNV3_BF16_MIXED
+#define DCNV3_BF16_MIXED 1
+#endif
+#ifndef DCNV3_BF16_FWD_W
+#define DCNV3_BF16_FWD_W 1
+#endif
+// HV / HW = 0 / 1 pick the low / high half of v and of w
+template <int HV, int HW>
+__device__ __forceinline__ void fhfma_x(float& acc, unsigned v, unsigned w) {
+    if (HV == 0 && HW == 0)
+        asm("{\n.reg .b16 a, b, c, d;\nmov.b32 {a, b}, %1;\nmov.b32 {c, d}, %2;\nfma.rn.f32.bf16 %0, a, c, %0;\n}" : "+f"(acc) : "r"(v), "r"(w));
+    else if (HV == 1 && HW == 0)
+        asm("{\n.reg .b16 a, b, c, d;\nmov.b32 {a, b}, %1;\nmov.b32 {c, d}, %2;\nfma.rn.f32.bf16 %0, b, c, %0;\n}" : "+f"(acc) : "r"(v), "r"(w));
+    else if (HV == 0 && HW == 1)
+        asm("{\n.reg .b16 a, b, c, d;\nmov.b32 {a, b}, %1;\nmov.b32 {c, d}, %2;\nfma.rn.f32.bf16 %0, a, d, %0;\n}" : "+f"(acc) : "r"(v), "r"(w));
+    else
+        asm("{\n.reg .b16 a, b, c, d;\nmov.b32 {a, b}, %1;\nmov.b32 {c, d}, %2;\nfma.rn.f32.bf16 %0, b, d, %0;\n}" : "+f"(acc) : "r"(v), "r"(w));
+}
 
 // global 16-byte piece <-> packed pairs (PAIRS = 2 for fp32, 4 for bf16)
 template <typename T>

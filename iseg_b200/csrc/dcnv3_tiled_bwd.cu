@@ -286,6 +286,7 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
                   const SideT<T> side_t, const KParams q, const TileGeom tg) {
     using C = Chunk<T>;
     using RS = RowStage<T>;
+    constexpr bool MIXED = sizeof(T) == 2 && DCNV3_BF16_MIXED;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ __align__(8) uint64_t sbar[kTiledWarps];
@@ -343,10 +344,24 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
             const size_t pg = (pix0 + min(px_l, npx - 1)) * q.G + g;
             const T* offp = offset + pg * 18;
             const T* mskp = mask + pg * 9;
-            f2 go[8];
+            // bf16: grad_out stays packed (gw) and meets the packed slabs in FHFMA; fp32: pairs (go)
+            f2 go[MIXED ? 1 : 8];
+            unsigned gw[MIXED ? 8 : 1];
+            if constexpr (MIXED) {
 #pragma unroll
-            for (int pc = 0; pc < C::NPIECE; ++pc)
-                load_piece<T>(grad_out + pg * kGC + Slab<T>::chan_of(pc, rot), go + pc * C::PAIRS);
+                for (int pc = 0; pc < C::NPIECE; ++pc) {
+                    const uint4 r = __ldg(reinterpret_cast<const uint4*>(grad_out + pg * kGC + Slab<T>::chan_of(pc, rot)));
+                    gw[4 * pc + 0] = r.x; gw[4 * pc + 1] = r.y; gw[4 * pc + 2] = r.z; gw[4 * pc + 3] = r.w;
+                }
+            } else {
+#pragma unroll
+                for (int pc = 0; pc < C::NPIECE; ++pc)
+                    load_piece<T>(grad_out + pg * kGC + Slab<T>::chan_of(pc, rot), go + pc * C::PAIRS);
+            }
+            auto go_pair = [&](int c) -> f2 {
+                if constexpr (MIXED) return bf16x2_to_f2(gw[c]);
+                else return go[c];
+            };
             float ref0, ref1;
             ref_point(q, h, w, ref0, ref1);
             // centre-feature-scale blend around the op (dcn_v3.py:146): the core's output gradient is go * (1 - s)
@@ -408,11 +423,32 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
                             f2 v[C::PAIRS];
                             load_piece<T>(src + Slab<T>::chan_of(pc, rot), v);
 #pragma unroll
-                            for (int j = 0; j < C::PAIRS; ++j) ffma2v(dk2, v[j], go[pc * C::PAIRS + j]);
+                            for (int j = 0; j < C::PAIRS; ++j) ffma2v(dk2, v[j], go_pair(pc * C::PAIRS + j));
                         }
                         const float dk = lo_of(dk2) + hi_of(dk2);
                         if (kk == 0) d0 = dk; else if (kk == 1) d1 = dk; else if (kk == 2) d2 = dk; else d3 = dk;
                     }
+                } else if constexpr (MIXED) {
+                    // two chains per corner (even / odd channels), the association of the FFMA2 form below
+                    const unsigned char* a = sbase + (size_t)(t.alive ? by * tg.bw + bx : 0) * kCellBytes;
+                    unsigned va[8], vb[8];
+                    float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+                    Slab<T>::load_packed(a, rot, va);
+                    Slab<T>::load_packed(a + (size_t)tg.bw * kCellBytes, rot, vb);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) { fhfma_x<0, 0>(e0, va[c], gw[c]); fhfma_x<1, 1>(o0, va[c], gw[c]); }
+                    Slab<T>::load_packed(a + kCellBytes, rot, va);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) { fhfma_x<0, 0>(e1, vb[c], gw[c]); fhfma_x<1, 1>(o1, vb[c], gw[c]); }
+                    Slab<T>::load_packed(a + (size_t)(tg.bw + 1) * kCellBytes, rot, vb);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) { fhfma_x<0, 0>(e2, va[c], gw[c]); fhfma_x<1, 1>(o2, va[c], gw[c]); }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) { fhfma_x<0, 0>(e3, vb[c], gw[c]); fhfma_x<1, 1>(o3, vb[c], gw[c]); }
+                    d0 = e0 + o0;
+                    d1 = e1 + o1;
+                    d2 = e2 + o2;
+                    d3 = e3 + o3;
                 } else {
                     const unsigned char* a = sbase + (size_t)(t.alive ? by * tg.bw + bx : 0) * kCellBytes;
                     f2 va[8], vb[8], e0 = 0ull, e1 = 0ull, e2 = 0ull, e3 = 0ull;
@@ -453,8 +489,10 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
             //  the first tap's dot products, behind its coordinate arithmetic and shared-memory loads)
             // ... of what the scatter kernel will convert: RN(grad_out * (1 - s)), the same product there
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                amax = max(amax, max(abs_bits(__fmul_rn(lo_of(go[c]), oms)), abs_bits(__fmul_rn(hi_of(go[c]), oms))));
+            for (int c = 0; c < 8; ++c) {
+                const f2 gc2 = go_pair(c);
+                amax = max(amax, max(abs_bits(__fmul_rn(lo_of(gc2), oms)), abs_bits(__fmul_rn(hi_of(gc2), oms))));
+            }
             if (BLEND) {
                 // d s = sum_c grad_out[c] * (x_proj[c] - core[c]) = <grad_out, x_proj> - sum_p m_p * dL/dm_p
                 f2 dx2 = 0ull;
@@ -463,7 +501,7 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
                     f2 xo[C::PAIRS];
                     load_piece<T>(x + pg * kGC + Slab<T>::chan_of(pc, rot), xo);
 #pragma unroll
-                    for (int j = 0; j < C::PAIRS; ++j) ffma2v(dx2, xo[j], go[pc * C::PAIRS + j]);
+                    for (int j = 0; j < C::PAIRS; ++j) ffma2v(dx2, xo[j], go_pair(pc * C::PAIRS + j));
                 }
                 if (px_l < npx && chunk * C::GQ + g_l < q.G)
                     Elem<T>::st(reinterpret_cast<T*>(q.grad_cfs) + pg, lo_of(dx2) + hi_of(dx2) - gm_dot_m);

@@ -30,6 +30,7 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                  T* __restrict__ out, const KParams q, const TileGeom tg) {
     using C = Chunk<T>;
     using RS = RowStage<T>;
+    constexpr bool WMIX = sizeof(T) == 2 && DCNV3_BF16_FWD_W;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ __align__(8) uint64_t sbar[kTiledWarps];
@@ -94,8 +95,13 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 else softmax_stats9<T>(mskp, mx, inv_sum);
             }
             f2 acc[8];
+            float facc[WMIX ? 16 : 1];
 #pragma unroll
             for (int c = 0; c < 8; ++c) acc[c] = 0ull;
+            if constexpr (WMIX) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) facc[c] = 0.f;
+            }
             float ox, oy, ml, ox2 = 0.f, oy2 = 0.f, ml2 = 0.f;
             if (STAGED) {
                 RS::tap(st, lane, 0, ox, oy, ml);
@@ -137,6 +143,23 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                             for (int j = 0; j < C::PAIRS; ++j) ffma2s(acc[pc * C::PAIRS + j], v[j], wk);
                         }
                     }
+                } else if constexpr (WMIX) {
+                    // bf16 weights meet the packed slabs in FHFMA (fp32 accumulators)
+                    const unsigned char* a = sbase + (size_t)(t.alive ? by * tg.bw + bx : 0) * kCellBytes;
+                    unsigned va[8], vb[8];
+                    const unsigned wab = pack_bf16x2(wa, wb_), wcd = pack_bf16x2(wc, wd);
+                    Slab<T>::load_packed(a, rot, va);
+                    Slab<T>::load_packed(a + (size_t)tg.bw * kCellBytes, rot, vb);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) { fhfma_x<0, 0>(facc[2 * c], va[c], wab); fhfma_x<1, 0>(facc[2 * c + 1], va[c], wab); }
+                    Slab<T>::load_packed(a + kCellBytes, rot, va);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) { fhfma_x<0, 1>(facc[2 * c], vb[c], wab); fhfma_x<1, 1>(facc[2 * c + 1], vb[c], wab); }
+                    Slab<T>::load_packed(a + (size_t)(tg.bw + 1) * kCellBytes, rot, vb);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) { fhfma_x<0, 0>(facc[2 * c], va[c], wcd); fhfma_x<1, 0>(facc[2 * c + 1], va[c], wcd); }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) { fhfma_x<0, 1>(facc[2 * c], vb[c], wcd); fhfma_x<1, 1>(facc[2 * c + 1], vb[c], wcd); }
                 } else {
                     // dead taps carry zero weights and read cell 0
                     const unsigned char* a = sbase + (size_t)(t.alive ? by * tg.bw + bx : 0) * kCellBytes;
@@ -154,6 +177,11 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
                     for (int c = 0; c < 8; ++c) ffma2s(acc[c], vb[c], wd);
                 }
+            }
+            if constexpr (WMIX) {  // (acc holds what the rare out-of-box taps added)
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    acc[c] = pack2(lo_of(acc[c]) + facc[2 * c], hi_of(acc[c]) + facc[2 * c + 1]);
             }
             if (STAGED) {
                 // every lane has consumed its slot values (they fed the arithmetic above): refill for the next iteration
