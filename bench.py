@@ -272,7 +272,8 @@ def bf16_parity_numbers():
     worst["fixtures"] = len(files)
     worst["note"] = ("bf16 tensors: DCNV3_FLAG_REF_DTYPE rounds every intermediate to bf16 like the reference under "
                      "mixed_bfloat16 (<= 1e-2 bar); the default bf16 mode -- the one benchmarked -- keeps coordinates and "
-                     "accumulation in fp32 and is held to 1e-2 against the fp32 oracle on the bf16-rounded inputs instead")
+                     "accumulation in fp32 (forward: each finished corner weight rounded once to bf16 for its FHFMA product) and is "
+                     "held to 1e-2 against the fp32 oracle on the bf16-rounded inputs instead")
     return worst
 
 
