@@ -49,7 +49,11 @@ def inference_with_sliding_window(model_fn, image, crop_h=769, crop_w=769, strat
 
     image: [N, H, W, C] on this rank's device (every rank holds the full image, as every replica does in
     the reference); model_fn maps a [N, h, w, C] tile to [N, h, w, K] logits.  Every rank returns the full
-    [N, H, W, K] result: per-rank partial sums and the count map are combined by ONE all-reduce."""
+    [N, H, W, K] result: per-rank partial sums and the count map are combined by ONE all-reduce.
+
+    All windows of an image have the same shape, so a model_fn wrapped in
+    iseg_b200.backbones.intern_image.GraphedInference runs as one CUDA graph replayed per tile (batch-1 tiles are
+    launch bound: 66 -> 20 ms per 1024x2048 image with InternImage-T on one B200, tools/config_bench.py cfg5)."""
     import torch.distributed as dist
 
     n, height, width, _ = image.shape

@@ -133,6 +133,18 @@ def test_sliding_window_with_intern_image_tiles_matches_reference_rule():
     ref = acc / cnt
     assert torch.isfinite(out).all() and (out - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
 
+    # every window has the same shape: the tile network as ONE CUDA graph, replayed per tile -- same numbers
+    from iseg_b200.backbones.intern_image import GraphedInference
+
+    class TileNet(torch.nn.Module):
+        def forward(self, tile):
+            return model_fn(tile)
+
+    graphed = GraphedInference(TileNet().eval())
+    with torch.no_grad():
+        out_g = inference_with_sliding_window(graphed, image, crop_h=crop, crop_w=crop)
+    assert len(graphed._graphs) == 1 and torch.equal(out_g, out)
+
 
 @pytest.mark.gpu
 def test_graphed_inference_matches_eager():
