@@ -100,8 +100,8 @@ static int check_ptr_align(const void* ptr, const char* name, size_t align = 16)
 
 // is the centre-feature-scale blend available for these parameters?  (fused into the tiled kernels only)
 static bool blend_supported(const dcnv3_params* p) {
-    const KParams q = derive(p);
-    return tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC) && !ref_dtype_mode(p);
+    const KParams q = derive(p);  // (32 channels per group run the tiled kernels as half groups, without the blend)
+    return p->group_channels == 16 && tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC) && !ref_dtype_mode(p);
 }
 
 static int forward_impl(const void* x, const void* offset, const void* mask, void* out,

@@ -31,6 +31,11 @@ struct KParams {
     float scale;           // offset_scale
     float fx, fy;          // d xq/d offset0 = (W_in-2)*s/W_in ; d yq/d offset1 = (H_in-2)*s/H_in
     unsigned flags;
+    // Tiled kernels on 32 channels per group (InternImage-H): every group is run as two 16-channel half groups
+    // that share the group's offsets and mask.  gsh = 1 then, G counts the HALF groups (x / out / grad_x are
+    // addressed with it unchanged: channel = g*16 + k) and the side tensors are indexed with g >> gsh among
+    // G >> gsh groups per pixel (side_entry below).  0 everywhere else.
+    int gsh;
     // centre-feature-scale blend fused around the op (reference layers/dcn_v3/dcn_v3.py:138-146; tiled kernels
     // only): out = core * (1 - s) + x * s with s = cfs[n, h, w, g] broadcast over the group's channels.
     // NULL = plain op.  grad_cfs is written by the gather kernel.
@@ -39,6 +44,17 @@ struct KParams {
     float gs0[DCNV3_MAX_TAPS];  // (dx_p / W_in) * s   -- grid*offset_scale, channel 0 (op.py:82)
     float gs1[DCNV3_MAX_TAPS];  // (dy_p / H_in) * s
 };
+
+// (pixel, group) entry of offset / mask / their gradients for pixel index `pixel` and kernel-side group g
+__host__ __device__ __forceinline__ size_t side_entry(const KParams& q, size_t pixel, int g) {
+    return pixel * (size_t)(q.G >> q.gsh) + (size_t)(g >> q.gsh);
+}
+// the view of the parameters the tiled kernels run on (see KParams::gsh)
+static inline KParams tiled_view(const KParams& q) {
+    KParams v = q;
+    if (q.gc == 32 && q.gsh == 0) { v.G = q.G * 2; v.gc = 16; v.gsh = 1; }
+    return v;
+}
 
 struct Tap {
     int x0, y0;        // clipped lower corner (x1 = x0+1, y1 = y0+1 whenever the tap is alive)

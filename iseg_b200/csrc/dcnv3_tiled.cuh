@@ -440,6 +440,26 @@ struct RowStage {
         }
         __syncwarp();
     }
+    // The same for half groups (KParams::gsh = 1): slot entries 2r and 2r+1 of a pixel hold identical results of group
+    // r; the even one is stored.  G / ng = whole groups per pixel / in this chunk; off_row / msk_row = the first
+    // pixel's run of this chunk's whole groups.
+    static __device__ __forceinline__ void store_off_msk_halves(const unsigned char* st, T* off_row, T* msk_row, int G,
+                                                                int npx, int ng, int lane) {
+        __syncwarp();
+        const size_t off_stride = (size_t)G * 18 * sizeof(T), msk_stride = (size_t)G * 9 * sizeof(T);
+        const int ro = ng * 18, rm = ng * 9;  // elements per pixel
+        for (int c = lane; c < npx * ro; c += 32) {
+            const int px = c / ro, r = c - px * ro, gr = r / 18, e = r - gr * 18;
+            reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(off_row) + px * off_stride)[r] =
+                reinterpret_cast<const T*>(st + px * OFF_PX + 2 * gr * LANE_OFF)[e];
+        }
+        for (int c = lane; c < npx * rm; c += 32) {
+            const int px = c / rm, r = c - px * rm, gr = r / 9, e = r - gr * 9;
+            reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(msk_row) + px * msk_stride)[r] =
+                reinterpret_cast<const T*>(st + OFF_BYTES + px * MSK_PX + 2 * gr * LANE_MSK)[e];
+        }
+        __syncwarp();
+    }
 };
 
 // Per-tap inputs of one (pixel, group): the offset pair and the mask value (or logit) of tap p.

@@ -341,9 +341,10 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
             const int npx = min(C::PXW, ctx.w0 + ctx.tw - wb);
             const int w = wb + min(px_l, npx - 1);  // idle lanes shadow the last pixel (their slots are never stored)
             const size_t pix0 = ((size_t)n * q.ho + h) * q.wo + wb;
-            const size_t pg = (pix0 + min(px_l, npx - 1)) * q.G + g;
-            const T* offp = offset + pg * 18;
-            const T* mskp = mask + pg * 9;
+            // (half groups -- KParams::gsh -- never run the staged instance: it stays free of their arithmetic)
+            const size_t pg = (pix0 + min(px_l, npx - 1)) * q.G + g, ps = STAGED ? pg : side_entry(q, pix0 + min(px_l, npx - 1), g);
+            const T* offp = offset + ps * 18;
+            const T* mskp = mask + ps * 9;
             // bf16: grad_out stays packed (gw) and meets the packed slabs in FHFMA; fp32: pairs (go)
             f2 go[MIXED ? 1 : 8];
             unsigned gw[MIXED ? 8 : 1];
@@ -367,7 +368,7 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
             // centre-feature-scale blend around the op (dcn_v3.py:146): the core's output gradient is go * (1 - s)
             float cs = 0.f, oms = 1.f;
             if (BLEND) {
-                cs = Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + pg);
+                cs = Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + ps);
                 oms = __fsub_rn(1.0f, cs);
             }
             // this lane's entries of the transposed side copy (real pixels and real groups only)
@@ -469,6 +470,12 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
                     d2 = lo_of(e2) + hi_of(e2);
                     d3 = lo_of(e3) + hi_of(e3);
                 }
+                if (!STAGED && q.gsh) {  // half groups: the group's dot products are the sums over its two halves (adjacent lanes)
+                    d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+                    d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+                    d2 += __shfl_xor_sync(0xffffffffu, d2, 1);
+                    d3 += __shfl_xor_sync(0xffffffffu, d3, 1);
+                }
                 // dead taps have all four deltas zero => zero gradients
                 // (the dot products are taken with the unscaled grad_out; (1 - s) is applied to the results)
                 const float g_m = t.dx1 * t.dy1 * d0 + t.dx1 * t.dy0 * d1 + t.dx0 * t.dy1 * d2 + t.dx0 * t.dy0 * d3;
@@ -524,8 +531,12 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
                                   npx, lane);
                 if (it + kTiledWarps < ctx.nit) request(ctx, it + kTiledWarps);  // the slot is free again
             } else {
-                RS::store_off_msk(st, grad_offset + (pix0 * q.G + chunk * C::GQ) * 18,
-                                  grad_mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, npx, ng, lane);
+                if (q.gsh)  // both halves of a group hold the same results: the even half's are stored
+                    RS::store_off_msk_halves(st, grad_offset + side_entry(q, pix0, chunk * C::GQ) * 18,
+                                             grad_mask + side_entry(q, pix0, chunk * C::GQ) * 9, q.G >> 1, npx, ng >> 1, lane);
+                else
+                    RS::store_off_msk(st, grad_offset + (pix0 * q.G + chunk * C::GQ) * 18,
+                                      grad_mask + (pix0 * q.G + chunk * C::GQ) * 9, q.G, npx, ng, lane);
             }
         }
         if (!waited) mbar_wait(&bar, 0);  // never leave with a TMA in flight
@@ -601,7 +612,7 @@ __device__ __forceinline__ void side_add(const FarWs& ws, size_t cellg, const in
 // kernel's walk below, per-tap loop, inputs straight from the reference-layout tensors):
 //   MODE 1 (pass 1): rebuilds the weight counters exactly as the scatter kernel left them
 //   MODE 2 (pass 2): landings on hot cells of the box -> 64-bit side buffer
-template <typename T, int MODE, int TJ>
+template <typename T, int MODE, int TJ, bool SPLIT = true>  // SPLIT: half groups possible (KParams::gsh read at run time)
 __device__ __forceinline__ void redo_walk(int* wsum, const T* __restrict__ offset, const T* __restrict__ mask,
                                           const T* __restrict__ grad_out, const FarWs& ws, const KParams& q,
                                           const TileBox& box, int n, int chunk, Range hh, Range hw, int eg) {
@@ -624,9 +635,10 @@ __device__ __forceinline__ void redo_walk(int* wsum, const T* __restrict__ offse
         if (pix >= npix) continue;
         const int row = pix / nw;
         const int h = hh.lo + row, w = hw.lo + (pix - row * nw);
-        const size_t pg = (((size_t)n * q.ho + h) * q.wo + w) * q.G + g;
-        const T* offp = offset + pg * 18;
-        const T* mskp = mask + pg * 9;
+        const size_t pixel = ((size_t)n * q.ho + h) * q.wo + w;
+        const size_t pg = pixel * q.G + g, ps = SPLIT ? side_entry(q, pixel, g) : pg;
+        const T* offp = offset + ps * 18;
+        const T* mskp = mask + ps * 9;
         int G[16];
         bool have_g = false;
         float mx = 0.f, inv_sum = 1.f;
@@ -717,9 +729,10 @@ __device__ __forceinline__ void scatter_walk_per_tap(int* acc, int* wsum, const 
         if (pix >= npix) continue;
         const int row = pix / nw;
         const int h = hh.lo + row, w = hw.lo + (pix - row * nw);
-        const size_t pg = (((size_t)n * q.ho + h) * q.wo + w) * q.G + g;
-        const T* offp = offset + pg * 18;
-        const T* mskp = mask + pg * 9;
+        const size_t pixel = ((size_t)n * q.ho + h) * q.wo + w;
+        const size_t pg = pixel * q.G + g, ps = side_entry(q, pixel, g);
+        const T* offp = offset + ps * 18;
+        const T* mskp = mask + ps * 9;
         float ox, oy, ml, ox2, oy2, ml2;
         load_tap_inputs<T>(offp, mskp, p_lo, ox, oy, ml);
         load_tap_inputs<T>(offp, mskp, min(p_lo + 1, kTaps - 1), ox2, oy2, ml2);
@@ -1018,14 +1031,14 @@ __device__ __forceinline__ void scatter_walk_batched(int* acc, int* wsum, const 
 // recomputes them itself, right after its flush: the landings on hot cells go to the 64-bit side buffer (pass 2 of the
 // redo; the weight counters of pass 1 are still in shared memory), and are then converted and added to what the flush
 // left in grad_x (0, or the blend's direct term).  Leaves the side buffer zero again.
-template <typename T, int TJ>
+template <typename T, int TJ, bool SPLIT = true>
 __device__ __forceinline__ void redo_own_tile(int* wsum, const T* __restrict__ offset, const T* __restrict__ mask,
                                               const T* __restrict__ grad_out, T* __restrict__ grad_x, const FarWs& ws,
                                               const KParams& q, const TileBox& box, int n, int chunk, Range hh, Range hw,
                                               int eg) {
     constexpr int PITCH = ScatterShape<TJ>::PITCH;
     constexpr int WP = ScatterShape<TJ>::WPITCH;
-    redo_walk<T, 2, TJ>(wsum, offset, mask, grad_out, ws, q, box, n, chunk, hh, hw, eg);
+    redo_walk<T, 2, TJ, SPLIT>(wsum, offset, mask, grad_out, ws, q, box, n, chunk, hh, hw, eg);
     __threadfence();
     __syncthreads();
     const size_t img_pixels = (size_t)q.h * q.w;
@@ -1215,7 +1228,7 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
     if (!PER_TAP && bg.tiles_x * bg.tiles_y == 1) {
         // whole-image tile: hot cells are redone here and this kernel is the last one of the call
         if (__syncthreads_or(any_hot) && !nonfinite)
-            redo_own_tile<T, TJ>(wsum, offset, mask, grad_out, grad_x, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
+            redo_own_tile<T, TJ, false>(wsum, offset, mask, grad_out, grad_x, ws, q, box, n, chunk, s_home_h, s_home_w, eg);
         finalize_workspace(ws, q.n);
     } else if (any_hot) {
         ws.redo[blockIdx.x] = 1;
@@ -1374,9 +1387,10 @@ static BwdGeom make_bwd_geom(const KParams& q) {
 static size_t flag_bytes(size_t count) { return (count * sizeof(int) + 255) / 256 * 256; }
 static size_t dirty_bytes(const KParams& q) { return ((size_t)q.n * q.h * q.w * q.G + 255) / 256 * 256; }
 
-size_t bwd_tiled_scratch_bytes(const KParams& q, int dtype) { return side_t_bytes(q, dtype); }
+size_t bwd_tiled_scratch_bytes(const KParams& q, int dtype) { return side_t_bytes(tiled_view(q), dtype); }
 
-size_t bwd_tiled_workspace_bytes(const KParams& q) {
+size_t bwd_tiled_workspace_bytes(const KParams& q_in) {
+    const KParams q = tiled_view(q_in);
     const size_t tiles = (size_t)q.n * ((q.w + 15) / 16) * ((q.h + 15) / 16);  // upper bound (16x16 tiles)
     const size_t chunks = (size_t)(q.G + 1) / 2;
     return sizeof(WsHeader) + img_max_bytes(q.n) + dirty_bytes(q) + flag_bytes(tiles * chunks) +
@@ -1406,7 +1420,7 @@ static cudaError_t launch_scatter(const T* offset, const T* mask, const T* grad_
         blend ? bwd_scatter_kernel<T, TJ, true, true> : bwd_scatter_kernel<T, TJ, false, true>;
     bool per_tap = true;
     if constexpr (sizeof(T) == 4) {
-        per_tap = bg.narrow != 0;
+        per_tap = bg.narrow != 0 || q.gsh != 0;  // (half groups: only the per-tap walk and the redo kernel index them)
         if (!per_tap) kernel = blend ? bwd_scatter_kernel<T, TJ, true, false> : bwd_scatter_kernel<T, TJ, false, false>;
     }
     const unsigned threads = per_tap ? S::THREADS_PER_TAP : S::THREADS;
@@ -1449,7 +1463,7 @@ static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const v
     {
         const size_t entries = (size_t)q.n * ((q.G + 1) / 2) * kTaps * q.h * q.w * 2;
         // (no copy where the per-tap walk runs: it reads the reference-layout tensors)
-        side_t.off = (kUseSideT<T> && !bg.narrow) ? (typename SideT<T>::Pair*)scratch : nullptr;
+        side_t.off = (kUseSideT<T> && !bg.narrow && !q.gsh) ? (typename SideT<T>::Pair*)scratch : nullptr;
         side_t.msk = (T*)((char*)scratch + (entries * 2 * sizeof(T) + 255) / 256 * 256);
         side_t.cs = (q.G + 1) / 2;
         side_t.hw = q.h * q.w;
@@ -1510,7 +1524,8 @@ static cudaError_t launch_bwd_tiled_t(const void* x, const void* offset, const v
     return cudaGetLastError();
 }
 
-void bwd_tiled_plan(const KParams& q, int dtype, int out[16]) {
+void bwd_tiled_plan(const KParams& q_in, int dtype, int out[16]) {
+    const KParams q = tiled_view(q_in);
     gather_tiled_plan(q, dtype, kTiledWarps * (dtype == DCNV3_F32 ? kGatherStageBytes<float> : kGatherStageBytes<__nv_bfloat16>), out);
     const BwdGeom bg = make_bwd_geom(q);
     out[8] = bg.tj; out[9] = bg.ring_lo; out[10] = bg.ring_hi; out[11] = bg.box_rows;
@@ -1522,8 +1537,9 @@ void bwd_tiled_plan(const KParams& q, int dtype, int out[16]) {
 }
 
 cudaError_t launch_bwd_tiled(const void* x, const void* offset, const void* mask, const void* grad_out,
-                             void* grad_x, void* grad_offset, void* grad_mask, void* ws, void* scratch, const KParams& q,
+                             void* grad_x, void* grad_offset, void* grad_mask, void* ws, void* scratch, const KParams& q_in,
                              int dtype, bool ws_clean, cudaStream_t st) {
+    const KParams q = tiled_view(q_in);
     return dtype == DCNV3_F32
                ? launch_bwd_tiled_t<float>(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, scratch, q, dtype, ws_clean, st)
                : launch_bwd_tiled_t<__nv_bfloat16>(x, offset, mask, grad_out, grad_x, grad_offset, grad_mask, ws, scratch, q, dtype, ws_clean, st);

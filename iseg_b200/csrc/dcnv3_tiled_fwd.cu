@@ -78,9 +78,10 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             const int npx = min(C::PXW, ctx.w0 + ctx.tw - wb);
             const bool valid = real_g && px_l < npx;
             const int w = wb + min(px_l, npx - 1);  // idle lanes shadow the last pixel (loads stay in bounds)
-            const size_t pg = (((size_t)n * q.ho + h) * q.wo + w) * q.G + g;
-            const T* offp = offset + pg * 18;
-            const T* mskp = mask + pg * 9;
+            const size_t pixel = ((size_t)n * q.ho + h) * q.wo + w;
+            const size_t pg = pixel * q.G + g, ps = STAGED ? pg : side_entry(q, pixel, g);  // (half groups are never staged)
+            const T* offp = offset + ps * 18;
+            const T* mskp = mask + ps * 9;
             float ref0, ref1;
             ref_point(q, h, w, ref0, ref1);
             if (STAGED) {
@@ -192,7 +193,7 @@ fwd_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 if (q.cfs != nullptr) {
                     // centre-feature-scale blend (dcn_v3.py:146): core * (1 - s) + x_proj * s, the reference's three
                     // separately rounded operations; x_proj is this pixel's own slab of x (ho == h, wo == w here)
-                    const float s = Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + pg);
+                    const float s = Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + ps);
                     const float oms = __fsub_rn(1.0f, s);
 #pragma unroll
                     for (int pc = 0; pc < C::NPIECE; ++pc) {
@@ -304,7 +305,7 @@ bool make_x_tensor_map(CUtensorMap* map, const void* x, const KParams& q, int dt
 // pixels of one warp iteration.  (The mask's 72-byte runs are not a legal box width; see RowStage.)
 bool side_stageable(const KParams& q, int dtype) {
     const int gq = dtype == DCNV3_F32 ? 2 : 4;
-    return q.G % gq == 0 && (long long)q.n * q.ho < (1ll << 31);
+    return q.gsh == 0 && q.G % gq == 0 && (long long)q.n * q.ho < (1ll << 31);  // (half groups: 72-byte runs, no TMA box)
 }
 bool make_side_tensor_map(CUtensorMap* map, const void* base, const KParams& q, int dtype, int per_group) {
     const cuuint64_t es = dtype == DCNV3_F32 ? 4 : 2;
@@ -384,7 +385,8 @@ static int fwd_box_bytes(const KParams& q, int dtype) { return side_stageable(q,
 
 // Tiled kernels serve the InternImage configuration only -- and only images whose tile boxes fit shared
 // memory (everything but extreme aspect ratios at large offset_scale); the rest runs the generic kernels.
-bool tiled_applicable(const KParams& q, int dtype) {
+bool tiled_applicable(const KParams& q_in, int dtype) {
+    const KParams q = tiled_view(q_in);  // (32 channels per group run as half groups)
     // any group count: the last chunk may be partly empty (phantom groups are masked)
     if (!(q.P == 9 && q.kh == 3 && q.sh == 1 && q.sw == 1 && q.dh == 1 && q.dw == 1 && q.gc == kGC && q.ho == q.h &&
           q.wo == q.w && q.ph == 1 && q.pw == 1 && q.scale > 0.f && q.scale <= 16.f && q.h <= 16384 && q.w <= 16384 &&
@@ -431,7 +433,8 @@ static void geom_numbers(const KParams& q, const TileGeom& tg, long long smem, i
     out[7] = (int)smem;
 }
 
-void fwd_tiled_plan(const KParams& q, int dtype, int out[8]) {
+void fwd_tiled_plan(const KParams& q_in, int dtype, int out[8]) {
+    const KParams q = tiled_view(q_in);
     const TileGeom tg = make_geom(q, dtype, 16, 16, 3.0f, fwd_box_bytes(q, dtype) / kCellBytes);
     const int slot = dtype == DCNV3_F32 ? RowStage<float>::BYTES : RowStage<__nv_bfloat16>::BYTES;
     geom_numbers(q, tg, (long long)tg.bw * tg.bh * kCellBytes + (side_stageable(q, dtype) ? kTiledWarps * slot : 0), out);
@@ -443,7 +446,8 @@ void gather_tiled_plan(const KParams& q, int dtype, int stage_bytes, int out[8])
 }
 
 cudaError_t launch_fwd_tiled(const void* x, const void* offset, const void* mask, void* out,
-                             const KParams& q, int dtype, cudaStream_t st) {
+                             const KParams& q_in, int dtype, cudaStream_t st) {
+    const KParams q = tiled_view(q_in);
     return dtype == DCNV3_F32 ? launch_fwd_tiled_t<float>(x, offset, mask, out, q, dtype, st)
                               : launch_fwd_tiled_t<__nv_bfloat16>(x, offset, mask, out, q, dtype, st);
 }

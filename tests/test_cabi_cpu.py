@@ -148,6 +148,17 @@ def test_launch_plans_fit_the_hardware_for_any_shape(cabi):
         if scale == 1.0:
             assert plan["scatter"]["ring_lo"] == 4 and plan["scatter"]["ring_hi"] == 5
             assert plan["forward"]["halo_x"] == (4 if h == w else 3)  # (a 2:1 image gives up a little reach to fit 82 KB)
+    # 32 channels per group (InternImage-H): the tiled kernels run every group as two 16-channel half groups, so the
+    # plan is that of twice the groups at 16 channels -- except that the side inputs are not staged (72-byte runs)
+    for dtype in (cabi.F32, cabi.BF16):
+        p32 = cabi.make_params((16, 40, 40, 40 * 32), (40, 40), (3, 3), (1, 1), (1, 1), (1, 1), 40, 32, 2.0, dtype)
+        p16 = cabi.make_params((16, 40, 40, 80 * 16), (40, 40), (3, 3), (1, 1), (1, 1), (1, 1), 80, 16, 2.0, dtype)
+        a, b = cabi.launch_plan(p32), cabi.launch_plan(p16)
+        assert a["tiled"] and b["tiled"] and a["scatter"] == b["scatter"]
+        assert a["gather"]["ctas"] == b["gather"]["ctas"] and a["forward"]["ctas"] <= b["forward"]["ctas"]  # (100 KB box)
+        assert a["forward"]["smem"] == a["forward"]["bw"] * a["forward"]["bh"] * 128   # no side slots
+        ws = lambda p: int(cabi.lib.dcnv3_backward_workspace_bytes(ctypes.byref(p)))  # noqa: E731
+        assert ws(p32) >= ws(p16)   # (>=: the generic kernels' workspace is the floor in both)
     # other kernel sizes / strides / channel counts are served by the generic kernels
     p = cabi.make_params((2, 32, 32, 64), (32, 32), (5, 5), (1, 1), (2, 2), (1, 1), 4, 16, 1.0, cabi.F32)
     assert not cabi.launch_plan(p)["tiled"]

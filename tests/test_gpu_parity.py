@@ -111,7 +111,9 @@ CASES = [  # n, h, w, G, gc, sigma, offset_scale
     (2, 16, 16, 32, 16, 1.0, 1.0),
     (1, 49, 97, 4, 16, 4.0, 1.0),      # odd, non-square (sliding-window tile shapes), wide offsets
     (1, 40, 40, 10, 16, 1.0, 2.0),     # InternImage-L style: G=10, offset_scale 2
-    (1, 20, 20, 40, 32, 1.0, 2.0),     # gc = 32
+    (1, 20, 20, 40, 32, 1.0, 2.0),     # gc = 32 (InternImage-H): tiled kernels on half groups
+    (2, 40, 33, 5, 32, 2.0, 1.0),      # gc = 32, odd group count, several tiles per image
+    (1, 70, 64, 10, 32, 4.0, 1.0),     # gc = 32, wide offsets (out-of-box taps, landings beyond the ring)
     (1, 24, 24, 7, 16, 1.0, 1.0),      # odd group count (InternImage-B): trailing half-empty chunk
     (2, 40, 33, 5, 16, 2.0, 1.0),      # InternImage-S stage 1 style (G=5)
     (1, 9, 11, 3, 5, 1.5, 1.0),        # gc not a multiple of 4 -> scalar path
@@ -135,8 +137,8 @@ def test_random_fp32_vs_c_oracle(ops, case):
     assert rel_err(gm, rm) <= TOL_F32
 
 
-@pytest.mark.parametrize("case", CASES[:4] + CASES[5:9] + [(1, 20, 300, 4, 16, 1.0, 1.0), (1, 130, 70, 6, 16, 3.0, 2.0),
-                                                          (1, 20, 20, 80, 16, 1.0, 2.0)])
+@pytest.mark.parametrize("case", CASES[:4] + CASES[5:11] + [(1, 20, 300, 4, 16, 1.0, 1.0), (1, 130, 70, 6, 16, 3.0, 2.0),
+                                                           (1, 20, 20, 80, 16, 1.0, 2.0)])
 def test_random_bf16(ops, case):
     n, h, w, g, gc, sigma, scale = case
     x, off, m, go = make_inputs(n, h, w, g, gc, sigma=sigma, seed=7 + h)
@@ -229,6 +231,12 @@ def test_workspace_stays_zeroed_across_generic_and_tiled(ops):
 
 
 def test_backward_bitwise_reproducible(ops):
+    x, off, m, go = make_inputs(2, 48, 40, 5, 32, sigma=2.0, seed=4)   # 32 channels per group: half groups
+    kw = dict(groups=5, group_channels=32)
+    a = run_op(ops, x, off, m, go, **kw)
+    for _ in range(2):
+        b = run_op(ops, x, off, m, go, **kw)
+        assert all(np.array_equal(p, q) for p, q in zip(a, b))
     x, off, m, go = make_inputs(4, 64, 64, 8, 16, sigma=2.0, seed=3)
     kw = dict(groups=8, group_channels=16)
     a = run_op(ops, x, off, m, go, **kw)
@@ -268,7 +276,7 @@ def test_backward_bitwise_reproducible(ops):
     assert rel_err(c[1], rx) <= TOL_F32
 
 
-@pytest.mark.parametrize("shape,sigma", [((2, 24, 20, 4, 16), 1.0), ((1, 70, 45, 5, 16), 4.0)])
+@pytest.mark.parametrize("shape,sigma", [((2, 24, 20, 4, 16), 1.0), ((1, 70, 45, 5, 16), 4.0), ((2, 40, 36, 3, 32), 2.0)])
 def test_fused_softmax_matches_layer_semantics(ops, shape, sigma):
     """(second case: several scatter tiles, odd group count, landings beyond the ring)"""
     n, h, w, g, gc = shape
@@ -425,6 +433,8 @@ FULL_CASES = [  # dtype, (n, h, w, g, gc), offset_scale -- BASELINE.json configs
     (torch.bfloat16, (4, 160, 160, 10, 16), 2.0),  # config 4: InternImage-L at a 640 crop, stage 1 (4 images) ...
     (torch.bfloat16, (16, 20, 20, 80, 16), 2.0),   # ... and stage 4 (G = 80)
     (torch.bfloat16, (2, 193, 193, 4, 16), 1.0),   # config 5: 769x769 sliding-window tiles, stage 1
+    (torch.bfloat16, (16, 40, 40, 40, 32), 2.0),   # config 4's gc = 32 variant: C1280 / G40 (InternImage-H stage 3 at 640)
+    (torch.float32, (4, 80, 80, 20, 32), 1.0),     # InternImage-H stage 2 shape, fp32
 ]
 
 
@@ -620,7 +630,7 @@ def test_center_scale_blend_fused(ops, shape, dtype, logits, scale):
 
 
 def test_center_scale_blend_unfused_configurations(ops):
-    """32 channels per group (InternImage-H) runs the generic kernels: the blend is then applied around the op
+    """32 channels per group (InternImage-H) runs without the fused blend: it is then applied around the op
     with torch operations, same values; and the C ABI says so instead of computing something else."""
     iseg, cabi = ops
     n, h, w, g, gc = 1, 12, 12, 2, 32
