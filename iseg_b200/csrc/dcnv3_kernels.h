@@ -22,7 +22,7 @@ cudaError_t launch_bwd_generic(const void* x, const void* offset, const void* ma
                                const void* grad_out, void* grad_x, void* grad_offset, void* grad_mask,
                                void* ws, const KParams& q, int dtype, bool ws_clean, cudaStream_t st);
 
-// tiled path (dcnv3_tiled_*.cu): k=3, s=1, d=1, SAME, 16 channels per group
+// tiled path (dcnv3_tiled_*.cu): k=3, s=1, d=1, SAME, 16 channels per group (or 32, run as half groups: tiled_view())
 bool tiled_applicable(const KParams& q, int dtype);
 cudaError_t launch_fwd_tiled(const void* x, const void* offset, const void* mask, void* out,
                              const KParams& q, int dtype, cudaStream_t st);
