@@ -84,6 +84,34 @@ def test_backbone_forward_backward_on_gpu():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_huge_variant_32_channels_per_group(dtype):
+    """InternImage-H wiring in small (intern_image.py:261: 32 channels per group, 5x5 depthwise branch, res-post-norm,
+    level-2 post-norms, centre-feature-scale): forward + backward; its DCNv3 layers run the tiled kernels on half
+    groups (the C ABI's launch plan says so), the blend stays outside the op."""
+    from iseg_b200 import _cabi
+    from iseg_b200.backbones.intern_image.intern_image import InternImage
+    torch.manual_seed(3)
+    m = InternImage(64, [1, 1, 3, 1], [2, 4, 8, 16], 4.0, layer_scale=None, offset_scale=1.0, use_post_norm=False,
+                    depthwise_kernel_size=5, use_res_post_norm=True, use_level2_post_norm=True,
+                    level2_post_norm_block_ids=[1], use_center_feature_scale=True).cuda().to(dtype).eval()
+    for blk in m.blocks:
+        for layer in blk.blocks:
+            assert layer.dcn.filters_per_group == 32
+            torch.nn.init.normal_(layer.dcn.offset.weight, std=0.05)
+            torch.nn.init.normal_(layer.dcn.mask.weight, std=0.05)
+    p = _cabi.make_params((2, 24, 32, 64), (24, 32), (3, 3), (1, 1), (1, 1), (1, 1), 2, 32, 1.0,
+                          _cabi.F32 if dtype == torch.float32 else _cabi.BF16)
+    assert _cabi.launch_plan(p)["tiled"]
+    x = torch.randn(2, 96, 128, 3, device="cuda", dtype=dtype, requires_grad=True)
+    y = m(x)
+    assert y.shape == (2, 3, 4, 512) and torch.isfinite(y.float()).all()
+    y.float().square().mean().backward()
+    assert torch.isfinite(x.grad.float()).all() and x.grad.abs().sum() > 0
+    assert all(torch.isfinite(q.grad.float()).all() for q in m.parameters() if q.grad is not None)
+
+
+@pytest.mark.gpu
 def test_base_variant_odd_groups_bf16():
     m = intern_image_base().cuda().to(torch.bfloat16).eval()
     with torch.no_grad():
