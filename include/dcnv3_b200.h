@@ -72,8 +72,10 @@ typedef enum { DCNV3_F32 = 0, DCNV3_BF16 = 1 } dcnv3_dtype;
 /* bf16 tensors only (ignored for fp32): reproduce the arithmetic the reference performs under the
    mixed_bfloat16 policy -- reference points, grids, sampling locations, pixel coordinates, bilinear weights
    and the forward accumulation all rounded to bfloat16 after every primitive (op.py:62-87, utils.py:130-206).
-   Default (flag clear): coordinates and accumulation in fp32 on the bf16 inputs -- better numerics, but a
-   different result, because bf16 coordinates near 130 have a step of 1 pixel.  Runs the generic kernels. */
+   Default (flag clear): coordinates, weights and accumulation in fp32 on the bf16 inputs (the tiled forward rounds
+   each finished corner weight -- bilinear weight x mask -- once to bf16 for its bf16 x bf16 -> fp32 product) --
+   better numerics, but a different result, because bf16 coordinates near 130 have a step of 1 pixel.
+   The flag runs the generic kernels. */
 #define DCNV3_FLAG_REF_DTYPE 8u
 
 typedef struct dcnv3_params {
