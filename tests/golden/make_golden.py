@@ -44,6 +44,7 @@ OP_CASES = {
     "rect_20x9_g3c8_s2": (1, 20, 9, 3, 8, (3, 3), (1, 1), (1, 1), "SAME", 2.0, 1.5, "f4", 3),
     "far_offsets_12x12_g2c16": (1, 12, 12, 2, 16, (3, 3), (1, 1), (1, 1), "SAME", 1.0, 12.0, "f4", 4),
     "gc32_10x10_g2": (1, 10, 10, 2, 32, (3, 3), (1, 1), (1, 1), "SAME", 1.0, 1.0, "f4", 5),
+    "gc32_33x34_g3": (1, 33, 34, 3, 32, (3, 3), (1, 1), (1, 1), "SAME", 1.0, 3.0, "f4", 13),  # 2 x 2 scatter tiles, odd G
     "valid_11x13_g2c4": (1, 11, 13, 2, 4, (3, 3), (1, 1), (1, 1), "VALID", 1.0, 1.0, "f4", 6),
     "k5_9x9_g2c4": (1, 9, 9, 2, 4, (5, 5), (1, 1), (1, 1), "SAME", 1.0, 1.0, "f4", 7),
     "k3x5_8x10_g1c8": (1, 8, 10, 1, 8, (3, 5), (1, 1), (1, 1), "SAME", 1.0, 1.0, "f4", 8),
