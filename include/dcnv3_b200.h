@@ -127,7 +127,7 @@ int dcnv3_backward(const void* x, const void* offset, const void* mask, const vo
         (center_scale: [n, h, w, groups], dtype of x; no sigmoid, as in the reference).  The backward also returns
         grad_center_scale [n, h, w, groups]; grad_x includes the direct path grad_out * s.
         Available where the shared-memory tiled kernels run (dcnv3_blend_supported() == 1: 3x3, stride 1,
-        dilation 1, SAME, 16 channels per group -- what InternImage-T/S/B/L instantiate); DCNV3_ERR_ARGUMENT
+        dilation 1, SAME, 16 or 32 channels per group -- what InternImage-T/S/B/L and -H instantiate); DCNV3_ERR_ARGUMENT
         otherwise, and the caller applies the blend itself around dcnv3_forward / dcnv3_backward. ---- */
 int dcnv3_blend_supported(const dcnv3_params* p);
 int dcnv3_forward_blend(const void* x, const void* offset, const void* mask, const void* center_scale, void* out,

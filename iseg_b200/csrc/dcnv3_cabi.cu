@@ -100,8 +100,8 @@ static int check_ptr_align(const void* ptr, const char* name, size_t align = 16)
 
 // is the centre-feature-scale blend available for these parameters?  (fused into the tiled kernels only)
 static bool blend_supported(const dcnv3_params* p) {
-    const KParams q = derive(p);  // (32 channels per group run the tiled kernels as half groups, without the blend)
-    return p->group_channels == 16 && tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC) && !ref_dtype_mode(p);
+    const KParams q = derive(p);
+    return tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC) && !ref_dtype_mode(p);
 }
 
 static int forward_impl(const void* x, const void* offset, const void* mask, void* out,
@@ -117,7 +117,7 @@ static int forward_impl(const void* x, const void* offset, const void* mask, voi
         if ((rc = check_ptr_align(cfs, "center_scale", 4))) return rc;
         if (!blend_supported(p))
             return fail(DCNV3_ERR_ARGUMENT, "the fused centre-feature-scale blend needs the tiled configuration "
-                                            "(3x3, stride 1, dilation 1, SAME, 16 channels per group); see dcnv3_blend_supported");
+                                            "(3x3, stride 1, dilation 1, SAME, 16 or 32 channels per group); see dcnv3_blend_supported");
         q.cfs = cfs;
     }
     const bool tiled = tiled_applicable(q, p->dtype) && !(p->flags & DCNV3_FLAG_FORCE_GENERIC) && !ref_dtype_mode(p);
@@ -193,7 +193,7 @@ static int backward_impl(const void* x, const void* offset, const void* mask, co
         if ((rc = check_ptr_align(cfs, "center_scale", 4)) || (rc = check_ptr_align(grad_cfs, "grad_center_scale", 4))) return rc;
         if (!blend_supported(p))
             return fail(DCNV3_ERR_ARGUMENT, "the fused centre-feature-scale blend needs the tiled configuration "
-                                            "(3x3, stride 1, dilation 1, SAME, 16 channels per group); see dcnv3_blend_supported");
+                                            "(3x3, stride 1, dilation 1, SAME, 16 or 32 channels per group); see dcnv3_blend_supported");
         q.cfs = cfs;
         q.grad_cfs = grad_cfs;
     }

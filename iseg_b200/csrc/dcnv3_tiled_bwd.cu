@@ -510,8 +510,13 @@ bwd_gather_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
 #pragma unroll
                     for (int j = 0; j < C::PAIRS; ++j) ffma2v(dx2, xo[j], go_pair(pc * C::PAIRS + j));
                 }
-                if (px_l < npx && chunk * C::GQ + g_l < q.G)
-                    Elem<T>::st(reinterpret_cast<T*>(q.grad_cfs) + pg, lo_of(dx2) + hi_of(dx2) - gm_dot_m);
+                float dxs = lo_of(dx2) + hi_of(dx2);
+                bool writer = px_l < npx && chunk * C::GQ + g_l < q.G;
+                if (!STAGED && q.gsh) {  // half groups: <grad_out, x_proj> over both halves, stored once
+                    dxs += __shfl_xor_sync(0xffffffffu, dxs, 1);
+                    writer = writer && (g_l & 1) == 0;
+                }
+                if (writer) Elem<T>::st(reinterpret_cast<T*>(q.grad_cfs) + ps, dxs - gm_dot_m);
             }
             if (logits) {
                 // softmax Jacobian needs sum_p m_p*dL/dm_p: second sweep over this lane's own 9 values.  The logits
@@ -670,7 +675,7 @@ __device__ __forceinline__ void redo_walk(int* wsum, const T* __restrict__ offse
                 if (!((unsigned)cx < (unsigned)box.bw && (unsigned)cy < (unsigned)box.bh)) continue;
                 if (!(ax >= 0 && ax < q.w && ay >= 0 && ay < q.h) || !cell_is_hot<WP>(wsum, cy, cx, g_l)) continue;
                 if (!have_g) {
-                    const float oms = q.cfs != nullptr ? __fsub_rn(1.0f, Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + pg)) : 1.0f;
+                    const float oms = q.cfs != nullptr ? __fsub_rn(1.0f, Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + ps)) : 1.0f;
                     load_fixed_point_go<T>(grad_out + pg * kGC, oms, sg, px_l, G);
                     have_g = true;
                 }
@@ -744,7 +749,7 @@ __device__ __forceinline__ void scatter_walk_per_tap(int* acc, int* wsum, const 
         if (logits) softmax_stats9<T>(mskp, mx, inv_sum);
         float ref0, ref1;
         ref_point(q, h, w, ref0, ref1);
-        const float oms = BLEND ? __fsub_rn(1.0f, Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + pg)) : 1.0f;
+        const float oms = BLEND ? __fsub_rn(1.0f, Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + ps)) : 1.0f;
         if (MODE == 0) {  // every tap of a home pixel lands: convert grad_out once, with the whole warp converged
             fixed_point_go(gf, oms, sg, px_l, G);
             have_g = true;
@@ -1157,7 +1162,7 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
                     const int e = ax * (q.G * kGC) + piece * 4;
                     float f0 = (float)v.x * inv_s, f1 = (float)v.y * inv_s, f2_ = (float)v.z * inv_s, f3 = (float)v.w * inv_s;
                     if (blend) {  // the blend's direct path: d x_proj += grad_out * s at the pixel itself
-                        const float cs = Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + (grow * q.w + ax) * q.G + g);
+                        const float cs = Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + (PER_TAP ? side_entry(q, grow * q.w + ax, g) : (grow * q.w + ax) * q.G + g));
                         const float4 g4 = Elem<T>::ld4(grad_out + grow * row_elems + chunk * kSCell + e);
                         f0 = __fadd_rn(f0, __fmul_rn(g4.x, cs)); f1 = __fadd_rn(f1, __fmul_rn(g4.y, cs));
                         f2_ = __fadd_rn(f2_, __fmul_rn(g4.z, cs)); f3 = __fadd_rn(f3, __fmul_rn(g4.w, cs));
@@ -1202,7 +1207,7 @@ bwd_scatter_kernel(const T* __restrict__ offset, const T* __restrict__ mask, con
             float f0 = drop ? fill : (float)v.x * inv_s, f1 = drop ? fill : (float)v.y * inv_s;
             float f2_ = drop ? fill : (float)v.z * inv_s, f3 = drop ? fill : (float)v.w * inv_s;
             if (blend) {  // the blend's direct path (hot cells: the redo / merge kernels add to this)
-                const float cs = Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + gpix * q.G + g);
+                const float cs = Elem<T>::ld(reinterpret_cast<const T*>(q.cfs) + (PER_TAP ? side_entry(q, gpix, g) : gpix * q.G + g));
                 const float4 g4 = Elem<T>::ld4(grad_out + gidx);
                 f0 = __fadd_rn(f0, __fmul_rn(g4.x, cs)); f1 = __fadd_rn(f1, __fmul_rn(g4.y, cs));
                 f2_ = __fadd_rn(f2_, __fmul_rn(g4.z, cs)); f3 = __fadd_rn(f3, __fmul_rn(g4.w, cs));

@@ -598,6 +598,8 @@ def _blend_reference(x, off, m, cs, go, g, gc, offset_scale=1.0, logits=False):
     ((3, 17, 23, 3, 16), torch.float32, True, 1.0),      # single tile, odd group count (phantom group), fused soft-max
     ((2, 64, 48, 8, 16), torch.bfloat16, False, 1.0),
     ((1, 48, 40, 10, 16), torch.float32, False, 2.0),    # offset_scale 2: narrow ring, the per-tap scatter walk
+    ((2, 40, 36, 3, 32), torch.float32, True, 1.0),      # 32 channels per group (InternImage-H): half groups, fused soft-max
+    ((2, 24, 40, 5, 32), torch.bfloat16, False, 1.0),    # ... bf16, odd group count (phantom half groups)
 ])
 def test_center_scale_blend_fused(ops, shape, dtype, logits, scale):
     iseg, cabi = ops
@@ -630,10 +632,10 @@ def test_center_scale_blend_fused(ops, shape, dtype, logits, scale):
 
 
 def test_center_scale_blend_unfused_configurations(ops):
-    """32 channels per group (InternImage-H) runs without the fused blend: it is then applied around the op
-    with torch operations, same values; and the C ABI says so instead of computing something else."""
+    """Where the tiled kernels do not run (here 8 channels per group) there is no fused blend: it is then applied
+    around the op with torch operations, same values; and the C ABI says so instead of computing something else."""
     iseg, cabi = ops
-    n, h, w, g, gc = 1, 12, 12, 2, 32
+    n, h, w, g, gc = 1, 12, 12, 2, 8
     x, off, m, go = make_inputs(n, h, w, g, gc, seed=8)
     cs = np.random.default_rng(2).uniform(0, 1, size=(n, h, w, g)).astype(np.float32)
     tx, to, tm, ts = cuda(x, off, m, cs)

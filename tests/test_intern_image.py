@@ -88,7 +88,7 @@ def test_backbone_forward_backward_on_gpu():
 def test_huge_variant_32_channels_per_group(dtype):
     """InternImage-H wiring in small (intern_image.py:261: 32 channels per group, 5x5 depthwise branch, res-post-norm,
     level-2 post-norms, centre-feature-scale): forward + backward; its DCNv3 layers run the tiled kernels on half
-    groups (the C ABI's launch plan says so), the blend stays outside the op."""
+    groups (the C ABI's launch plan says so), centre-feature-scale blend included."""
     from iseg_b200 import _cabi
     from iseg_b200.backbones.intern_image.intern_image import InternImage
     torch.manual_seed(3)
