@@ -201,6 +201,21 @@ __device__ __forceinline__ Tap make_tap_refdtype(const KParams& q, int h, int w,
     return t;
 }
 
+// acc += bf16(half HV of v) * bf16(half HW of w), fp32 accumulator: PTX fma.rn.f32.bf16 (sm_100+), SASS FHFMA.BF16.
+// The product of two bf16 values is exact in fp32, so packed bf16 pairs need no shift / mask to fp32 first.
+// HV / HW = 0 / 1 pick the low / high half of v and of w
+template <int HV, int HW>
+__device__ __forceinline__ void fhfma_x(float& acc, unsigned v, unsigned w) {
+    if (HV == 0 && HW == 0)
+        asm("{\n.reg .b16 a, b, c, d;\nmov.b32 {a, b}, %1;\nmov.b32 {c, d}, %2;\nfma.rn.f32.bf16 %0, a, c, %0;\n}" : "+f"(acc) : "r"(v), "r"(w));
+    else if (HV == 1 && HW == 0)
+        asm("{\n.reg .b16 a, b, c, d;\nmov.b32 {a, b}, %1;\nmov.b32 {c, d}, %2;\nfma.rn.f32.bf16 %0, b, c, %0;\n}" : "+f"(acc) : "r"(v), "r"(w));
+    else if (HV == 0 && HW == 1)
+        asm("{\n.reg .b16 a, b, c, d;\nmov.b32 {a, b}, %1;\nmov.b32 {c, d}, %2;\nfma.rn.f32.bf16 %0, a, d, %0;\n}" : "+f"(acc) : "r"(v), "r"(w));
+    else
+        asm("{\n.reg .b16 a, b, c, d;\nmov.b32 {a, b}, %1;\nmov.b32 {c, d}, %2;\nfma.rn.f32.bf16 %0, b, d, %0;\n}" : "+f"(acc) : "r"(v), "r"(w));
+}
+
 // ---- element access -----------------------------------------------------------------------------
 template <typename T>
 struct Elem;

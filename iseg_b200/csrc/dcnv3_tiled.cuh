@@ -263,18 +263,6 @@ struct Slab<__nv_bfloat16> {
 #ifndef DCNV3_BF16_FWD_W
 #define DCNV3_BF16_FWD_W 1
 #endif
-// HV / HW = 0 / 1 pick the low / high half of v and of w
-template <int HV, int HW>
-__device__ __forceinline__ void fhfma_x(float& acc, unsigned v, unsigned w) {
-    if (HV == 0 && HW == 0)
-        asm("{\n.reg .b16 a, b, c, d;\nmov.b32 {a, b}, %1;\nmov.b32 {c, d}, %2;\nfma.rn.f32.bf16 %0, a, c, %0;\n}" : "+f"(acc) : "r"(v), "r"(w));
-    else if (HV == 1 && HW == 0)
-        asm("{\n.reg .b16 a, b, c, d;\nmov.b32 {a, b}, %1;\nmov.b32 {c, d}, %2;\nfma.rn.f32.bf16 %0, b, c, %0;\n}" : "+f"(acc) : "r"(v), "r"(w));
-    else if (HV == 0 && HW == 1)
-        asm("{\n.reg .b16 a, b, c, d;\nmov.b32 {a, b}, %1;\nmov.b32 {c, d}, %2;\nfma.rn.f32.bf16 %0, a, d, %0;\n}" : "+f"(acc) : "r"(v), "r"(w));
-    else
-        asm("{\n.reg .b16 a, b, c, d;\nmov.b32 {a, b}, %1;\nmov.b32 {c, d}, %2;\nfma.rn.f32.bf16 %0, b, d, %0;\n}" : "+f"(acc) : "r"(v), "r"(w));
-}
 
 // global 16-byte piece <-> packed pairs (PAIRS = 2 for fp32, 4 for bf16)
 template <typename T>

@@ -276,8 +276,13 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 dwconv3_ln_act_reg_kernel(const T* __restrict__ x, const T* __restrict__ wt, const T* __restrict__ bias,
                           const T* __restrict__ lw, const T* __restrict__ lb, T* __restrict__ out, int N, int H, int W, int C,
                           int pad_lo, float eps, int act, int PW) {
-    extern __shared__ float swt[];   // [9][C]
-    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) swt[i] = Elem<T>::ld(wt + i);
+    extern __shared__ float swt[];   // [9][C]: fp32, or (bf16) the packed values themselves
+    constexpr bool PACKED = sizeof(T) == 2;  // bf16 x bf16 straight into FHFMA.BF16: no unpacking of either operand
+    if constexpr (PACKED) {
+        for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) reinterpret_cast<T*>(swt)[i] = wt[i];
+    } else {
+        for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) swt[i] = Elem<T>::ld(wt + i);
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     bool on[QPL];
@@ -311,16 +316,30 @@ dwconv3_ln_act_reg_kernel(const T* __restrict__ x, const T* __restrict__ wt, con
 #pragma unroll
         for (int i = 0; i < QPL; ++i) {
             const int c = (lane + 32 * i) * 4;
-            float4 v[9];
+            if constexpr (PACKED) {
+                uint2 v[9];
 #pragma unroll
-            for (int t = 0; t < 9; ++t)   // the nine loads of a piece first, then its arithmetic
-                v[t] = (in[t] && on[i]) ? Elem<T>::ld4(x + base[t] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            acc[i] = param(bias, i, 0.f);
+                for (int t = 0; t < 9; ++t)   // the nine loads of a piece first, then its arithmetic
+                    v[t] = (in[t] && on[i]) ? __ldg(reinterpret_cast<const uint2*>(x + base[t] + c)) : make_uint2(0u, 0u);
+                acc[i] = param(bias, i, 0.f);
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const float4 k4 = on[i] ? *reinterpret_cast<const float4*>(swt + t * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                acc[i].x = fmaf(v[t].x, k4.x, acc[i].x); acc[i].y = fmaf(v[t].y, k4.y, acc[i].y);
-                acc[i].z = fmaf(v[t].z, k4.z, acc[i].z); acc[i].w = fmaf(v[t].w, k4.w, acc[i].w);
+                for (int t = 0; t < 9; ++t) {   // (the same products and the same order as the fp32 form below: exact either way)
+                    const uint2 k2 = on[i] ? *reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(swt) + t * C + c) : make_uint2(0u, 0u);
+                    fhfma_x<0, 0>(acc[i].x, v[t].x, k2.x); fhfma_x<1, 1>(acc[i].y, v[t].x, k2.x);
+                    fhfma_x<0, 0>(acc[i].z, v[t].y, k2.y); fhfma_x<1, 1>(acc[i].w, v[t].y, k2.y);
+                }
+            } else {
+                float4 v[9];
+#pragma unroll
+                for (int t = 0; t < 9; ++t)   // the nine loads of a piece first, then its arithmetic
+                    v[t] = (in[t] && on[i]) ? Elem<T>::ld4(x + base[t] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                acc[i] = param(bias, i, 0.f);
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const float4 k4 = on[i] ? *reinterpret_cast<const float4*>(swt + t * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    acc[i].x = fmaf(v[t].x, k4.x, acc[i].x); acc[i].y = fmaf(v[t].y, k4.y, acc[i].y);
+                    acc[i].z = fmaf(v[t].z, k4.z, acc[i].z); acc[i].w = fmaf(v[t].w, k4.w, acc[i].w);
+                }
             }
             // (the unfused chain stores the convolution result in T before normalising it)
             acc[i] = make_float4(round_to<T>(acc[i].x), round_to<T>(acc[i].y), round_to<T>(acc[i].z), round_to<T>(acc[i].w));
