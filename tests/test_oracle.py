@@ -118,6 +118,26 @@ def test_c_vs_numpy_medium():
         assert rel_err(a, b) < 2e-6
 
 
+def test_half_group_identity():
+    """What the tiled kernels rely on for 32 channels per group (KParams::gsh): a group of 32 channels is two groups of
+    16 that share its offsets and mask -- same output and grad_x bit for bit, grad_offset / grad_mask = the sums over
+    the two halves (here on the op_gc32 fixture of the reference's own run)."""
+    z, _ = load_op_case("gc32_33x34_g3")
+    x, off, m, go = z["x"], z["offset"], z["mask"], z["grad_out"]
+    n, h, w, _ = x.shape
+    g = 3
+    dup = lambda a, per: np.repeat(a.reshape(n, h, w, g, per), 2, axis=3).reshape(n, h, w, 2 * g * per)  # noqa: E731
+    kw32 = dict(groups=g, group_channels=32, offset_scale=float(z["offset_scale"]))
+    kw16 = dict(groups=2 * g, group_channels=16, offset_scale=float(z["offset_scale"]))
+    out32, out16 = c_oracle.forward(x, off, m, **kw32), c_oracle.forward(x, dup(off, 18), dup(m, 9), **kw16)
+    assert np.array_equal(out32, out16) and rel_err(out32, z["out"]) == 0.0
+    gx32, goff32, gm32 = c_oracle.backward(x, off, m, go, **kw32)
+    gx16, goff16, gm16 = c_oracle.backward(x, dup(off, 18), dup(m, 9), go, **kw16)
+    assert np.array_equal(gx32, gx16)
+    halves = lambda a, per: a.reshape(n, h, w, g, 2, per).sum(4).reshape(n, h, w, g * per)  # noqa: E731
+    assert rel_err(halves(goff16, 18), goff32) <= 1e-6 and rel_err(halves(gm16, 9), gm32) <= 1e-6
+
+
 def test_softmax_matches_layer_semantics():
     rng = np.random.default_rng(0)
     z = rng.standard_normal((2, 3, 3, 4 * 9)).astype(np.float32)
