@@ -14,7 +14,7 @@ bash tools/gpu_prof.sh ${tag}_s1_f32 128 128 64 4 f32
 bash tools/gpu_prof.sh ${tag}_s3_f32 32 32 256 16 f32
 bash tools/gpu_prof.sh ${tag}_s1_bf16 128 128 64 4 bf16
 bash tools/gpu_prof.sh ${tag}_s3_bf16 32 32 256 16 bf16
-python tools/config_bench.py cfg3 cfg4 cfg5 > gpurun_out/${tag}_config_bench.jsonl 2>/dev/null; echo "config rc=$?"
+python tools/config_bench.py cfg3 cfg4 cfg5 siblings > gpurun_out/${tag}_config_bench.jsonl 2>/dev/null; echo "config rc=$?"
 python - <<PY
 import json
 d = json.loads(open("gpurun_out/${tag}_bench.json").read().strip().splitlines()[-1])
